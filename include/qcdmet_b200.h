@@ -1,0 +1,150 @@
+/* qcdmet_b200.h -- C ABI of libqcdmet_b200.so (sm_100a).
+ *
+ * Drop-in boundary for QC-DMET's RHF 1-RDM linear response hot path.  The reference binds
+ * its native library with ctypes (src/qcdmethelper.py:23-24) and calls exactly one symbol,
+ *     extern "C" void rhf_response(...)                       lib/rhf_response.cc:31-32
+ * from qcdmethelper.construct1RDM_response (src/qcdmethelper.py:102-109); the Jacobian of
+ * the umat fit is then assembled in Python from the N x N x P response
+ * (dmet.rdm_differences_derivative, src/dmet.py:477-525).
+ *
+ * This library exports
+ *   (1) rhf_response           -- same symbol, same arguments, same semantics (compat);
+ *   (2) qcdmet_jacobian*       -- the fused path: fragment blocks of dD_p written directly
+ *                                 as Jacobian columns, replacing lib/rhf_response.cc:73-112
+ *                                 + src/dmet.py:496-520 in one call;
+ *   (3) qcdmet_plan_*          -- the same path with device-resident state (used by the
+ *                                 Python mirror of qcdmethelper/dmet and by bench.py).
+ *
+ * Plain pointers and sizes only.  All entry points return 0 on success, a negative
+ * QCDMET_E_* code otherwise; qcdmet_last_error() gives the message.  There is no CPU
+ * fallback: without a CUDA device every compute entry point fails with QCDMET_E_CUDA.
+ *
+ * Array contracts (identical to the reference's, src/qcdmethelper.py:62-64,97,100):
+ *   H1start[Nterms+1] monotone, H1start[0] = 0; H1row/H1col 0-based site indices < Norb,
+ *   int32; every stored element has value 1.  H0: symmetric Norb x Norb float64.
+ */
+#ifndef QCDMET_B200_H
+#define QCDMET_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QCDMET_OK          0
+#define QCDMET_E_ARG      -1   /* invalid argument                                   */
+#define QCDMET_E_CUDA     -2   /* CUDA runtime / no device                           */
+#define QCDMET_E_SOLVER   -3   /* cuSOLVER syevd failed (info != 0)                  */
+#define QCDMET_E_ALLOC    -4   /* device or host allocation failed                   */
+#define QCDMET_E_STATE    -5   /* plan used before orbitals / Jacobian are available */
+#define QCDMET_E_GAP      -6   /* e[numPairs] - e[numPairs-1] <= 0: response diverges */
+
+/* Kernel selection for qcdmet_plan_set_kernel(). */
+#define QCDMET_KERNEL_AUTO     0   /* DMMA site-factorised kernel when eligible, else general */
+#define QCDMET_KERNEL_GENERAL  1   /* plain FP64 general kernel (any CSR, any rows)           */
+#define QCDMET_KERNEL_DMMA     2   /* force the DMMA kernel (error if not eligible)           */
+
+/* ---------------------------------------------------------------------------------------
+ * (1) Compat symbol.  Replaces lib/rhf_response.cc:32-119 one to one:
+ *     diagonalises H0 (cuSOLVER syevd instead of dsyev, :42-52), overwrites H0 with the
+ *     1-RDM 2*C_o*C_o^T (:57-64), and fills rdm_deriv[row + Norb*(col + Norb*deriv)] with
+ *     dD_deriv (:104-108).  The reference returns void; an int status is ABI-compatible with
+ *     its ctypes call site (src/qcdmethelper.py:102), which ignores the return value.
+ *     Unlike the reference, indices are 64-bit: Norb^2*Nterms >= 2^31 is legal.
+ * ------------------------------------------------------------------------------------- */
+int rhf_response(const int Norb, const int Nterms, const int numPairs,
+                 int *H1start, int *H1row, int *H1col, double *H0, double *rdm_deriv);
+
+/* ---------------------------------------------------------------------------------------
+ * (2) Fused Jacobian, host buffers in / host buffers out.
+ *     Replaces the pair  helper.construct1RDM_response (src/qcdmethelper.py:84-112)  +
+ *     the assembly loop of dmet.rdm_differences_derivative (src/dmet.py:484-520).
+ *
+ *     Fragments: Nfrag blocks of residual rows, fragment f owning rows
+ *     rowStart[f] .. rowStart[f+1]-1 (S = rowStart[Nfrag] rows in total).
+ *       R != NULL : dense projector rows, row-major S x Norb; the rows of fragment f are
+ *                   dmetOrbs[f]^T (fitImpBath == True, src/dmet.py:502)
+ *       R == NULL : rowIdx[S] site index per row = flatnonzero(impClust[f]) concatenated
+ *                   (fitImpBath == False, src/dmet.py:509)
+ *     Output: J[q + Q*(p - colBegin)], Q = sum_f r_f^2, p in [colBegin, colEnd); inside
+ *     fragment f the r_f x r_f block of dD_p is stored column-major (reshape order='F',
+ *     src/dmet.py:515-517).  This is exactly the memory of the (Q, P) array the reference
+ *     returns (np.array(list).T, src/dmet.py:520).
+ *     D_blocks (optional, may be NULL): Q doubles, the same blocks of the mean-field 1-RDM
+ *     2*C_o*C_o^T (the model part of dmet.rdm_differences, src/dmet.py:416-421).
+ *     eig_out (optional): Norb eigenvalues, ascending.
+ * ------------------------------------------------------------------------------------- */
+int qcdmet_jacobian(int Norb, int Nterms, int numPairs,
+                    const int *H1start, const int *H1row, const int *H1col,
+                    const double *H0,
+                    int Nfrag, const int *rowStart, const double *R, const int *rowIdx,
+                    int colBegin, int colEnd,
+                    double *J, double *D_blocks, double *eig_out);
+
+/* Test-only variant: orbitals given instead of H0 (no eigensolve), so that the kernels
+ * can be compared against the oracle on bit-identical (C, e).
+ * C: column-major Norb x Norb, eigenvector k in column k (LAPACK layout), e ascending. */
+int qcdmet_jacobian_from_orbitals(int Norb, int Nterms, int numPairs,
+                    const int *H1start, const int *H1row, const int *H1col,
+                    const double *C, const double *e,
+                    int Nfrag, const int *rowStart, const double *R, const int *rowIdx,
+                    int colBegin, int colEnd,
+                    double *J, double *D_blocks);
+
+/* ---------------------------------------------------------------------------------------
+ * (3) Plans: perturbation list + fragment rows live on the device across calls
+ *     (the reference freezes list_H1 at dmet.__init__, src/dmet.py:86).
+ * ------------------------------------------------------------------------------------- */
+typedef struct qcdmet_plan qcdmet_plan;
+
+/* device < 0: use the current CUDA device.  Copies all index arrays and R to the device. */
+int qcdmet_plan_create(qcdmet_plan **plan, int device, int Norb, int Nterms, int numPairs,
+                       const int *H1start, const int *H1row, const int *H1col,
+                       int Nfrag, const int *rowStart, const double *R, const int *rowIdx);
+int qcdmet_plan_destroy(qcdmet_plan *plan);
+
+/* Restrict the plan to Jacobian columns [colBegin, colEnd) (multi-GPU column sharding). */
+int qcdmet_plan_set_columns(qcdmet_plan *plan, int colBegin, int colEnd);
+/* QCDMET_KERNEL_*; default AUTO. */
+int qcdmet_plan_set_kernel(qcdmet_plan *plan, int kernel);
+/* CUDA stream (cudaStream_t) every launch of this plan goes to; NULL = legacy default stream. */
+int qcdmet_plan_set_stream(qcdmet_plan *plan, void *stream);
+
+/* Upload H0 (host), run cuSOLVER syevd on the device, build the operand panels. */
+int qcdmet_plan_set_h0(qcdmet_plan *plan, const double *H0);
+/* Upload orbitals (host; layout as in qcdmet_jacobian_from_orbitals), build the panels. */
+int qcdmet_plan_set_orbitals(qcdmet_plan *plan, const double *C, const double *e);
+
+/* Launch the Jacobian kernels for the plan's column range (asynchronous on the plan stream;
+ * inputs and output stay in HBM). */
+int qcdmet_plan_compute(qcdmet_plan *plan);
+/* Synchronise the plan stream; returns the first asynchronous error, if any. */
+int qcdmet_plan_sync(qcdmet_plan *plan);
+
+/* Device pointer of the column slice J[Q x (colEnd-colBegin)], column-major (for NCCL). */
+void *qcdmet_plan_jacobian_device(qcdmet_plan *plan);
+/* Blocking device->host copies. */
+int qcdmet_plan_get_jacobian(qcdmet_plan *plan, double *J);
+int qcdmet_plan_get_dblocks(qcdmet_plan *plan, double *D_blocks);
+int qcdmet_plan_get_eigenvalues(qcdmet_plan *plan, double *e);
+int qcdmet_plan_get_orbitals(qcdmet_plan *plan, double *C);
+/* Full response written like the compat symbol (small problems): rdm_deriv[N*N*ncols], and
+ * the 1-RDM (N*N) if one_rdm != NULL. */
+int qcdmet_plan_get_full_response(qcdmet_plan *plan, double *rdm_deriv, double *one_rdm);
+
+/* Introspection (bench / tests). */
+long long qcdmet_plan_num_residuals(qcdmet_plan *plan);    /* Q                                  */
+int  qcdmet_plan_kernel_used(qcdmet_plan *plan);           /* QCDMET_KERNEL_GENERAL or _DMMA      */
+int  qcdmet_plan_launches(qcdmet_plan *plan);              /* kernels launched by the last compute */
+double qcdmet_plan_flops(qcdmet_plan *plan);               /* FP64 flops executed by the last compute */
+/* Device time of the dominant kernel of the last compute (CUDA events recorded on the plan
+ * stream around that launch; synchronises the stream).  ms < 0 if nothing was computed. */
+int  qcdmet_plan_kernel_time_ms(qcdmet_plan *plan, double *ms);
+
+const char *qcdmet_last_error(void);
+const char *qcdmet_version(void);
+int qcdmet_device_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QCDMET_B200_H */

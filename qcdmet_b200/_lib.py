@@ -1,0 +1,206 @@
+"""ctypes binding of libqcdmet_b200.so (include/qcdmet_b200.h).
+
+Same mechanism the reference uses for libqcdmet (src/qcdmethelper.py:23-24: ctypes.CDLL, which
+releases the GIL for the duration of every call).  The library path is $QCDMET_B200_LIB, else
+the in-tree build next to this file.  There is NO fallback: a missing library or a missing
+CUDA device raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.environ.get("QCDMET_B200_LIB", os.path.join(_HERE, "libqcdmet_b200.so"))
+
+KERNEL_AUTO, KERNEL_GENERAL, KERNEL_DMMA = 0, 1, 2
+
+c_int_p = ctypes.POINTER(ctypes.c_int)
+c_double_p = ctypes.POINTER(ctypes.c_double)
+
+# name -> (restype, argtypes); mirrors include/qcdmet_b200.h one to one
+SIGNATURES = {
+    "rhf_response": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
+                                    ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "qcdmet_jacobian": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
+                                       ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
+                                       ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
+                                       ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "qcdmet_jacobian_from_orbitals": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                                     ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                                     ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
+                                                     ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                                     ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
+                                                     ctypes.c_void_p]),
+    "qcdmet_plan_create": (ctypes.c_int, [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, ctypes.c_int,
+                                          ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
+                                          ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
+                                          ctypes.c_void_p]),
+    "qcdmet_plan_destroy": (ctypes.c_int, [ctypes.c_void_p]),
+    "qcdmet_plan_set_columns": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]),
+    "qcdmet_plan_set_kernel": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
+    "qcdmet_plan_set_stream": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
+    "qcdmet_plan_set_h0": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
+    "qcdmet_plan_set_orbitals": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "qcdmet_plan_compute": (ctypes.c_int, [ctypes.c_void_p]),
+    "qcdmet_plan_sync": (ctypes.c_int, [ctypes.c_void_p]),
+    "qcdmet_plan_jacobian_device": (ctypes.c_void_p, [ctypes.c_void_p]),
+    "qcdmet_plan_get_jacobian": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
+    "qcdmet_plan_get_dblocks": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
+    "qcdmet_plan_get_eigenvalues": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
+    "qcdmet_plan_get_orbitals": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
+    "qcdmet_plan_get_full_response": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "qcdmet_plan_num_residuals": (ctypes.c_longlong, [ctypes.c_void_p]),
+    "qcdmet_plan_kernel_used": (ctypes.c_int, [ctypes.c_void_p]),
+    "qcdmet_plan_launches": (ctypes.c_int, [ctypes.c_void_p]),
+    "qcdmet_plan_flops": (ctypes.c_double, [ctypes.c_void_p]),
+    "qcdmet_plan_kernel_time_ms": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
+    "qcdmet_last_error": (ctypes.c_char_p, []),
+    "qcdmet_version": (ctypes.c_char_p, []),
+    "qcdmet_device_count": (ctypes.c_int, []),
+}
+
+_lib = None
+
+
+class QcdmetError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__(f"libqcdmet_b200 error {code}: {message}")
+        self.code = code
+
+
+def load():
+    """Load the shared library (once).  Raises OSError if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise OSError(f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; "
+                      f"g.build()'` or `make -C qcdmet_b200/csrc` (there is no CPU fallback)")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (restype, argtypes) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = restype
+        fn.argtypes = argtypes
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc != 0:
+        raise QcdmetError(rc, load().qcdmet_last_error().decode())
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+def as_i32(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.int32)
+
+
+def as_f64(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.float64)
+
+
+class Plan:
+    """Thin RAII wrapper over qcdmet_plan_* (device-resident perturbation list + fragment rows)."""
+
+    def __init__(self, norb, num_pairs, h1start, h1row, h1col, row_start, rows=None, row_idx=None,
+                 device=-1):
+        self.lib = load()
+        self.norb, self.num_pairs = int(norb), int(num_pairs)
+        self._keep = [as_i32(h1start), as_i32(h1row), as_i32(h1col), as_i32(row_start), as_f64(rows),
+                      as_i32(row_idx)]
+        hs, hr, hc, rs, r, ri = self._keep
+        self.nterms = len(hs) - 1
+        self.nfrag = len(rs) - 1
+        if hr.size == 0:
+            hr = hc = np.zeros(1, dtype=np.int32)
+        self.handle = ctypes.c_void_p()
+        check(self.lib.qcdmet_plan_create(ctypes.byref(self.handle), device, self.norb, self.nterms,
+                                          self.num_pairs, _ptr(hs), _ptr(hr), _ptr(hc), self.nfrag,
+                                          _ptr(rs), _ptr(r), _ptr(ri)))
+        self.nresid = int(self.lib.qcdmet_plan_num_residuals(self.handle))
+        self.col_begin, self.col_end = 0, self.nterms
+
+    def close(self):
+        if getattr(self, "handle", None) is not None and self.handle.value:
+            self.lib.qcdmet_plan_destroy(self.handle)
+            self.handle = ctypes.c_void_p()
+
+    __del__ = close
+
+    def set_columns(self, begin, end):
+        check(self.lib.qcdmet_plan_set_columns(self.handle, int(begin), int(end)))
+        self.col_begin, self.col_end = int(begin), int(end)
+
+    def set_kernel(self, kernel):
+        check(self.lib.qcdmet_plan_set_kernel(self.handle, int(kernel)))
+
+    def set_stream(self, stream_ptr):
+        check(self.lib.qcdmet_plan_set_stream(self.handle, ctypes.c_void_p(stream_ptr)))
+
+    def set_h0(self, h0):
+        h0 = as_f64(h0)
+        assert h0.size == self.norb * self.norb
+        check(self.lib.qcdmet_plan_set_h0(self.handle, _ptr(h0)))
+
+    def set_orbitals(self, c, e):
+        """c: (N, N) with eigenvector k in column k (numpy convention); e ascending."""
+        c_colmajor = np.asfortranarray(np.asarray(c, dtype=np.float64))
+        e = as_f64(e)
+        check(self.lib.qcdmet_plan_set_orbitals(self.handle, c_colmajor.ctypes.data_as(ctypes.c_void_p),
+                                                _ptr(e)))
+
+    def compute(self):
+        check(self.lib.qcdmet_plan_compute(self.handle))
+
+    def sync(self):
+        check(self.lib.qcdmet_plan_sync(self.handle))
+
+    def jacobian(self, out=None):
+        """(Q, ncols) float64, Fortran order: the memory of the reference's returned array."""
+        ncols = self.col_end - self.col_begin
+        if out is None:
+            out = np.empty((self.nresid, ncols), dtype=np.float64, order="F")
+        assert out.flags.f_contiguous and out.shape == (self.nresid, ncols)
+        check(self.lib.qcdmet_plan_get_jacobian(self.handle, _ptr(out)))
+        return out
+
+    def dblocks(self):
+        out = np.empty(self.nresid, dtype=np.float64)
+        check(self.lib.qcdmet_plan_get_dblocks(self.handle, _ptr(out)))
+        return out
+
+    def eigenvalues(self):
+        out = np.empty(self.norb, dtype=np.float64)
+        check(self.lib.qcdmet_plan_get_eigenvalues(self.handle, _ptr(out)))
+        return out
+
+    def orbitals(self):
+        out = np.empty((self.norb, self.norb), dtype=np.float64, order="F")
+        check(self.lib.qcdmet_plan_get_orbitals(self.handle, _ptr(out)))
+        return out
+
+    def device_ptr(self):
+        return self.lib.qcdmet_plan_jacobian_device(self.handle)
+
+    @property
+    def kernel_used(self):
+        return self.lib.qcdmet_plan_kernel_used(self.handle)
+
+    @property
+    def launches(self):
+        return self.lib.qcdmet_plan_launches(self.handle)
+
+    @property
+    def flops(self):
+        return self.lib.qcdmet_plan_flops(self.handle)
+
+    def kernel_time_ms(self):
+        ms = ctypes.c_double(-1.0)
+        check(self.lib.qcdmet_plan_kernel_time_ms(self.handle, ctypes.byref(ms)))
+        return ms.value

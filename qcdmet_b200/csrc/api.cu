@@ -1,0 +1,567 @@
+// api.cu -- C ABI of libqcdmet_b200.so: plans, host-buffer wrappers, compat rhf_response.
+#include "common.cuh"
+#include <cstdarg>
+#include <algorithm>
+#include <numeric>
+
+namespace qcdmet {
+
+static thread_local char g_err[1024] = "";
+
+void set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+}  // namespace qcdmet
+
+using namespace qcdmet;
+
+struct qcdmet_plan {
+    int device = 0;
+    int N = 0, P = 0, no = 0, nv = 0, F = 0, S = 0;
+    long long Q = 0;
+    int ldo = 0, ldv = 0;
+    int colBegin = 0, colEnd = 0;
+    int kernel_req = QCDMET_KERNEL_AUTO, kernel_used = 0;
+    bool denseRows = false;
+    bool dmma_ok = false;
+    std::string dmma_why;
+    cudaStream_t stream = nullptr;
+    // host copies of the index arrays (schedule building, flop counts)
+    std::vector<int> h1start, h1row, h1col, rowStart, rowIdx;
+    // device
+    int *d_h1start = nullptr, *d_h1row = nullptr, *d_h1col = nullptr;
+    int *d_rowStart = nullptr, *d_rowFrag = nullptr, *d_rowIdx = nullptr;
+    long long *d_qoff = nullptr;
+    double *d_R = nullptr;
+    double *d_C = nullptr, *d_e = nullptr;
+    double *d_CoT = nullptr, *d_CvT = nullptr, *d_PO = nullptr, *d_PV = nullptr;
+    double *d_J = nullptr;
+    size_t J_capacity = 0;
+    double *d_D = nullptr;
+    double *d_work = nullptr;
+    int lwork = 0;
+    int *d_info = nullptr;
+    cusolverDnHandle_t solver = nullptr;
+    cublasHandle_t blas = nullptr;
+    DmmaPlanData *dmma = nullptr;
+    bool have_orbitals = false, have_jac = false;
+    int launches = 0;
+    double flops = 0.0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;   // around the dominant kernel of the last compute
+};
+
+namespace {
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+        if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+template <typename T>
+int dev_alloc_copy(T **dst, const T *src, size_t n)
+{
+    *dst = nullptr;
+    size_t bytes = sizeof(T) * std::max<size_t>(n, 1);
+    if (cudaMalloc((void **)dst, bytes) != cudaSuccess) {
+        cudaGetLastError();
+        set_error("cudaMalloc of %zu bytes failed", bytes);
+        return QCDMET_E_ALLOC;
+    }
+    if (n && src) QC_CUDA(cudaMemcpy(*dst, src, sizeof(T) * n, cudaMemcpyHostToDevice));
+    return QCDMET_OK;
+}
+
+template <typename T>
+int dev_alloc(T **dst, size_t n)
+{
+    return dev_alloc_copy<T>(dst, nullptr, n);
+}
+
+JacView make_view(const qcdmet_plan *p)
+{
+    JacView v;
+    v.N = p->N; v.no = p->no; v.nv = p->nv; v.ldo = p->ldo; v.ldv = p->ldv;
+    v.P = p->P; v.colBegin = p->colBegin; v.colEnd = p->colEnd;
+    v.F = p->F; v.S = p->S; v.Q = p->Q;
+    v.h1start = p->d_h1start; v.h1row = p->d_h1row; v.h1col = p->d_h1col;
+    v.rowStart = p->d_rowStart; v.rowFrag = p->d_rowFrag; v.qoff = p->d_qoff;
+    v.CoT = p->d_CoT; v.CvT = p->d_CvT; v.PO = p->d_PO; v.PV = p->d_PV; v.e = p->d_e;
+    v.J = p->d_J;
+    return v;
+}
+
+int validate_lists(int N, int P, int no, const int *h1start, const int *h1row, const int *h1col,
+                   int F, const int *rowStart, const double *R, const int *rowIdx)
+{
+    QC_CHECK(N > 0, QCDMET_E_ARG, "Norb must be positive (got %d)", N);
+    QC_CHECK(P >= 0, QCDMET_E_ARG, "Nterms must be >= 0 (got %d)", P);
+    QC_CHECK(no > 0 && no < N, QCDMET_E_ARG,
+             "numPairs must satisfy 0 < numPairs < Norb (got %d, Norb %d)", no, N);
+    QC_CHECK(h1start != nullptr, QCDMET_E_ARG, "H1start is NULL");
+    QC_CHECK(h1start[0] == 0, QCDMET_E_ARG, "H1start[0] must be 0");
+    for (int p = 0; p < P; ++p)
+        QC_CHECK(h1start[p + 1] >= h1start[p], QCDMET_E_ARG, "H1start not monotone at %d", p);
+    const int nnz = h1start[P];
+    QC_CHECK(nnz == 0 || (h1row && h1col), QCDMET_E_ARG, "H1row/H1col is NULL");
+    for (int e = 0; e < nnz; ++e)
+        QC_CHECK(h1row[e] >= 0 && h1row[e] < N && h1col[e] >= 0 && h1col[e] < N, QCDMET_E_ARG,
+                 "H1 element %d = (%d,%d) out of range for Norb %d", e, h1row[e], h1col[e], N);
+    QC_CHECK(F >= 0, QCDMET_E_ARG, "Nfrag must be >= 0");
+    if (F > 0) {
+        QC_CHECK(rowStart != nullptr && rowStart[0] == 0, QCDMET_E_ARG, "rowStart[0] must be 0");
+        for (int f = 0; f < F; ++f)
+            QC_CHECK(rowStart[f + 1] >= rowStart[f], QCDMET_E_ARG, "rowStart not monotone at %d", f);
+        const int S = rowStart[F];
+        QC_CHECK(S == 0 || R != nullptr || rowIdx != nullptr, QCDMET_E_ARG,
+                 "either R or rowIdx must be given");
+        if (R == nullptr)
+            for (int a = 0; a < S; ++a)
+                QC_CHECK(rowIdx[a] >= 0 && rowIdx[a] < N, QCDMET_E_ARG,
+                         "rowIdx[%d] = %d out of range", a, rowIdx[a]);
+    }
+    return QCDMET_OK;
+}
+
+int ensure_jacobian_buffer(qcdmet_plan *p)
+{
+    const size_t need = (size_t)std::max<long long>(p->Q, 1) * std::max(p->colEnd - p->colBegin, 1);
+    if (need > p->J_capacity) {
+        if (p->d_J) cudaFree(p->d_J);
+        p->d_J = nullptr;
+        p->J_capacity = 0;
+        if (cudaMalloc((void **)&p->d_J, sizeof(double) * need) != cudaSuccess) {
+            cudaGetLastError();
+            set_error("cudaMalloc of the Jacobian slice (%zu doubles) failed", need);
+            return QCDMET_E_ALLOC;
+        }
+        p->J_capacity = need;
+    }
+    return QCDMET_OK;
+}
+
+// Build the panels from d_C / d_e (already on the device).
+int build_panels(qcdmet_plan *p)
+{
+    QC_TRY(launch_split_transpose(p->d_C, p->N, p->no, p->d_CoT, p->ldo, p->d_CvT, p->ldv, p->stream));
+    if (p->S > 0) {
+        if (p->denseRows) {
+            // PO^T (ldo x S, col-major) = C_o^T (no x N) * R^T (N x S);  same for PV.
+            const double one = 1.0, zero = 0.0;
+            QC_CUDA(cudaMemsetAsync(p->d_PO, 0, sizeof(double) * (size_t)p->S * p->ldo, p->stream));
+            QC_CUDA(cudaMemsetAsync(p->d_PV, 0, sizeof(double) * (size_t)p->S * p->ldv, p->stream));
+            cublasSetStream(p->blas, p->stream);
+            cublasStatus_t s1 = cublasDgemm(p->blas, CUBLAS_OP_T, CUBLAS_OP_N, p->no, p->S, p->N, &one,
+                                            p->d_C, p->N, p->d_R, p->N, &zero, p->d_PO, p->ldo);
+            cublasStatus_t s2 = cublasDgemm(p->blas, CUBLAS_OP_T, CUBLAS_OP_N, p->nv, p->S, p->N, &one,
+                                            p->d_C + (size_t)p->N * p->no, p->N, p->d_R, p->N, &zero,
+                                            p->d_PV, p->ldv);
+            QC_CHECK(s1 == CUBLAS_STATUS_SUCCESS && s2 == CUBLAS_STATUS_SUCCESS, QCDMET_E_CUDA,
+                     "cublasDgemm (row projection) failed: %d %d", (int)s1, (int)s2);
+        } else {
+            QC_TRY(launch_gather_rows(p->d_CoT, p->ldo, p->d_rowIdx, p->S, p->d_PO, p->stream));
+            QC_TRY(launch_gather_rows(p->d_CvT, p->ldv, p->d_rowIdx, p->S, p->d_PV, p->stream));
+        }
+    }
+    JacView v = make_view(p);
+    QC_TRY(launch_dblocks(v, p->d_D, p->stream));
+    if (p->dmma) QC_TRY(dmma_prepare_orbitals(p->dmma, v, p->stream));
+    // gap check (the response diverges for a vanishing HOMO-LUMO gap, lib/rhf_response.cc:66-71)
+    double eg[2];
+    QC_CUDA(cudaMemcpyAsync(eg, p->d_e + p->no - 1, 2 * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    QC_CUDA(cudaStreamSynchronize(p->stream));
+    QC_CHECK(eg[1] - eg[0] > 0.0, QCDMET_E_GAP,
+             "HOMO-LUMO gap %.3e is not positive: the RHF response is undefined", eg[1] - eg[0]);
+    p->have_orbitals = true;
+    p->have_jac = false;
+    return QCDMET_OK;
+}
+
+double count_flops_general(const qcdmet_plan *p)
+{
+    // W_col of SURVEY.md 8(d): 2 S nv no + (2 nnz_p + 1) nv no * (a-tiles rebuild) + 2 no sum r_f^2 + 2 sum r_f^2
+    double total = 0.0;
+    const double nvno = (double)p->nv * p->no;
+    for (int c = p->colBegin; c < p->colEnd; ++c) {
+        const double nnz = p->h1start[c + 1] - p->h1start[c];
+        total += 2.0 * p->S * nvno + (2.0 * nnz + 1.0) * nvno + 2.0 * p->no * (double)p->Q + 2.0 * (double)p->Q;
+    }
+    return total;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *qcdmet_last_error(void) { return g_err; }
+const char *qcdmet_version(void) { return "qcdmet_b200 0.1 (sm_100a)"; }
+
+int qcdmet_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int qcdmet_plan_create(qcdmet_plan **out, int device, int Norb, int Nterms, int numPairs,
+                       const int *H1start, const int *H1row, const int *H1col,
+                       int Nfrag, const int *rowStart, const double *R, const int *rowIdx)
+{
+    QC_CHECK(out != nullptr, QCDMET_E_ARG, "plan output pointer is NULL");
+    *out = nullptr;
+    QC_TRY(validate_lists(Norb, Nterms, numPairs, H1start, H1row, H1col, Nfrag, rowStart, R, rowIdx));
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        set_error("no CUDA device available: libqcdmet_b200 has no CPU fallback");
+        return QCDMET_E_CUDA;
+    }
+    if (device < 0) QC_CUDA(cudaGetDevice(&device));
+    QC_CHECK(device < ndev, QCDMET_E_ARG, "device %d out of range (%d devices)", device, ndev);
+    DeviceGuard guard(device);
+    QC_CHECK(guard.ok, QCDMET_E_CUDA, "cudaSetDevice(%d) failed", device);
+
+    qcdmet_plan *p = new qcdmet_plan();
+    p->device = device;
+    p->N = Norb; p->P = Nterms; p->no = numPairs; p->nv = Norb - numPairs; p->F = Nfrag;
+    p->S = Nfrag > 0 ? rowStart[Nfrag] : 0;
+    p->ldo = round_up(p->no, 16);
+    p->ldv = round_up(p->nv, 16);
+    p->colBegin = 0; p->colEnd = Nterms;
+    p->denseRows = (R != nullptr);
+    const int nnz = H1start[Nterms];
+    p->h1start.assign(H1start, H1start + Nterms + 1);
+    p->h1row.assign(H1row, H1row + nnz);
+    p->h1col.assign(H1col, H1col + nnz);
+    if (Nfrag > 0) p->rowStart.assign(rowStart, rowStart + Nfrag + 1);
+    else p->rowStart.assign(1, 0);
+    if (!p->denseRows && p->S > 0) p->rowIdx.assign(rowIdx, rowIdx + p->S);
+    std::vector<int> rowFrag(std::max(p->S, 1), 0);
+    std::vector<long long> qoff(Nfrag + 1, 0);
+    for (int f = 0; f < Nfrag; ++f) {
+        const long long rf = rowStart[f + 1] - rowStart[f];
+        qoff[f + 1] = qoff[f] + rf * rf;
+        for (int a = rowStart[f]; a < rowStart[f + 1]; ++a) rowFrag[a] = f;
+    }
+    p->Q = qoff[Nfrag];
+
+    int rc = QCDMET_OK;
+    auto fail = [&](int code) { qcdmet_plan_destroy(p); return code; };
+    if ((rc = dev_alloc_copy(&p->d_h1start, p->h1start.data(), p->h1start.size()))) return fail(rc);
+    if ((rc = dev_alloc_copy(&p->d_h1row, p->h1row.data(), p->h1row.size()))) return fail(rc);
+    if ((rc = dev_alloc_copy(&p->d_h1col, p->h1col.data(), p->h1col.size()))) return fail(rc);
+    if ((rc = dev_alloc_copy(&p->d_rowStart, p->rowStart.data(), p->rowStart.size()))) return fail(rc);
+    if ((rc = dev_alloc_copy(&p->d_rowFrag, rowFrag.data(), rowFrag.size()))) return fail(rc);
+    if ((rc = dev_alloc_copy(&p->d_qoff, qoff.data(), qoff.size()))) return fail(rc);
+    if (p->denseRows) {
+        if ((rc = dev_alloc_copy(&p->d_R, R, (size_t)p->S * Norb))) return fail(rc);
+    } else {
+        if ((rc = dev_alloc_copy(&p->d_rowIdx, p->rowIdx.data(), p->rowIdx.size()))) return fail(rc);
+    }
+    if ((rc = dev_alloc(&p->d_C, (size_t)Norb * Norb))) return fail(rc);
+    if ((rc = dev_alloc(&p->d_e, (size_t)Norb))) return fail(rc);
+    if ((rc = dev_alloc(&p->d_CoT, (size_t)Norb * p->ldo))) return fail(rc);
+    if ((rc = dev_alloc(&p->d_CvT, (size_t)Norb * p->ldv))) return fail(rc);
+    if ((rc = dev_alloc(&p->d_PO, (size_t)p->S * p->ldo))) return fail(rc);
+    if ((rc = dev_alloc(&p->d_PV, (size_t)p->S * p->ldv))) return fail(rc);
+    if ((rc = dev_alloc(&p->d_D, (size_t)p->Q))) return fail(rc);
+    if ((rc = dev_alloc(&p->d_info, 1))) return fail(rc);
+
+    if (cusolverDnCreate(&p->solver) != CUSOLVER_STATUS_SUCCESS) {
+        set_error("cusolverDnCreate failed");
+        return fail(QCDMET_E_CUDA);
+    }
+    if (cublasCreate(&p->blas) != CUBLAS_STATUS_SUCCESS) {
+        set_error("cublasCreate failed");
+        return fail(QCDMET_E_CUDA);
+    }
+    // site-factorised DMMA schedule, when the perturbation/fragment structure allows it
+    p->dmma_ok = dmma_eligible(Norb, Nterms, Nfrag, p->h1start.data(), p->h1row.data(), p->h1col.data(),
+                               p->rowStart.data(), p->denseRows ? nullptr : p->rowIdx.data(),
+                               p->denseRows, &p->dmma_why);
+    if (p->dmma_ok) {
+        rc = dmma_plan_build(&p->dmma, Norb, numPairs, Nterms, Nfrag, p->h1start.data(), p->h1row.data(),
+                             p->h1col.data(), p->rowStart.data(), p->rowIdx.data());
+        if (rc) return fail(rc);
+    }
+    *out = p;
+    return QCDMET_OK;
+}
+
+int qcdmet_plan_destroy(qcdmet_plan *p)
+{
+    if (!p) return QCDMET_OK;
+    DeviceGuard guard(p->device);
+    cudaFree(p->d_h1start); cudaFree(p->d_h1row); cudaFree(p->d_h1col);
+    cudaFree(p->d_rowStart); cudaFree(p->d_rowFrag); cudaFree(p->d_rowIdx); cudaFree(p->d_qoff);
+    cudaFree(p->d_R); cudaFree(p->d_C); cudaFree(p->d_e);
+    cudaFree(p->d_CoT); cudaFree(p->d_CvT); cudaFree(p->d_PO); cudaFree(p->d_PV);
+    cudaFree(p->d_J); cudaFree(p->d_D); cudaFree(p->d_work); cudaFree(p->d_info);
+    if (p->ev0) cudaEventDestroy(p->ev0);
+    if (p->ev1) cudaEventDestroy(p->ev1);
+    if (p->solver) cusolverDnDestroy(p->solver);
+    if (p->blas) cublasDestroy(p->blas);
+    if (p->dmma) dmma_plan_free(p->dmma);
+    cudaGetLastError();
+    delete p;
+    return QCDMET_OK;
+}
+
+int qcdmet_plan_set_columns(qcdmet_plan *p, int colBegin, int colEnd)
+{
+    QC_CHECK(p != nullptr, QCDMET_E_ARG, "plan is NULL");
+    QC_CHECK(0 <= colBegin && colBegin <= colEnd && colEnd <= p->P, QCDMET_E_ARG,
+             "column range [%d,%d) invalid for Nterms %d", colBegin, colEnd, p->P);
+    p->colBegin = colBegin;
+    p->colEnd = colEnd;
+    p->have_jac = false;
+    return QCDMET_OK;
+}
+
+int qcdmet_plan_set_kernel(qcdmet_plan *p, int kernel)
+{
+    QC_CHECK(p != nullptr, QCDMET_E_ARG, "plan is NULL");
+    QC_CHECK(kernel >= QCDMET_KERNEL_AUTO && kernel <= QCDMET_KERNEL_DMMA, QCDMET_E_ARG,
+             "unknown kernel id %d", kernel);
+    QC_CHECK(kernel != QCDMET_KERNEL_DMMA || p->dmma_ok, QCDMET_E_ARG,
+             "DMMA kernel not eligible for this plan: %s", p->dmma_why.c_str());
+    p->kernel_req = kernel;
+    return QCDMET_OK;
+}
+
+int qcdmet_plan_set_stream(qcdmet_plan *p, void *stream)
+{
+    QC_CHECK(p != nullptr, QCDMET_E_ARG, "plan is NULL");
+    p->stream = (cudaStream_t)stream;
+    return QCDMET_OK;
+}
+
+int qcdmet_plan_set_h0(qcdmet_plan *p, const double *H0)
+{
+    QC_CHECK(p != nullptr && H0 != nullptr, QCDMET_E_ARG, "plan or H0 is NULL");
+    DeviceGuard guard(p->device);
+    const int N = p->N;
+    QC_CUDA(cudaMemcpyAsync(p->d_C, H0, sizeof(double) * (size_t)N * N, cudaMemcpyHostToDevice, p->stream));
+    cusolverDnSetStream(p->solver, p->stream);
+    int lwork = 0;
+    // Upper triangle of the column-major view, as dsyev('V','U') in lib/rhf_response.cc:45-50
+    cusolverStatus_t cs = cusolverDnDsyevd_bufferSize(p->solver, CUSOLVER_EIG_MODE_VECTOR,
+                                                      CUBLAS_FILL_MODE_UPPER, N, p->d_C, N, p->d_e, &lwork);
+    QC_CHECK(cs == CUSOLVER_STATUS_SUCCESS, QCDMET_E_SOLVER, "cusolverDnDsyevd_bufferSize failed: %d", (int)cs);
+    if (lwork > p->lwork) {
+        cudaFree(p->d_work);
+        p->d_work = nullptr;
+        p->lwork = 0;
+        QC_TRY(dev_alloc(&p->d_work, (size_t)lwork));
+        p->lwork = lwork;
+    }
+    cs = cusolverDnDsyevd(p->solver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_UPPER, N, p->d_C, N,
+                          p->d_e, p->d_work, p->lwork, p->d_info);
+    QC_CHECK(cs == CUSOLVER_STATUS_SUCCESS, QCDMET_E_SOLVER, "cusolverDnDsyevd failed: %d", (int)cs);
+    int info = 0;
+    QC_CUDA(cudaMemcpyAsync(&info, p->d_info, sizeof(int), cudaMemcpyDeviceToHost, p->stream));
+    QC_CUDA(cudaStreamSynchronize(p->stream));
+    QC_CHECK(info == 0, QCDMET_E_SOLVER, "cusolverDnDsyevd: info = %d", info);
+    return build_panels(p);
+}
+
+int qcdmet_plan_set_orbitals(qcdmet_plan *p, const double *C, const double *e)
+{
+    QC_CHECK(p != nullptr && C != nullptr && e != nullptr, QCDMET_E_ARG, "plan, C or e is NULL");
+    DeviceGuard guard(p->device);
+    QC_CUDA(cudaMemcpyAsync(p->d_C, C, sizeof(double) * (size_t)p->N * p->N, cudaMemcpyHostToDevice, p->stream));
+    QC_CUDA(cudaMemcpyAsync(p->d_e, e, sizeof(double) * (size_t)p->N, cudaMemcpyHostToDevice, p->stream));
+    return build_panels(p);
+}
+
+int qcdmet_plan_compute(qcdmet_plan *p)
+{
+    QC_CHECK(p != nullptr, QCDMET_E_ARG, "plan is NULL");
+    QC_CHECK(p->have_orbitals, QCDMET_E_STATE, "plan has no orbitals: call set_h0/set_orbitals first");
+    DeviceGuard guard(p->device);
+    QC_TRY(ensure_jacobian_buffer(p));
+    JacView v = make_view(p);
+    const bool use_dmma = (p->kernel_req == QCDMET_KERNEL_DMMA) ||
+                          (p->kernel_req == QCDMET_KERNEL_AUTO && p->dmma_ok);
+    if (!p->ev0) {
+        QC_CUDA(cudaEventCreate(&p->ev0));
+        QC_CUDA(cudaEventCreate(&p->ev1));
+    }
+    if (use_dmma) {
+        QC_TRY(launch_jacobian_dmma(p->dmma, v, p->stream, &p->launches, &p->flops, p->ev0, p->ev1));
+        p->kernel_used = QCDMET_KERNEL_DMMA;
+    } else {
+        QC_TRY(launch_jacobian_general(v, p->stream, &p->launches, &p->flops, p->ev0, p->ev1));
+        p->flops = count_flops_general(p);
+        p->kernel_used = QCDMET_KERNEL_GENERAL;
+    }
+    p->have_jac = true;
+    return QCDMET_OK;
+}
+
+int qcdmet_plan_sync(qcdmet_plan *p)
+{
+    QC_CHECK(p != nullptr, QCDMET_E_ARG, "plan is NULL");
+    DeviceGuard guard(p->device);
+    QC_CUDA(cudaStreamSynchronize(p->stream));
+    QC_CUDA(cudaGetLastError());
+    return QCDMET_OK;
+}
+
+void *qcdmet_plan_jacobian_device(qcdmet_plan *p) { return p ? (void *)p->d_J : nullptr; }
+
+int qcdmet_plan_get_jacobian(qcdmet_plan *p, double *J)
+{
+    QC_CHECK(p != nullptr && J != nullptr, QCDMET_E_ARG, "plan or J is NULL");
+    QC_CHECK(p->have_jac, QCDMET_E_STATE, "no Jacobian computed yet");
+    DeviceGuard guard(p->device);
+    const size_t n = (size_t)p->Q * (p->colEnd - p->colBegin);
+    if (n) QC_CUDA(cudaMemcpyAsync(J, p->d_J, sizeof(double) * n, cudaMemcpyDeviceToHost, p->stream));
+    QC_CUDA(cudaStreamSynchronize(p->stream));
+    return QCDMET_OK;
+}
+
+int qcdmet_plan_get_dblocks(qcdmet_plan *p, double *D)
+{
+    QC_CHECK(p != nullptr && D != nullptr, QCDMET_E_ARG, "plan or D_blocks is NULL");
+    QC_CHECK(p->have_orbitals, QCDMET_E_STATE, "plan has no orbitals");
+    DeviceGuard guard(p->device);
+    if (p->Q) QC_CUDA(cudaMemcpyAsync(D, p->d_D, sizeof(double) * (size_t)p->Q, cudaMemcpyDeviceToHost, p->stream));
+    QC_CUDA(cudaStreamSynchronize(p->stream));
+    return QCDMET_OK;
+}
+
+int qcdmet_plan_get_eigenvalues(qcdmet_plan *p, double *e)
+{
+    QC_CHECK(p != nullptr && e != nullptr, QCDMET_E_ARG, "plan or e is NULL");
+    QC_CHECK(p->have_orbitals, QCDMET_E_STATE, "plan has no orbitals");
+    DeviceGuard guard(p->device);
+    QC_CUDA(cudaMemcpyAsync(e, p->d_e, sizeof(double) * (size_t)p->N, cudaMemcpyDeviceToHost, p->stream));
+    QC_CUDA(cudaStreamSynchronize(p->stream));
+    return QCDMET_OK;
+}
+
+int qcdmet_plan_get_orbitals(qcdmet_plan *p, double *C)
+{
+    QC_CHECK(p != nullptr && C != nullptr, QCDMET_E_ARG, "plan or C is NULL");
+    QC_CHECK(p->have_orbitals, QCDMET_E_STATE, "plan has no orbitals");
+    DeviceGuard guard(p->device);
+    QC_CUDA(cudaMemcpyAsync(C, p->d_C, sizeof(double) * (size_t)p->N * p->N, cudaMemcpyDeviceToHost, p->stream));
+    QC_CUDA(cudaStreamSynchronize(p->stream));
+    return QCDMET_OK;
+}
+
+long long qcdmet_plan_num_residuals(qcdmet_plan *p) { return p ? p->Q : -1; }
+int qcdmet_plan_kernel_used(qcdmet_plan *p) { return p ? p->kernel_used : -1; }
+int qcdmet_plan_launches(qcdmet_plan *p) { return p ? p->launches : -1; }
+double qcdmet_plan_flops(qcdmet_plan *p) { return p ? p->flops : -1.0; }
+
+int qcdmet_plan_kernel_time_ms(qcdmet_plan *p, double *ms)
+{
+    QC_CHECK(p != nullptr && ms != nullptr, QCDMET_E_ARG, "plan or ms is NULL");
+    *ms = -1.0;
+    if (!p->have_jac || !p->ev0 || p->launches == 0) return QCDMET_OK;
+    DeviceGuard guard(p->device);
+    QC_CUDA(cudaEventSynchronize(p->ev1));
+    float f = 0.f;
+    QC_CUDA(cudaEventElapsedTime(&f, p->ev0, p->ev1));
+    *ms = f;
+    return QCDMET_OK;
+}
+
+int qcdmet_plan_get_full_response(qcdmet_plan *p, double *rdm_deriv, double *one_rdm)
+{
+    QC_CHECK(p != nullptr && rdm_deriv != nullptr, QCDMET_E_ARG, "plan or rdm_deriv is NULL");
+    QC_CHECK(p->F == 1 && p->S == p->N && !p->denseRows, QCDMET_E_ARG,
+             "full response needs a plan with one fragment holding all %d sites", p->N);
+    QC_TRY(qcdmet_plan_get_jacobian(p, rdm_deriv));
+    if (one_rdm) {
+        DeviceGuard guard(p->device);
+        double *d_full = nullptr;
+        QC_TRY(dev_alloc(&d_full, (size_t)p->N * p->N));
+        int rc = launch_one_rdm(p->d_CoT, p->ldo, p->N, p->no, d_full, p->stream);
+        if (rc == QCDMET_OK &&
+            cudaMemcpyAsync(one_rdm, d_full, sizeof(double) * (size_t)p->N * p->N, cudaMemcpyDeviceToHost,
+                            p->stream) != cudaSuccess) rc = QCDMET_E_CUDA;
+        if (cudaStreamSynchronize(p->stream) != cudaSuccess) rc = QCDMET_E_CUDA;
+        cudaFree(d_full);
+        if (rc) { set_error("1-RDM construction failed"); return rc; }
+    }
+    return QCDMET_OK;
+}
+
+static int jacobian_impl(int Norb, int Nterms, int numPairs, const int *H1start, const int *H1row,
+                         const int *H1col, const double *H0, const double *C, const double *e,
+                         int Nfrag, const int *rowStart, const double *R, const int *rowIdx,
+                         int colBegin, int colEnd, double *J, double *D_blocks, double *eig_out)
+{
+    qcdmet_plan *p = nullptr;
+    QC_TRY(qcdmet_plan_create(&p, -1, Norb, Nterms, numPairs, H1start, H1row, H1col, Nfrag, rowStart, R, rowIdx));
+    int rc = qcdmet_plan_set_columns(p, colBegin, colEnd);
+    if (!rc) rc = H0 ? qcdmet_plan_set_h0(p, H0) : qcdmet_plan_set_orbitals(p, C, e);
+    if (!rc && J) rc = qcdmet_plan_compute(p);
+    if (!rc && J) rc = qcdmet_plan_get_jacobian(p, J);
+    if (!rc && D_blocks) rc = qcdmet_plan_get_dblocks(p, D_blocks);
+    if (!rc && eig_out) rc = qcdmet_plan_get_eigenvalues(p, eig_out);
+    qcdmet_plan_destroy(p);
+    return rc;
+}
+
+int qcdmet_jacobian(int Norb, int Nterms, int numPairs, const int *H1start, const int *H1row,
+                    const int *H1col, const double *H0, int Nfrag, const int *rowStart,
+                    const double *R, const int *rowIdx, int colBegin, int colEnd, double *J,
+                    double *D_blocks, double *eig_out)
+{
+    QC_CHECK(H0 != nullptr, QCDMET_E_ARG, "H0 is NULL");
+    return jacobian_impl(Norb, Nterms, numPairs, H1start, H1row, H1col, H0, nullptr, nullptr, Nfrag,
+                         rowStart, R, rowIdx, colBegin, colEnd, J, D_blocks, eig_out);
+}
+
+int qcdmet_jacobian_from_orbitals(int Norb, int Nterms, int numPairs, const int *H1start,
+                                  const int *H1row, const int *H1col, const double *C, const double *e,
+                                  int Nfrag, const int *rowStart, const double *R, const int *rowIdx,
+                                  int colBegin, int colEnd, double *J, double *D_blocks)
+{
+    QC_CHECK(C != nullptr && e != nullptr, QCDMET_E_ARG, "C or e is NULL");
+    return jacobian_impl(Norb, Nterms, numPairs, H1start, H1row, H1col, nullptr, C, e, Nfrag, rowStart,
+                         R, rowIdx, colBegin, colEnd, J, D_blocks, nullptr);
+}
+
+// Compat symbol: lib/rhf_response.cc:32.  One fragment holding every site -> the "Jacobian"
+// is the full response, stored exactly as rdm_deriv[row + N*(col + N*deriv)].
+int rhf_response(const int Norb, const int Nterms, const int numPairs, int *H1start, int *H1row,
+                 int *H1col, double *H0, double *rdm_deriv)
+{
+    QC_CHECK(H0 != nullptr, QCDMET_E_ARG, "H0 is NULL");
+    QC_CHECK(Nterms == 0 || rdm_deriv != nullptr, QCDMET_E_ARG, "rdm_deriv is NULL");
+    std::vector<int> rowStart = {0, Norb}, rowIdx(std::max(Norb, 1));
+    std::iota(rowIdx.begin(), rowIdx.end(), 0);
+    qcdmet_plan *p = nullptr;
+    QC_TRY(qcdmet_plan_create(&p, -1, Norb, Nterms, numPairs, H1start, H1row, H1col, 1, rowStart.data(),
+                              nullptr, rowIdx.data()));
+    int rc = qcdmet_plan_set_kernel(p, QCDMET_KERNEL_GENERAL);
+    if (!rc) rc = qcdmet_plan_set_h0(p, H0);
+    if (!rc && Nterms > 0) rc = qcdmet_plan_compute(p);
+    if (!rc) {
+        if (Nterms > 0) rc = qcdmet_plan_get_full_response(p, rdm_deriv, H0);
+        else {
+            // Nterms == 0 is legal in the reference: eigensolve + 1-RDM only
+            p->have_jac = true;
+            static double dummy;
+            rc = qcdmet_plan_get_full_response(p, &dummy, H0);
+        }
+    }
+    qcdmet_plan_destroy(p);
+    return rc;
+}
+
+}  // extern "C"

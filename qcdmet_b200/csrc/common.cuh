@@ -1,0 +1,91 @@
+// common.cuh -- shared declarations of libqcdmet_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cublas_v2.h>
+#include <cusolverDn.h>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+#include "../../include/qcdmet_b200.h"
+
+namespace qcdmet {
+
+void set_error(const char *fmt, ...);
+
+#define QC_CUDA(call)                                                                         \
+    do {                                                                                      \
+        cudaError_t err__ = (call);                                                           \
+        if (err__ != cudaSuccess) {                                                           \
+            qcdmet::set_error("%s:%d CUDA error %d (%s) in %s", __FILE__, __LINE__,           \
+                              (int)err__, cudaGetErrorString(err__), #call);                  \
+            return QCDMET_E_CUDA;                                                             \
+        }                                                                                     \
+    } while (0)
+
+#define QC_CHECK(cond, code, ...)                                                             \
+    do {                                                                                      \
+        if (!(cond)) {                                                                        \
+            qcdmet::set_error(__VA_ARGS__);                                                   \
+            return (code);                                                                    \
+        }                                                                                     \
+    } while (0)
+
+#define QC_TRY(expr)                                                                          \
+    do {                                                                                      \
+        int rc__ = (expr);                                                                    \
+        if (rc__ != QCDMET_OK) return rc__;                                                   \
+    } while (0)
+
+inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+// ---------------------------------------------------------------------------------------
+// Device-side view of everything the Jacobian kernels read.  Layout in HBM:
+//   CoT [N ][ldo]  CoT[i][o] = C[i, o]          (site-major, orbital contiguous, zero padded)
+//   CvT [N ][ldv]  CvT[i][v] = C[i, no + v]
+//   PO  [S ][ldo]  fragment rows projected on the occupied orbitals (R*C_o or gathered CoT)
+//   PV  [S ][ldv]  fragment rows projected on the virtual orbitals
+//   e   [N]        eigenvalues, ascending
+//   J   [ncols][Q] column-major (Q, ncols): one Jacobian column per perturbation
+// ---------------------------------------------------------------------------------------
+struct JacView {
+    int N, no, nv, ldo, ldv;
+    int P;                 // perturbations in the plan
+    int colBegin, colEnd;  // column shard
+    int F;                 // fragments
+    int S;                 // fragment rows
+    long long Q;           // residuals
+    const int *h1start, *h1row, *h1col;
+    const int *rowStart;       // [F+1]
+    const int *rowFrag;        // [S] fragment of each row
+    const long long *qoff;     // [F+1] residual offset of each fragment
+    const double *CoT, *CvT, *PO, *PV, *e;
+    double *J;                 // [Q * ncols]
+};
+
+// kernels_prep.cu
+int launch_split_transpose(const double *C, int N, int no, double *CoT, int ldo, double *CvT,
+                           int ldv, cudaStream_t st);
+int launch_gather_rows(const double *src, int ld, const int *rowIdx, int S, double *dst,
+                       cudaStream_t st);
+int launch_dblocks(const JacView &v, double *D, cudaStream_t st);
+int launch_one_rdm(const double *CoT, int ldo, int N, int no, double *D, cudaStream_t st);
+
+// kernels_general.cu
+// ev0/ev1 are recorded on `st` around the dominant kernel (first column chunk).
+int launch_jacobian_general(const JacView &v, cudaStream_t st, int *launches, double *flops,
+                            cudaEvent_t ev0, cudaEvent_t ev1);
+
+// kernels_dmma.cu
+struct DmmaPlanData;   // site-factorised schedule (device arrays), built once per plan
+bool dmma_eligible(int N, int P, int F, const int *h1start, const int *h1row, const int *h1col,
+                   const int *rowStart, const int *rowIdx, bool denseRows, std::string *why);
+int dmma_plan_build(DmmaPlanData **out, int N, int no, int P, int F, const int *h1start,
+                    const int *h1row, const int *h1col, const int *rowStart, const int *rowIdx);
+void dmma_plan_free(DmmaPlanData *d);
+int dmma_prepare_orbitals(DmmaPlanData *d, const JacView &v, cudaStream_t st);
+int launch_jacobian_dmma(DmmaPlanData *d, const JacView &v, cudaStream_t st, int *launches,
+                         double *flops, cudaEvent_t ev0, cudaEvent_t ev1);
+
+}  // namespace qcdmet

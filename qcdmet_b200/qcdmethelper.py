@@ -1,0 +1,142 @@
+"""Mean-field helper with QC-DMET's interface, backed by libqcdmet_b200.so.
+
+Mirrors class qcdmethelper of the reference (src/qcdmethelper.py:26-168): same constructor and
+method names, argument order and return shapes, for the RHF-response path
+
+    construct1RDM_response(doSCF, umat_loc, NOrotation)        src/qcdmethelper.py:84-112
+    construct1RDM_loc_response(doSCF, umat, list_H1)           README.md:57 (older name)
+    convertH1sparse()                                          src/qcdmethelper.py:48-65
+
+plus the fused entry the Jacobian assembly uses instead of materialising N x N x P:
+
+    response_jacobian(umat_loc, row_start, rows=None, row_idx=None)  ->  (Q, P) Fortran-ordered
+
+All device work goes through the ctypes C ABI (include/qcdmet_b200.h).  No CPU fallback exists
+for the response; construct1RDM_loc / construct1RDM_base stay host numpy exactly as in the
+reference (they are not part of the response path, SURVEY.md 8a a14 "next").
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+
+from . import _lib
+
+
+class qcdmethelper:
+
+    def __init__(self, theLocalIntegrals, list_H1, altcf, minFunc):
+        self.locints = theLocalIntegrals
+        assert self.locints.Nelec % 2 == 0
+        self.numPairs = self.locints.Nelec // 2          # src/qcdmethelper.py:32
+        self.altcf = altcf
+        self.minFunc = None
+        if self.altcf:
+            assert minFunc == 'OEI' or minFunc == 'FOCK_INIT'
+            self.minFunc = minFunc
+
+        # list_H1: dense list of N x N 0/1 matrices (reference form, src/dmet.py:118-159), or a
+        # pre-built CSR triple (H1start, H1row, H1col): the dense list is 8 N^2 P bytes.
+        if isinstance(list_H1, tuple) and len(list_H1) == 3:
+            self.list_H1 = None
+            self.H1start, self.H1row, self.H1col = (np.ascontiguousarray(a, dtype=ctypes.c_int)
+                                                    for a in list_H1)
+        else:
+            self.list_H1 = list_H1
+            self.H1start, self.H1row, self.H1col = self.convertH1sparse()
+        self.Nterms = len(self.H1start) - 1
+        self._plans = {}
+
+    # ---------------------------------------------------------------- src/qcdmethelper.py:48-65
+    def convertH1sparse(self):
+        H1start, H1row, H1col = [0], [], []
+        for H1 in self.list_H1:
+            rowco, colco = np.where(np.asarray(H1) == 1)
+            H1row.extend(int(r) for r in rowco)
+            H1col.extend(int(c) for c in colco)
+            H1start.append(len(H1row))
+        return (np.array(H1start, dtype=ctypes.c_int), np.array(H1row, dtype=ctypes.c_int),
+                np.array(H1col, dtype=ctypes.c_int))
+
+    # ---------------------------------------------------------------- src/qcdmethelper.py:67-82
+    def construct1RDM_loc(self, doSCF, umat_loc):
+        if self.altcf and self.minFunc == 'OEI':
+            OEI = self.locints.loc_oei() + umat_loc
+        else:
+            OEI = self.locints.loc_rhf_fock() + umat_loc
+        if doSCF:
+            raise NotImplementedError("doSCF=True needs the reference's pyscf-based rhf module "
+                                      "(src/rhf.py); it is hard-coded False in src/dmet.py:44")
+        return self.construct1RDM_base(OEI, self.numPairs)
+
+    # ---------------------------------------------------------------- src/qcdmethelper.py:114-122
+    def construct1RDM_base(self, OEI, myNumPairs):
+        eigenvals, eigenvecs = np.linalg.eigh(OEI)
+        idx = eigenvals.argsort()
+        eigenvecs = eigenvecs[:, idx]
+        return 2 * np.dot(eigenvecs[:, :myNumPairs], eigenvecs[:, :myNumPairs].T)
+
+    def _oei(self, doSCF, umat_loc, NOrotation):
+        if doSCF:
+            raise NotImplementedError("doSCF=True is outside the response hot path (src/dmet.py:44)")
+        OEI = self.locints.loc_rhf_fock() + umat_loc          # src/qcdmethelper.py:87
+        if NOrotation is not None:                            # src/qcdmethelper.py:98-99
+            OEI = np.dot(np.dot(NOrotation.T, OEI), NOrotation)
+        return np.ascontiguousarray(OEI, dtype=ctypes.c_double)
+
+    # ---------------------------------------------------------------- src/qcdmethelper.py:84-112
+    def construct1RDM_response(self, doSCF, umat_loc, NOrotation):
+        """Full response, shape (Nterms, Norbs, Norbs) -- only sensible when 8 N^2 P bytes fit
+        in host memory; dmet.rdm_differences_derivative uses response_jacobian instead."""
+        N = self.locints.Norbs
+        OEI = self._oei(doSCF, umat_loc, NOrotation).reshape(N * N)
+        rdm_deriv_rot = np.ones([N * N * self.Nterms], dtype=ctypes.c_double)
+        lib = _lib.load()
+        h1row = self.H1row if self.H1row.size else np.zeros(1, dtype=ctypes.c_int)
+        h1col = self.H1col if self.H1col.size else np.zeros(1, dtype=ctypes.c_int)
+        rc = lib.rhf_response(ctypes.c_int(N), ctypes.c_int(self.Nterms), ctypes.c_int(self.numPairs),
+                              self.H1start.ctypes.data_as(ctypes.c_void_p),
+                              h1row.ctypes.data_as(ctypes.c_void_p),
+                              h1col.ctypes.data_as(ctypes.c_void_p),
+                              OEI.ctypes.data_as(ctypes.c_void_p),
+                              rdm_deriv_rot.ctypes.data_as(ctypes.c_void_p))
+        _lib.check(rc)
+        return rdm_deriv_rot.reshape((self.Nterms, N, N), order='C')
+
+    def construct1RDM_loc_response(self, doSCF, umat, list_H1=None):
+        """README-era signature (README.md:57); list_H1 now lives in the constructor."""
+        if list_H1 is not None and list_H1 is not self.list_H1:
+            other = qcdmethelper(self.locints, list_H1, self.altcf, self.minFunc)
+            return other.construct1RDM_response(doSCF, umat, None)
+        return self.construct1RDM_response(doSCF, umat, None)
+
+    # ---------------------------------------------------------------- fused path
+    def _plan(self, row_start, rows, row_idx):
+        key = (np.asarray(row_start).tobytes(),
+               None if rows is None else (rows.shape, rows.tobytes()),
+               None if row_idx is None else np.asarray(row_idx).tobytes())
+        plan = self._plans.get(key)
+        if plan is None:
+            if len(self._plans) > 4:
+                for old in self._plans.values():
+                    old.close()
+                self._plans.clear()
+            plan = _lib.Plan(self.locints.Norbs, self.numPairs, self.H1start, self.H1row, self.H1col,
+                             row_start, rows, row_idx)
+            self._plans[key] = plan
+        return plan
+
+    def response_jacobian(self, umat_loc, row_start, rows=None, row_idx=None, NOrotation=None,
+                          want_dblocks=False):
+        """Fragment blocks of every dD_p, written directly as Jacobian columns.
+
+        Replaces construct1RDM_response + the assembly loop of src/dmet.py:496-520.
+        Returns a Fortran-ordered (Q, Nterms) float64 array (and the mean-field 1-RDM blocks)."""
+        plan = self._plan(row_start, rows, row_idx)
+        plan.set_h0(self._oei(False, umat_loc, NOrotation))
+        plan.compute()
+        jac = plan.jacobian()
+        if want_dblocks:
+            return jac, plan.dblocks()
+        return jac

@@ -1,0 +1,64 @@
+"""CPU tests of the C-ABI boundary: the library loads, exports every symbol the header declares,
+validates arguments, and fails loudly (no CPU fallback) when there is no CUDA device."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from qcdmet_b200 import _lib, workloads as wl
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    text = open(os.path.join(ROOT, "include", "qcdmet_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    names = re.findall(r"\b([A-Za-z_][A-Za-z0-9_]*)\s*\(", text)
+    return sorted({n for n in names if n.startswith("qcdmet_") or n == "rhf_response"})
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    syms = header_symbols()
+    assert "rhf_response" in syms and "qcdmet_jacobian" in syms and len(syms) >= 25
+    for name in syms:
+        assert hasattr(lib, name), f"{name} declared in include/qcdmet_b200.h but not exported"
+    assert set(syms) == set(_lib.SIGNATURES), "python binding table and header disagree"
+    assert b"sm_100a" in lib.qcdmet_version()
+
+
+def test_argument_validation():
+    lib = _lib.load()
+    w = wl.sweep(8)
+    handle = ctypes.c_void_p()
+    hs = w.h1start.copy()
+    bad_row = w.h1row.copy()
+    bad_row[0] = 99
+    rc = lib.qcdmet_plan_create(ctypes.byref(handle), -1, 8, w.nterms, 4, _lib._ptr(hs), _lib._ptr(bad_row),
+                                _lib._ptr(w.h1col), len(w.row_start) - 1, _lib._ptr(w.row_start), None,
+                                _lib._ptr(w.row_idx))
+    assert rc == -1 and b"out of range" in lib.qcdmet_last_error()
+    rc = lib.qcdmet_plan_create(ctypes.byref(handle), -1, 8, w.nterms, 8, _lib._ptr(hs), _lib._ptr(w.h1row),
+                                _lib._ptr(w.h1col), len(w.row_start) - 1, _lib._ptr(w.row_start), None,
+                                _lib._ptr(w.row_idx))
+    assert rc == -1 and b"numPairs" in lib.qcdmet_last_error()
+    assert lib.qcdmet_plan_compute(None) == -1
+    assert lib.qcdmet_plan_destroy(None) == 0
+
+
+def test_no_cpu_fallback_without_device():
+    lib = _lib.load()
+    if lib.qcdmet_device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    w = wl.sweep(8)
+    with pytest.raises(_lib.QcdmetError) as ei:
+        _lib.Plan(w.norb, w.num_pairs, w.h1start, w.h1row, w.h1col, w.row_start, w.rows, w.row_idx)
+    assert ei.value.code == -2 and "no CPU fallback" in str(ei.value)
+    h0 = np.array(w.h0, copy=True).reshape(-1)
+    out = np.ones(w.norb * w.norb * w.nterms)
+    rc = lib.rhf_response(w.norb, w.nterms, w.num_pairs, _lib._ptr(w.h1start), _lib._ptr(w.h1row),
+                          _lib._ptr(w.h1col), _lib._ptr(h0), _lib._ptr(out))
+    assert rc == -2
+    assert (out == 1.0).all() and np.array_equal(h0, w.h0.reshape(-1))   # nothing written

@@ -1,0 +1,238 @@
+"""GPU parity tests (run on the B200 box): the CUDA path, called through the C ABI, against the
+oracle / the compiled reference's golden outputs.  Tolerance: 1e-10 absolute on response and
+Jacobian elements (BASELINE.json north_star)."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from oracle import response_oracle as ro
+from qcdmet_b200 import _lib, dmet as dmet_mod, workloads as wl
+from util import GOLDEN, golden_ids, load_golden
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+KERNELS = {"general": _lib.KERNEL_GENERAL, "auto": _lib.KERNEL_AUTO}
+
+
+def run_plan(w, kernel, from_orbitals=None, cols=None):
+    plan = _lib.Plan(w.norb, w.num_pairs, w.h1start, w.h1row, w.h1col, w.row_start, w.rows, w.row_idx)
+    plan.set_kernel(kernel)
+    if cols is not None:
+        plan.set_columns(*cols)
+    if from_orbitals is not None:
+        plan.set_orbitals(*from_orbitals)
+    else:
+        plan.set_h0(w.h0)
+    plan.compute()
+    jac, c, e, d = plan.jacobian(), plan.orbitals(), plan.eigenvalues(), plan.dblocks()
+    used = plan.kernel_used
+    plan.close()
+    return jac, c, e, d, used
+
+
+def oracle_jac(w, c, e):
+    return ro.jacobian_from_orbitals(c, e, w.num_pairs, w.h1start, w.h1row, w.h1col, w.row_start,
+                                     w.rows, w.row_idx)
+
+
+@pytest.mark.parametrize("kernel", list(KERNELS))
+@pytest.mark.parametrize("path", GOLDEN, ids=golden_ids())
+def test_jacobian_matches_golden(path, kernel):
+    """End to end from H0 (cuSOLVER syevd on the device) against the compiled reference's output."""
+    g = load_golden(path)
+    plan = _lib.Plan(g["norb"], g["num_pairs"], g["h1start"], g["h1row"], g["h1col"], g["row_start"],
+                     g["rows"], g["row_idx"])
+    plan.set_kernel(KERNELS[kernel])
+    plan.set_h0(g["h0"])
+    plan.compute()
+    jac = plan.jacobian()
+    assert jac.shape == g["jac"].shape and jac.flags.f_contiguous
+    assert np.abs(jac - g["jac"]).max() <= TOL
+    plan.close()
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=golden_ids())
+def test_compat_rhf_response_matches_golden(path):
+    """The compat symbol with the reference's own ctypes call shape (src/qcdmethelper.py:102-109)."""
+    g = load_golden(path)
+    lib = _lib.load()
+    n, p = g["norb"], len(g["h1start"]) - 1
+    h0 = np.array(g["h0"].reshape(n * n), dtype=ctypes.c_double)
+    out = np.ones(n * n * p, dtype=ctypes.c_double)
+    rc = lib.rhf_response(ctypes.c_int(n), ctypes.c_int(p), ctypes.c_int(g["num_pairs"]),
+                          g["h1start"].ctypes.data_as(ctypes.c_void_p), g["h1row"].ctypes.data_as(ctypes.c_void_p),
+                          g["h1col"].ctypes.data_as(ctypes.c_void_p), h0.ctypes.data_as(ctypes.c_void_p),
+                          out.ctypes.data_as(ctypes.c_void_p))
+    assert rc == 0, lib.qcdmet_last_error()
+    resp = out.reshape((p, n, n), order="C")
+    assert np.abs(resp - g["resp"]).max() <= TOL
+    assert np.abs(h0.reshape(n, n) - g["one_rdm"]).max() <= TOL      # H0 overwritten by the 1-RDM
+    assert np.abs(resp - resp.transpose(0, 2, 1)).max() == 0.0        # exactly symmetric, like the reference
+
+
+SHAPES = {
+    "sweep200": lambda: wl.sweep(200),
+    "sweep96_ragged_cols": lambda: wl.sweep(96, nterms=101),
+    "hubbard8x8": lambda: wl.hubbard24(False, l=8),
+    "hubbard12x12_TI": lambda: wl.hubbard24(True, l=12),
+    "hubbard8x8_TI_bath": lambda: wl.hubbard24(True, fit_imp_bath=True, l=8),
+    "polyyne_like": wl.polyyne_like,
+    "hydrogen_like": wl.hydrogen_like,
+    "odd_sizes": lambda: wl.make_workload("odd", 67, 23, [6, 1, 5, 2, 9, 3]),
+    "bath_mixed": lambda: wl.make_workload("bath", 50, 21, [3, 4, 2, 5], fit_imp_bath=True),
+    "one_occupied": lambda: wl.make_workload("one_occ", 12, 1, [4, 4, 4]),
+    "one_virtual": lambda: wl.make_workload("one_virt", 12, 11, [4, 4, 4]),
+}
+
+
+@pytest.mark.parametrize("kernel", list(KERNELS))
+@pytest.mark.parametrize("shape", list(SHAPES))
+def test_jacobian_matches_oracle_on_same_orbitals(shape, kernel):
+    w = SHAPES[shape]()
+    jac, c, e, d, used = run_plan(w, KERNELS[kernel])
+    ref = oracle_jac(w, c, e)
+    assert jac.shape == (w.nresid, w.nterms)
+    assert np.abs(jac - ref).max() <= TOL
+    # eigenvalues / 1-RDM blocks from the device eigensolver agree with LAPACK
+    e_ref, c_ref = ro.eigh_sorted(w.h0)
+    assert np.abs(e - e_ref).max() < 1e-11
+    co = c_ref[:, :w.num_pairs]
+    dfull = 2.0 * co @ co.T
+    if w.rows is not None:
+        blocks = [w.rows[a:b] @ dfull @ w.rows[a:b].T for a, b in zip(w.row_start[:-1], w.row_start[1:])]
+    else:
+        blocks = [dfull[np.ix_(w.row_idx[a:b], w.row_idx[a:b])] for a, b in zip(w.row_start[:-1], w.row_start[1:])]
+    dref = np.concatenate([b.reshape(-1, order="F") for b in blocks])
+    assert np.abs(d - dref).max() < 1e-11
+
+
+@pytest.mark.parametrize("kernel", list(KERNELS))
+def test_from_given_orbitals_and_column_slices(kernel):
+    w = wl.sweep(120)
+    e, c = ro.eigh_sorted(w.h0)
+    full, *_ = run_plan(w, KERNELS[kernel], from_orbitals=(c, e))
+    ref = oracle_jac(w, c, e)
+    assert np.abs(full - ref).max() <= TOL
+    # column sharding: any slice equals the same columns of the full Jacobian, bit for bit
+    for lo, hi in ((0, 1), (7, 133), (150, 300), (299, 300), (40, 40)):
+        part, *_ = run_plan(w, KERNELS[kernel], from_orbitals=(c, e), cols=(lo, hi))
+        assert part.shape == (w.nresid, hi - lo)
+        assert np.array_equal(part, full[:, lo:hi])
+
+
+def test_sn2_like_sampled_columns():
+    w = wl.sn2_like()
+    e, c = ro.eigh_sorted(w.h0)
+    cols = (2000, 2040)
+    part, *_ = run_plan(w, _lib.KERNEL_AUTO, from_orbitals=(c, e), cols=cols)
+    s = w.h1start
+    ref = ro.jacobian_from_orbitals(c, e, w.num_pairs, s[cols[0]:cols[1] + 1] - s[cols[0]],
+                                    w.h1row[s[cols[0]]:s[cols[1]]], w.h1col[s[cols[0]]:s[cols[1]]],
+                                    w.row_start, w.rows, w.row_idx)
+    assert np.abs(part - ref).max() <= TOL
+
+
+def test_invariants_large():
+    """Size-independent properties at a size the CPU oracle does not reach in seconds."""
+    w = wl.sweep(1000, nterms=600)
+    a, c, e, d, used_a = run_plan(w, _lib.KERNEL_AUTO)
+    b, *_ = run_plan(w, _lib.KERNEL_GENERAL, from_orbitals=(c, e))
+    assert np.abs(a - b).max() <= TOL           # two independent kernels agree
+    q = w.nresid
+    jac = a
+    # each 4x4 block is symmetric and the full dD_p is traceless: with fragments tiling all sites,
+    # the sum of the diagonal entries over all blocks vanishes
+    blocks = jac.reshape(4, 4, w.norb // 4, w.nterms, order="F")
+    assert np.abs(blocks - blocks.transpose(1, 0, 2, 3)).max() == 0.0
+    tr = np.einsum("aafp->p", blocks)
+    assert np.abs(tr).max() < 1e-11
+    # Gram symmetry of the static response function: rows (f;a,b) and columns p=(g;c<=d) index the
+    # same operator pairs; the column operator is E_cd+E_dc = (2-delta_cd) x the row operator.
+    pair_rows, scale = [], []
+    for f in range(w.norb // 4):
+        for r in range(4):
+            for cc in range(r, 4):
+                pair_rows.append(16 * f + r + 4 * cc)
+                scale.append(1.0 if r == cc else 0.5)
+    sq = jac[np.array(pair_rows[:w.nterms]), :] * np.array(scale[:w.nterms])[None, :]
+    assert np.abs(sq - sq.T).max() < 1e-11
+
+
+def test_linearity_in_perturbation():
+    """dD is linear in H1: a TI perturbation equals the sum of its per-cell perturbations."""
+    l = 8
+    wt = wl.hubbard24(True, l=l)
+    wn = wl.hubbard24(False, l=l)
+    e, c = ro.eigh_sorted(wt.h0)
+    # rows: fragment 0 only, in both
+    wn_rows = wl.Workload(**{**wn.__dict__})
+    wn_rows.row_start = wt.row_start
+    wn_rows.row_idx = wt.row_idx
+    jt, *_ = run_plan(wt, _lib.KERNEL_AUTO, from_orbitals=(c, e))
+    jn, *_ = run_plan(wn_rows, _lib.KERNEL_AUTO, from_orbitals=(c, e))
+    ncell = l * l // 4
+    summed = jn.reshape(16, ncell, 10).sum(axis=1)
+    assert np.abs(jt - summed).max() <= TOL
+
+
+def test_gap_error_is_reported():
+    w = wl.sweep(16)
+    h0 = np.zeros((16, 16))    # fully degenerate: no HOMO-LUMO gap
+    plan = _lib.Plan(w.norb, w.num_pairs, w.h1start, w.h1row, w.h1col, w.row_start, w.rows, w.row_idx)
+    with pytest.raises(_lib.QcdmetError) as ei:
+        plan.set_h0(h0)
+    assert ei.value.code == -6
+    with pytest.raises(_lib.QcdmetError) as ei:
+        plan.compute()
+    assert ei.value.code == -5
+    plan.close()
+
+
+class Ints:
+    TI_OK = True
+    ERIinMEM = False
+
+    def __init__(self, fock, nelec):
+        self._f, self.Norbs, self.Nelec = np.asarray(fock), fock.shape[0], nelec
+
+    def loc_rhf_fock(self):
+        return self._f
+
+    def loc_oei(self):
+        return self._f
+
+
+@pytest.mark.parametrize("case", ["imp_only", "imp_bath", "ti_bath"])
+def test_dmet_class_jacobian_and_gradient(case):
+    """dmet.rdm_differences_derivative (reference name/shape) against the oracle's restatement of
+    src/dmet.py:477-525, at a non-zero umat, plus the verify_gradient check of src/dmet.py:527-539."""
+    w = {"imp_only": lambda: wl.make_workload("m", 40, 17, [4, 6, 3, 5]),
+         "imp_bath": lambda: wl.make_workload("b", 36, 15, [3, 4, 2], fit_imp_bath=True),
+         "ti_bath": lambda: wl.hubbard24(True, fit_imp_bath=True, l=6)}[case]()
+    d = dmet_mod.dmet(Ints(w.h0, 2 * w.num_pairs), w.imp_clust, w.trans_inv, fitImpBath=w.fit_imp_bath)
+    if w.fit_imp_bath:
+        d.dmetOrbs = w.dmet_orbs
+    rng = np.random.default_rng(5)
+    nfit = len(d.imp_size)
+    sizes = [b.shape[1] for b in w.dmet_orbs] if w.fit_imp_bath else [2 * int(m) for m in d.imp_size]
+    d.imp_1RDM = [(lambda a: a + a.T)(rng.standard_normal((s, s))) for s in sizes[:nfit]]
+    x = rng.standard_normal(d.helper.Nterms) * 0.02
+    jac = d.rdm_differences_derivative(x)
+    ref = ro.rdm_differences_derivative(w.h0, x, w.num_pairs, w.imp_clust, w.trans_inv, w.fit_imp_bath, w.dmet_orbs)
+    assert jac.shape == ref.shape
+    assert np.abs(jac - ref).max() <= TOL
+    diff, norm = d.verify_gradient(x)
+    assert diff < 1e-4 * max(norm, 1.0)
+    assert d.time_grad > 0.0
+
+
+def test_helper_full_response_api():
+    w = wl.make_workload("m", 24, 10, [4, 4, 4])
+    d = dmet_mod.dmet(Ints(w.h0, 20), w.imp_clust, False, fitImpBath=False)
+    resp = d.helper.construct1RDM_response(False, np.zeros((24, 24)), None)
+    ref, _ = ro.rhf_response(24, w.nterms, 10, w.h1start, w.h1row, w.h1col, w.h0)
+    assert resp.shape == (w.nterms, 24, 24)
+    assert np.abs(resp - ref).max() <= TOL
+    resp2 = d.helper.construct1RDM_loc_response(False, np.zeros((24, 24)), None)
+    assert np.array_equal(resp, resp2)

@@ -1,0 +1,72 @@
+"""CPU tests of the host-side mirror of qcdmethelper / dmet (no device needed)."""
+import numpy as np
+
+from oracle import response_oracle as ro
+from qcdmet_b200 import dmet as dmet_mod, qcdmethelper as helper_mod, workloads as wl
+
+
+class Ints:
+    """Minimal duck-type of theLocalIntegrals for this path."""
+    TI_OK = True
+    ERIinMEM = False
+
+    def __init__(self, fock, nelec):
+        self._f = np.asarray(fock)
+        self.Norbs = self._f.shape[0]
+        self.Nelec = nelec
+
+    def loc_rhf_fock(self):
+        return self._f
+
+    def loc_oei(self):
+        return self._f
+
+
+def make_dmet(w, **kw):
+    return dmet_mod.dmet(Ints(w.h0, 2 * w.num_pairs), w.imp_clust, w.trans_inv, fitImpBath=w.fit_imp_bath, **kw)
+
+
+def test_dmet_parameter_lists_match_oracle():
+    for w in (wl.sweep(16), wl.make_workload("m", 20, 8, [3, 5, 2]), wl.hydrogen_like(),
+              wl.hubbard24(True, l=4)):
+        d = make_dmet(w)
+        assert (d.helper.H1start == w.h1start).all()
+        assert (d.helper.H1row == w.h1row).all() and (d.helper.H1col == w.h1col).all()
+        imp_size = ro.make_imp_size(w.imp_clust, w.trans_inv)
+        assert (d.imp_size == imp_size).all()
+        assert (d.mask == ro.make_mask(w.norb, imp_size)).all()
+        x = np.linspace(-1, 1, d.helper.Nterms)
+        assert np.array_equal(d.flat2square(x), ro.flat2square(x, w.norb, d.mask, imp_size, w.trans_inv))
+        assert np.allclose(d.square2flat(d.flat2square(x)), x)
+
+
+def test_helper_accepts_dense_and_sparse_lists():
+    w = wl.make_workload("m", 12, 5, [3, 4])
+    imp_size = ro.make_imp_size(w.imp_clust, False)
+    dense = ro.makelist_h1(12, imp_size, False)
+    h_dense = helper_mod.qcdmethelper(Ints(w.h0, 10), dense, False, None)
+    h_sparse = helper_mod.qcdmethelper(Ints(w.h0, 10), (w.h1start, w.h1row, w.h1col), False, None)
+    for a, b in ((h_dense.H1start, h_sparse.H1start), (h_dense.H1row, h_sparse.H1row),
+                 (h_dense.H1col, h_sparse.H1col)):
+        assert a.dtype == np.int32 and (a == b).all()
+    assert h_dense.Nterms == w.nterms and h_dense.numPairs == 5
+    assert np.allclose(h_dense.construct1RDM_loc(False, np.zeros((12, 12))),
+                       ro.construct1rdm_base(w.h0, 5))
+
+
+def test_fragment_rows_and_residual():
+    w = wl.make_workload("m", 20, 8, [3, 5, 2])
+    d = make_dmet(w)
+    rs, rows, idx = d._fragment_rows()
+    assert rows is None and (rs == w.row_start).all() and (idx == w.row_idx).all()
+    rng = np.random.default_rng(0)
+    d.imp_1RDM = [rng.standard_normal((2 * m, 2 * m)) for m in (3, 5, 2)]
+    x = rng.standard_normal(d.helper.Nterms) * 0.1
+    r = d.rdm_differences(x)
+    r_ref = ro.rdm_differences(w.h0, x, w.num_pairs, w.imp_clust, False, False, d.imp_1RDM)
+    assert np.abs(r - r_ref).max() < 1e-13
+    wb = wl.make_workload("b", 16, 6, [2, 3], fit_imp_bath=True)
+    db = make_dmet(wb)
+    db.dmetOrbs = wb.dmet_orbs
+    rs, rows, idx = db._fragment_rows()
+    assert idx is None and np.array_equal(rows, wb.rows) and (rs == wb.row_start).all()
