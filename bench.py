@@ -1,0 +1,376 @@
+#!/usr/bin/env python
+"""bench.py -- umat-fit Jacobian throughput (columns/s) on N B200s, vs the reference on host cores.
+
+    python bench.py --gpus N --steps K --warmup W                (this framework)
+    python bench.py --impl reference --gpus N --steps K --warmup W    (reference CPU kernel)
+
+A step = one full (Q, P) Jacobian of the synthetic response sweep: Norb orbitals,
+Nocc = Norb/2, 4-site fragments tiling all sites, P = 2.5 Norb perturbations; default Norb = 4000,
+P = 10^4 (BASELINE.json north_star target).  `value` = columns/s with (C, e), perturbation list and
+fragment rows resident in HBM (eigensolve excluded, as the metric defines); `e2e` = the same through
+the reference-facing host API (H0 on the host -> H2D, cuSOLVER syevd, kernels, D2H of J).
+At N > 1 (torchrun) the columns are sharded over the ranks (strong scaling: the Jacobian is fixed)
+and the slices are all-gathered with NCCL inside the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "umat_jacobian_columns_per_s"
+UNIT = "columns/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--norb", type=int, default=int(os.environ.get("QCDMET_BENCH_NORB", 4000)))
+    ap.add_argument("--nterms", type=int, default=None, help="default 2.5*norb")
+    ap.add_argument("--kernel", default="auto", choices=["auto", "general", "dmma"])
+    ap.add_argument("--cpu-sample-cols", type=int, default=None)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--check-cols", type=int, default=8, help="columns checked against the oracle (0 = off)")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) >= 7:
+                self.rows.append(parts)
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1])); pw.append(float(r[2]))
+            except ValueError:
+                continue
+            for n, val in zip(names, r[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------
+# peaks
+# ------------------------------------------------------------------------------------------
+def fp64_peak():
+    """FP64 ceiling for the roofline.  MEASURED_PEAKS.json (driver-written) carries only HBM and
+    bf16; the FP64 DMMA ceiling is measured by tools/fp64_peaks.cu on this pool's B200 and kept in
+    profiles/fp64_peaks.json.  Fallback: 37 TFLOP/s (148 SMs x 64 FP64 FMA/clk x 1.965 GHz)."""
+    path = os.path.join(ROOT, "profiles", "fp64_peaks.json")
+    try:
+        d = json.load(open(path))
+        return float(d["dmma_tflops_sustained"]), float(d.get("dmma_tflops_w8", 0.0)), "measured (profiles/fp64_peaks.json: DMMA.8x8x4 issue rate, sustained)"
+    except (OSError, KeyError, ValueError):
+        return 37.2, 37.2, "fallback (148 SM x 64 DFMA/clk x 1.965 GHz; profiles/fp64_peaks.json absent)"
+
+
+# ------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the UNMODIFIED reference kernel (oracle/_ref) on host cores
+# ------------------------------------------------------------------------------------------
+_T_EIG = {}
+
+
+def cpu_reference_rate(w, sample_cols, repeats=1):
+    """columns/s of lib/rhf_response.cc on the host: T(P_cpu) - T(0) isolates the response loop
+    from dsyev (the Nterms = 0 call is legal)."""
+    from oracle import ref_loader
+    if not ref_loader.available("mkl"):
+        return None
+    cores = os.cpu_count() or 1
+    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    sample_cols = min(sample_cols, w.nterms)
+    hs = w.h1start[:sample_cols + 1]
+    hr, hc = w.h1row[:hs[-1]], w.h1col[:hs[-1]]
+    if w.norb not in _T_EIG:       # the Nterms = 0 call: dsyev + 1-RDM only (measured once)
+        small = np.diag(np.arange(8.0))
+        ref_loader.rhf_response(8, 4, hs[:1], hr[:0], hc[:0], small, "mkl")   # library/thread-pool warm-up
+        best0 = None
+        for _ in range(2 if w.norb <= 2000 else 1):
+            t0 = time.perf_counter()
+            ref_loader.rhf_response(w.norb, w.num_pairs, hs[:1], hr[:0], hc[:0], w.h0, "mkl")
+            t = time.perf_counter() - t0
+            best0 = t if best0 is None else min(best0, t)
+        _T_EIG[w.norb] = best0
+    t_eig = _T_EIG[w.norb]
+    best = None
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        ref_loader.rhf_response(w.norb, w.num_pairs, hs, hr, hc, w.h0, "mkl")
+        t = time.perf_counter() - t0
+        best = t if best is None else min(best, t)
+    dt = max(best - t_eig, 1e-9)
+    return {"value": sample_cols / dt, "unit": UNIT, "cores": cores, "kind": "reference",
+            "sample": f"first {sample_cols} of {w.nterms} columns at Norb={w.norb}; T(P)-T(0), "
+                      f"dsyev+1RDM T(0)={t_eig:.2f}s excluded; MKL (torch) build of lib/rhf_response.cc, "
+                      f"OMP_NUM_THREADS={os.environ['OMP_NUM_THREADS']}",
+            "eigensolve_s": t_eig, "response_s": dt}
+
+
+def default_sample_cols(norb):
+    cores = os.cpu_count() or 1
+    # about 10-30 s of CPU work: reference cost 1.5 N^3 flop/column (a5+a6), ~25 GF/s per core assumed
+    per_col = 1.5 * norb ** 3 / (25e9 * cores)
+    cols = int(max(cores, min(20.0 / max(per_col, 1e-9), 2048)))
+    cols = max(cores, cols // cores * cores)
+    while norb * norb * cols >= 2 ** 31 or 8.0 * norb * norb * cols > 8e9:
+        cols -= cores
+    return max(cols, 1)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    from qcdmet_b200 import workloads
+    w = workloads.sweep(args.norb, args.nterms)
+    cols = args.cpu_sample_cols or default_sample_cols(args.norb)
+    rates = []
+    info = None
+    warm = min(args.warmup, 1)    # each call is tens of seconds of CPU work: one warm-up is enough
+    for i in range(warm + args.steps):
+        info = cpu_reference_rate(w, cols)
+        if info is None:
+            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libqcdmet_ref_mkl.so not built"}))
+            return
+        if i >= warm:
+            rates.append(info)
+    cols = min(cols, w.nterms)
+    tot_cols = cols * len(rates)
+    tot_t = sum(r["response_s"] for r in rates)
+    value = tot_cols / tot_t
+    info = dict(info, value=value)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 0,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / len(rates),
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": f"response sweep Norb={w.norb} Nocc={w.num_pairs} P={w.nterms} "
+                                   f"(4-site fragments, Q={w.nresid})", "sample_cols_per_step": cols},
+            "cpu_baseline": info,
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------
+# this framework
+# ------------------------------------------------------------------------------------------
+class DevArray:
+    """__cuda_array_interface__ view of a device pointer owned by the plan (for torch/NCCL)."""
+
+    def __init__(self, ptr, nelem):
+        self.__cuda_array_interface__ = {"shape": (nelem,), "typestr": "<f8", "data": (ptr, False),
+                                         "version": 2, "strides": None}
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from qcdmet_b200 import _lib, workloads
+
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+
+    w = workloads.sweep(args.norb, args.nterms)
+    P, Q = w.nterms, w.nresid
+    # column shard, aligned to whole fragments (10 parameters each) so the ranks do equal work
+    per = -(-(P // 10) // world) * 10 if P % 10 == 0 else -(-P // world)
+    lo, hi = min(rank * per, P), min((rank + 1) * per, P)
+    assert world == 1 or per * world == P, "bench shards need P divisible into equal whole-fragment slices"
+
+    e, c = np.linalg.eigh(w.h0)     # setup only: the metric takes (C, e) as given (eigensolve excluded)
+    plan = _lib.Plan(w.norb, w.num_pairs, w.h1start, w.h1row, w.h1col, w.row_start, w.rows, w.row_idx,
+                     device=local)
+    plan.set_kernel({"auto": _lib.KERNEL_AUTO, "general": _lib.KERNEL_GENERAL, "dmma": _lib.KERNEL_DMMA}[args.kernel])
+    plan.set_columns(lo, hi)
+    plan.set_orbitals(c, e)
+
+    gathered = None
+    if world > 1:
+        gathered = torch.empty(world * per * Q, dtype=torch.float64, device="cuda")
+    flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device="cuda")
+
+    def step():
+        flush.zero_()                       # evict L2 between steps (256 MB > 126 MB L2)
+        plan.compute()
+        if world > 1:
+            mine = torch.as_tensor(DevArray(plan.device_ptr(), per * Q), device="cuda")
+            dist.all_gather_into_tensor(gathered, mine)
+
+    if world > 1:
+        # slices are padded to `per` columns for the collective
+        plan.set_columns(lo, hi)
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kernel_ms = []
+    torch.cuda.synchronize()
+    ev0.record()
+    for _ in range(args.steps):
+        step()
+    ev1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if rank == 0 else None
+    # dominant kernel: events recorded by the library on the launching stream around that launch
+    for _ in range(max(1, min(args.steps, 3))):
+        flush.zero_()
+        plan.compute()
+        plan.sync()
+        kernel_ms.append(plan.kernel_time_ms())
+    k_ms = float(np.mean(kernel_ms))
+    flops = plan.flops
+    launches = plan.launches
+    kernel_used = plan.kernel_used
+    if world > 1:
+        t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    value = P / (ms_step * 1e-3)
+
+    # parity gate on a few columns (oracle as the checker only)
+    check = None
+    if rank == 0 and args.check_cols > 0:
+        from oracle import response_oracle as ro
+        ncheck = min(args.check_cols, hi - lo)
+        jac = plan.jacobian()
+        ref = ro.jacobian_from_orbitals(c, e, w.num_pairs, w.h1start[:ncheck + 1], w.h1row[:w.h1start[ncheck]],
+                                        w.h1col[:w.h1start[ncheck]], w.row_start, w.rows, w.row_idx)
+        check = float(np.abs(jac[:, :ncheck] - ref).max())
+
+    # end to end through the reference-facing host API (rank-local shard; host buffers)
+    e2e = None
+    if not args.no_e2e:
+        h0_pinned = torch.from_numpy(np.ascontiguousarray(w.h0)).pin_memory()
+        out_pinned = torch.empty(Q * max(hi - lo, 1), dtype=torch.float64).pin_memory()
+        h0_np = h0_pinned.numpy()
+        out_np = out_pinned.numpy()[:Q * (hi - lo)].reshape((Q, hi - lo), order="F")
+
+        def e2e_step():
+            plan.set_h0(h0_np)              # H2D + cuSOLVER syevd + panels
+            plan.compute()
+            plan.jacobian(out=out_np)       # D2H (blocking)
+
+        for _ in range(min(args.warmup, 2)):
+            e2e_step()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        nst = max(1, min(args.steps, 3))
+        t0 = time.perf_counter()
+        for _ in range(nst):
+            e2e_step()
+        torch.cuda.synchronize()
+        t_e2e = (time.perf_counter() - t0) / nst
+        if world > 1:
+            t = torch.tensor([t_e2e], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            t_e2e = float(t.item())
+        e2e = {"value": P / t_e2e, "unit": UNIT, "h2d_bytes_per_step": int(8 * w.norb * w.norb),
+               "d2h_bytes_per_step": int(8 * Q * (hi - lo)), "ms_per_step": 1e3 * t_e2e,
+               "includes": "H2D of H0 from pinned host memory, cuSOLVER syevd, panel build, Jacobian kernels, "
+                           "D2H of the rank's (Q x P/N) slice into pinned host memory"}
+
+    if rank == 0:
+        peak, peak_burst, peak_src = fp64_peak()
+        achieved = flops / (k_ms * 1e-3) * 1e-12 if k_ms > 0 else None
+        cpu = None
+        if not args.no_cpu_baseline:
+            cpu = cpu_reference_rate(w, args.cpu_sample_cols or default_sample_cols(args.norb))
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"response sweep Norb={w.norb} Nocc={w.num_pairs} P={P} "
+                                   f"(4-site fragments, impurity-only rows, Q={Q})",
+                       "kernel": {1: "general", 2: "dmma"}.get(kernel_used, str(kernel_used)),
+                       "sharding": f"{world} x {per} columns (whole fragments), NCCL all-gather of the slices inside the timed region" if world > 1 else "single GPU",
+                       "l2": "256 MB buffer zeroed between steps (L2 flush), inside the timed region"},
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                         "frac": (achieved / peak) if achieved else None, "traffic": None,
+                         "kernel_ms": k_ms, "flops_per_launch": flops,
+                         "peak_source": peak_src,
+                         "note": "FP64 flops actually executed by the dominant kernel on this rank / its CUDA-event time"},
+            "cpu_baseline": cpu,
+            "e2e": e2e,
+            "gpu_launches": int(launches * args.steps),
+            "clocks": clocks,
+            "parity_check_max_abs_err": check,
+        }
+        print(json.dumps(line))
+    plan.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()
