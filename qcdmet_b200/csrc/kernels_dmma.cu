@@ -1,13 +1,632 @@
-// kernels_dmma.cu -- placeholder until the site-factorised DMMA kernel lands.
+// kernels_dmma.cu -- site-factorised FP64 tensor-core (DMMA.8x8x4) Jacobian kernel for sm_100a.
+//
+// Mathematics (SURVEY.md 8a "mathematical statement", re-associated; exact, no approximation):
+//   M_r[a,o]    = sum_v PV[a,v] * Cv[r,v] * W[v,o]            W[v,o] = 1/(e_o - e_v)
+//   N_r[a;c,b]  = sum_o M_r[a,o] * Co[c,o] * PO[b,o]          b in the fragment of row a
+//   G_p[a,b]    = sum_{(r,c) in H1_p} N_r[a;c,b]
+//   J[(f;a,b),p]= 2 (G_p[a,b] + G_p[b,a])
+// M_r is shared by every perturbation that has an element in row r, so the dominant GEMM runs
+// once per *site* (N of them) instead of once per perturbation (P = N(m+1)/2): 2 S nv no flop per
+// site.  This replaces lib/rhf_response.cc:82-108 + src/dmet.py:496-520 for perturbation lists
+// whose connected components (perturbations sharing sites) have <= 4 sites and fragments of <= 4
+// rows -- the non-translation-invariant 2x2 / 4-site DMET shape of the north-star workload.
+//
+// One CTA = (component g of <= 4 sites) x (a-tile of 32 fragment rows): a 128 x no output panel
+// M[(r,a), o], produced 128 columns at a time:
+//   * B operand: W, pre-tiled in HBM in DMMA fragment order, one 16 KB TMA bulk copy per stage
+//   * A operand: (PV[a,:] * Cv[r,:]) built in registers from two TMA-staged panels (4 KB + 512 B)
+//   * 8 consumer warps (4 sites x 2 column halves), warp tile 32 x 64, 32 DMMA.8x8x4 per k4 step,
+//     accumulators in registers (FP64 has no tcgen05/TMEM path: tcgen05.mma has no f64 kind)
+//   * 1 producer warp, 4-stage mbarrier full/empty pipeline (cp.async.bulk -> UBLKCP)
+//   * epilogue per 128-column tile: accumulators x Co[c,o] x PO[b,o] on the FP64 pipe, warp-shuffle
+//     reduction over the 4 lanes of a row, running sums in shared memory; after the last tile the
+//     CTA assembles G_p, symmetrises, and stores its (32 rows x 4) x (<=16 columns) patch of J with
+//     coalesced stores.  No atomics: every J element is owned by exactly one CTA.
 #include "common.cuh"
+#include <algorithm>
+#include <cstdint>
+#include <map>
+#include <numeric>
+
 namespace qcdmet {
-struct DmmaPlanData {};
-bool dmma_eligible(int, int, int, const int *, const int *, const int *, const int *, const int *,
-                   bool, std::string *why) { if (why) *why = "not built"; return false; }
-int dmma_plan_build(DmmaPlanData **out, int, int, int, int, const int *, const int *, const int *,
-                    const int *, const int *) { *out = nullptr; return QCDMET_OK; }
-void dmma_plan_free(DmmaPlanData *) {}
-int dmma_prepare_orbitals(DmmaPlanData *, const JacView &, cudaStream_t) { return QCDMET_OK; }
-int launch_jacobian_dmma(DmmaPlanData *, const JacView &, cudaStream_t, int *, double *, cudaEvent_t, cudaEvent_t)
-{ set_error("DMMA kernel not built"); return QCDMET_E_STATE; }
+
+namespace {
+
+constexpr int BN = 128;       // occupied orbitals per output tile
+constexpr int KC = 16;        // virtual orbitals per pipeline stage
+constexpr int STAGES = 4;
+constexpr int RT = 4;         // site slots per component  (= M-warps)
+constexpr int AT = 32;        // row slots per a-tile
+constexpr int RF = 4;         // max rows per fragment
+constexpr int MAXP = 16;      // max perturbations per component
+constexpr int MAXE = 4;       // max elements per perturbation
+constexpr int NCONS = 256;    // consumer threads (8 warps)
+constexpr int NTHREADS = NCONS + 32;
+constexpr int PSTRIDE = BN + 8;   // POS row stride in doubles (bank-conflict padding)
+
+constexpr int W_STAGE = KC * BN;          // doubles
+constexpr int PV_STAGE = KC * AT;
+constexpr int CV_STAGE = KC * RT;
+constexpr int STAGE_DOUBLES = W_STAGE + PV_STAGE + CV_STAGE;
+constexpr uint32_t STAGE_BYTES = STAGE_DOUBLES * 8;
+
+constexpr int SM_STAGE_OFF = 0;
+constexpr int SM_POS_OFF = SM_STAGE_OFF + STAGES * STAGE_DOUBLES * 8;
+constexpr int SM_COS_OFF = SM_POS_OFF + (AT + 1) * PSTRIDE * 8;
+constexpr int SM_NS_OFF = SM_COS_OFF + RT * BN * 8;
+constexpr int SM_BAR_OFF = SM_NS_OFF + 2 * 128 * 16 * 8;
+constexpr int SM_TAB_OFF = SM_BAR_OFF + 2 * STAGES * 8;
+// tables: qrow[32] (8B) | tileRow[32] (4B) | compSites[4] (4B) | compP[16] (4B) | partner[32][4] (1B)
+//         | self[32] (1B) | compEnt[16][4] (1B)
+constexpr int TAB_QROW = 0;
+constexpr int TAB_TROW = TAB_QROW + AT * 8;
+constexpr int TAB_CSITE = TAB_TROW + AT * 4;
+constexpr int TAB_CP = TAB_CSITE + RT * 4;
+constexpr int TAB_PARTNER = TAB_CP + MAXP * 4;
+constexpr int TAB_SELF = TAB_PARTNER + AT * RF;
+constexpr int TAB_CENT = TAB_SELF + AT;
+constexpr int TAB_BYTES = TAB_CENT + MAXP * MAXE;
+constexpr int SMEM_BYTES = SM_TAB_OFF + ((TAB_BYTES + 15) / 16) * 16;
+
+struct DmmaArgs {
+    int nKc, nOt, no, nv, ldo;
+    int colBegin, colEnd;
+    long long Q;
+    const double *Wt, *PVt, *CVt;
+    const double *PO, *CoT;
+    const int *launchComps;
+    const int *compSites;               // [nComp][RT]   site or -1
+    const int *compP;                   // [nComp][MAXP] perturbation index or -1
+    const unsigned char *compEnt;       // [nComp][MAXP][MAXE]  rs | cs << 4, 0xFF = none
+    const int *tileRow;                 // [nTiles][AT]  fragment-row index or -1
+    const unsigned char *tilePartner;   // [nTiles][AT][RF] slot of the j-th row of the fragment, AT = none
+    const unsigned char *tileSelf;      // [nTiles][AT]  a_loc | r_f << 4
+    const long long *tileQ;             // [nTiles][AT]  qoff[f] + a_loc
+    double *J;
+};
+
+// ------------------------------------------------------------------------------------------
+// PTX helpers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+    return (uint32_t)__cvta_generic_to_shared(p);
 }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+// 1-D TMA bulk copy global -> shared, completion on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void consumer_sync()
+{
+    asm volatile("bar.sync 1, %0;" ::"n"(NCONS) : "memory");
+}
+__device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double b)
+{
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+        : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+// ------------------------------------------------------------------------------------------
+// operand tiling (once per set of orbitals)
+// ------------------------------------------------------------------------------------------
+// Wt[(ot*nKc + kc)][k4][njp][lane][2] = W[kc*KC + k4*4 + (lane&3)][ot*BN + (2 njp + e)*8 + (lane>>2)]
+__global__ void build_wt_kernel(const double *__restrict__ e, int no, int nv, int nKc, long long total,
+                                double *__restrict__ Wt)
+{
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int within = (int)(idx % W_STAGE);
+    const long long blk = idx / W_STAGE;
+    const int ot = (int)(blk / nKc), kc = (int)(blk % nKc);
+    const int e2 = within & 1, lane = (within >> 1) & 31, njp = (within >> 6) & 7, k4 = within >> 9;
+    const int k = kc * KC + k4 * 4 + (lane & 3);
+    const int o = ot * BN + (njp * 2 + e2) * 8 + (lane >> 2);
+    Wt[idx] = (k < nv && o < no) ? 1.0 / (e[o] - e[no + k]) : 0.0;
+}
+// PVt[(tile*nKc + kc)][k4][lane][mi] = PV[tileRow[tile][mi*8 + (lane>>2)]][kc*KC + k4*4 + (lane&3)]
+__global__ void build_pvt_kernel(const double *__restrict__ PV, int ldv, int nv, int nKc,
+                                 const int *__restrict__ tileRow, long long total, double *__restrict__ PVt)
+{
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int within = (int)(idx % PV_STAGE);
+    const long long blk = idx / PV_STAGE;
+    const int tile = (int)(blk / nKc), kc = (int)(blk % nKc);
+    const int mi = within & 3, lane = (within >> 2) & 31, k4 = within >> 7;
+    const int row = tileRow[tile * AT + mi * 8 + (lane >> 2)];
+    const int k = kc * KC + k4 * 4 + (lane & 3);
+    PVt[idx] = (row >= 0 && k < nv) ? PV[(size_t)row * ldv + k] : 0.0;
+}
+// CVt[(comp*nKc + kc)][r][kk] = CvT[compSites[comp][r]][kc*KC + kk]
+__global__ void build_cvt_kernel(const double *__restrict__ CvT, int ldv, int nv, int nKc,
+                                 const int *__restrict__ compSites, long long total, double *__restrict__ CVt)
+{
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int within = (int)(idx % CV_STAGE);
+    const long long blk = idx / CV_STAGE;
+    const int comp = (int)(blk / nKc), kc = (int)(blk % nKc);
+    const int kk = within % KC, r = within / KC;
+    const int site = compSites[comp * RT + r];
+    const int k = kc * KC + kk;
+    CVt[idx] = (site >= 0 && k < nv) ? CvT[(size_t)site * ldv + k] : 0.0;
+}
+
+// ------------------------------------------------------------------------------------------
+// the kernel
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NTHREADS, 1) jac_dmma_kernel(const DmmaArgs g)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    double *stageBase = reinterpret_cast<double *>(smem + SM_STAGE_OFF);
+    double *POS = reinterpret_cast<double *>(smem + SM_POS_OFF);
+    double *CoS = reinterpret_cast<double *>(smem + SM_COS_OFF);
+    double *Ns = reinterpret_cast<double *>(smem + SM_NS_OFF);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + SM_BAR_OFF);
+    unsigned char *tab = smem + SM_TAB_OFF;
+    long long *qrow = reinterpret_cast<long long *>(tab + TAB_QROW);
+    int *trow = reinterpret_cast<int *>(tab + TAB_TROW);
+    int *csite = reinterpret_cast<int *>(tab + TAB_CSITE);
+    int *cp = reinterpret_cast<int *>(tab + TAB_CP);
+    unsigned char *partner = tab + TAB_PARTNER;
+    unsigned char *selfi = tab + TAB_SELF;
+    unsigned char *cent = tab + TAB_CENT;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int comp = g.launchComps[blockIdx.x];
+    const int tile = blockIdx.y;
+    const int nKc = g.nKc, nOt = g.nOt;
+
+    // ---- set-up: barriers, tables, zeroed accumulators
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(smem_u32(&bars[s]), 1);              // full: producer's expect_tx arrival
+            mbar_init(smem_u32(&bars[STAGES + s]), 8);     // empty: one arrival per consumer warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (tid < AT) {
+        qrow[tid] = g.tileQ[tile * AT + tid];
+        trow[tid] = g.tileRow[tile * AT + tid];
+        selfi[tid] = g.tileSelf[tile * AT + tid];
+    }
+    if (tid < AT * RF) partner[tid] = g.tilePartner[tile * AT * RF + tid];
+    if (tid < RT) csite[tid] = g.compSites[comp * RT + tid];
+    if (tid < MAXP) cp[tid] = g.compP[comp * MAXP + tid];
+    if (tid < MAXP * MAXE) cent[tid] = g.compEnt[comp * MAXP * MAXE + tid];
+    for (int i = tid; i < 2 * 128 * 16; i += NTHREADS) Ns[i] = 0.0;
+    for (int i = tid; i < PSTRIDE; i += NTHREADS) POS[AT * PSTRIDE + i] = 0.0;   // the "no partner" row
+    __syncthreads();
+
+    if (warp == 8) {
+        // ================= producer warp: one elected lane drives the TMA pipeline =================
+        if (lane == 0) {
+            const double *pvsrc = g.PVt + (size_t)tile * nKc * PV_STAGE;
+            const double *cvsrc = g.CVt + (size_t)comp * nKc * CV_STAGE;
+            int it = 0;
+            for (int ot = 0; ot < nOt; ++ot) {
+                const double *wsrc = g.Wt + (size_t)ot * nKc * W_STAGE;
+                for (int kc = 0; kc < nKc; ++kc, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t full = smem_u32(&bars[s]), empty = smem_u32(&bars[STAGES + s]);
+                    mbar_wait(empty, ((it / STAGES) & 1) ^ 1);
+                    mbar_expect_tx(full, STAGE_BYTES);
+                    double *dst = stageBase + (size_t)s * STAGE_DOUBLES;
+                    tma_bulk_g2s(smem_u32(dst), wsrc + (size_t)kc * W_STAGE, W_STAGE * 8, full);
+                    tma_bulk_g2s(smem_u32(dst + W_STAGE), pvsrc + (size_t)kc * PV_STAGE, PV_STAGE * 8, full);
+                    tma_bulk_g2s(smem_u32(dst + W_STAGE + PV_STAGE), cvsrc + (size_t)kc * CV_STAGE, CV_STAGE * 8, full);
+                }
+            }
+        }
+        return;
+    }
+
+    // ================= consumer warps =================
+    const int warp_m = warp >> 1;     // site slot r
+    const int warp_n = warp & 1;      // 64-column half
+    const int g4 = lane >> 2, t4 = lane & 3;
+
+    double acc[4][8][2];
+    int it = 0;
+    for (int ot = 0; ot < nOt; ++ot) {
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+            for (int nj = 0; nj < 8; ++nj) { acc[mi][nj][0] = 0.0; acc[mi][nj][1] = 0.0; }
+
+        for (int kc = 0; kc < nKc; ++kc, ++it) {
+            const int s = it % STAGES;
+            mbar_wait(smem_u32(&bars[s]), (it / STAGES) & 1);
+            const double *Ws = stageBase + (size_t)s * STAGE_DOUBLES;
+            const double *PVs = Ws + W_STAGE;
+            const double *CVs = PVs + PV_STAGE + warp_m * KC;
+#pragma unroll
+            for (int k4 = 0; k4 < KC / 4; ++k4) {
+                const double2 p01 = *reinterpret_cast<const double2 *>(PVs + (k4 * 32 + lane) * 4);
+                const double2 p23 = *reinterpret_cast<const double2 *>(PVs + (k4 * 32 + lane) * 4 + 2);
+                const double cv = CVs[k4 * 4 + t4];
+                double a[4], b[8];
+                a[0] = p01.x * cv; a[1] = p01.y * cv; a[2] = p23.x * cv; a[3] = p23.y * cv;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const double2 bb = *reinterpret_cast<const double2 *>(
+                        Ws + ((k4 * 8 + warp_n * 4 + j) * 32 + lane) * 2);
+                    b[2 * j] = bb.x; b[2 * j + 1] = bb.y;
+                }
+#pragma unroll
+                for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+                    for (int nj = 0; nj < 8; ++nj) dmma884(acc[mi][nj][0], acc[mi][nj][1], a[mi], b[nj]);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&bars[STAGES + s]));
+        }
+
+        // ---- epilogue for this 128-column tile
+        consumer_sync();                              // previous tile's POS/CoS no longer read
+        {
+            const int o0 = ot * BN;
+            for (int i = tid; i < (AT + RT) * (BN / 2); i += NCONS) {
+                const int rowi = i / (BN / 2), oc = (i % (BN / 2)) * 2;
+                double2 val = make_double2(0.0, 0.0);
+                const double *src = nullptr;
+                if (rowi < AT) { const int r = trow[rowi]; if (r >= 0) src = g.PO + (size_t)r * g.ldo; }
+                else { const int sidx = csite[rowi - AT]; if (sidx >= 0) src = g.CoT + (size_t)sidx * g.ldo; }
+                if (src != nullptr && o0 + oc < g.ldo) val = *reinterpret_cast<const double2 *>(src + o0 + oc);
+                double *dst = (rowi < AT) ? (POS + rowi * PSTRIDE + oc) : (CoS + (rowi - AT) * BN + oc);
+                *reinterpret_cast<double2 *>(dst) = val;
+            }
+        }
+        consumer_sync();
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi) {
+            const int a_slot = mi * 8 + g4;
+            const double *pb[RF];
+#pragma unroll
+            for (int j = 0; j < RF; ++j) pb[j] = POS + (int)partner[a_slot * RF + j] * PSTRIDE + warp_n * 64 + t4 * 2;
+            const double *pc = CoS + warp_n * 64 + t4 * 2;
+            double nacc[RT][RF];
+#pragma unroll
+            for (int c = 0; c < RT; ++c)
+#pragma unroll
+                for (int j = 0; j < RF; ++j) nacc[c][j] = 0.0;
+#pragma unroll
+            for (int nj = 0; nj < 8; ++nj) {
+                double2 po[RF];
+#pragma unroll
+                for (int j = 0; j < RF; ++j) po[j] = *reinterpret_cast<const double2 *>(pb[j] + nj * 8);
+                const double m0 = acc[mi][nj][0], m1 = acc[mi][nj][1];
+#pragma unroll
+                for (int c = 0; c < RT; ++c) {
+                    const double2 co = *reinterpret_cast<const double2 *>(pc + c * BN + nj * 8);
+                    const double t0 = m0 * co.x, t1 = m1 * co.y;
+#pragma unroll
+                    for (int j = 0; j < RF; ++j) nacc[c][j] = fma(t0, po[j].x, fma(t1, po[j].y, nacc[c][j]));
+                }
+            }
+            // reduce over the 4 lanes that share this row; lane t4 keeps component site c == t4
+            double *dst = Ns + ((warp_n * 128 + warp_m * AT + a_slot) * 16);
+#pragma unroll
+            for (int c = 0; c < RT; ++c)
+#pragma unroll
+                for (int j = 0; j < RF; ++j) {
+                    double v = nacc[c][j];
+                    v += __shfl_xor_sync(0xffffffffu, v, 1);
+                    v += __shfl_xor_sync(0xffffffffu, v, 2);
+                    if (t4 == c) dst[c * RF + j] += v;
+                }
+        }
+    }
+
+    // ---- assemble G_p, symmetrise, store the CTA's patch of J
+    consumer_sync();
+    for (int idx = tid; idx < MAXP * AT * RF; idx += NCONS) {
+        const int pl = idx / (AT * RF), rem = idx % (AT * RF);
+        const int a_slot = rem / RF, j = rem % RF;
+        const int p = cp[pl];
+        if (p < g.colBegin || p >= g.colEnd) continue;
+        const int self = selfi[a_slot];
+        const int a_loc = self & 15, rf = self >> 4;
+        if (trow[a_slot] < 0 || j >= rf) continue;
+        const int b_slot = partner[a_slot * RF + j];
+        double gab = 0.0, gba = 0.0;
+#pragma unroll
+        for (int e = 0; e < MAXE; ++e) {
+            const unsigned char ent = cent[pl * MAXE + e];
+            if (ent == 0xFF) continue;
+            const int rs = ent & 15, cs = ent >> 4;
+            const int i1 = (rs * AT + a_slot) * 16 + cs * RF + j;
+            const int i2 = (rs * AT + b_slot) * 16 + cs * RF + a_loc;
+            gab += Ns[i1] + Ns[128 * 16 + i1];
+            gba += Ns[i2] + Ns[128 * 16 + i2];
+        }
+        g.J[(size_t)g.Q * (p - g.colBegin) + qrow[a_slot] + (long long)rf * j] = 2.0 * (gab + gba);
+    }
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+// host side: schedule (components, a-tiles), operand buffers, launch
+// ------------------------------------------------------------------------------------------
+struct DmmaPlanData {
+    int N = 0, no = 0, nv = 0, P = 0, S = 0;
+    int nComp = 0, nTiles = 0, nKc = 0, nOt = 0;
+    bool hasEmptyPerturbation = false;
+    std::vector<int> compSites, compP, compFirstP, compLastP, compNumSites;
+    std::vector<unsigned char> compEnt;
+    std::vector<int> tileRow;
+    std::vector<unsigned char> tilePartner, tileSelf;
+    std::vector<long long> tileQ;
+    std::vector<int> launchComps;
+    int launchBegin = -1, launchEnd = -1;
+    int *d_compSites = nullptr, *d_compP = nullptr, *d_tileRow = nullptr, *d_launchComps = nullptr;
+    unsigned char *d_compEnt = nullptr, *d_tilePartner = nullptr, *d_tileSelf = nullptr;
+    long long *d_tileQ = nullptr;
+    double *d_Wt = nullptr, *d_PVt = nullptr, *d_CVt = nullptr;
+    bool attrSet = false;
+};
+
+namespace {
+
+struct Schedule {
+    bool ok = false;
+    std::string why;
+    DmmaPlanData d;
+};
+
+Schedule build_schedule(int N, int no, int P, int F, const int *h1start, const int *h1row, const int *h1col,
+                        const int *rowStart)
+{
+    Schedule sc;
+    DmmaPlanData &d = sc.d;
+    d.N = N; d.no = no; d.nv = N - no; d.P = P; d.S = F > 0 ? rowStart[F] : 0;
+    if (P == 0 || d.S == 0) { sc.why = "empty problem"; return sc; }
+    // fragments: <= RF rows each, packed whole into tiles of AT row slots
+    std::vector<long long> qoff(F + 1, 0);
+    for (int f = 0; f < F; ++f) {
+        const int rf = rowStart[f + 1] - rowStart[f];
+        if (rf > RF) { sc.why = "a fragment has more than 4 rows"; return sc; }
+        qoff[f + 1] = qoff[f] + (long long)rf * rf;
+    }
+    int slot = AT;   // forces a new tile at the first fragment
+    for (int f = 0; f < F; ++f) {
+        const int rs = rowStart[f], rf = rowStart[f + 1] - rs;
+        if (rf == 0) continue;
+        if (slot + rf > AT) {
+            d.tileRow.insert(d.tileRow.end(), AT, -1);
+            d.tilePartner.insert(d.tilePartner.end(), AT * RF, (unsigned char)AT);
+            d.tileSelf.insert(d.tileSelf.end(), AT, 0);
+            d.tileQ.insert(d.tileQ.end(), AT, 0);
+            ++d.nTiles;
+            slot = 0;
+        }
+        const int base = (d.nTiles - 1) * AT;
+        for (int al = 0; al < rf; ++al) {
+            d.tileRow[base + slot + al] = rs + al;
+            d.tileSelf[base + slot + al] = (unsigned char)(al | (rf << 4));
+            d.tileQ[base + slot + al] = qoff[f] + al;
+            for (int j = 0; j < rf; ++j) d.tilePartner[(size_t)(base + slot + al) * RF + j] = (unsigned char)(slot + j);
+        }
+        slot += rf;
+    }
+    if (d.nTiles > 65535) { sc.why = "too many row tiles"; return sc; }
+    // components: perturbations connected through shared sites (union-find over sites)
+    std::vector<int> parent(N);
+    std::iota(parent.begin(), parent.end(), 0);
+    auto find = [&](int x) { while (parent[x] != x) { parent[x] = parent[parent[x]]; x = parent[x]; } return x; };
+    std::vector<char> used(N, 0);
+    for (int p = 0; p < P; ++p) {
+        const int b = h1start[p], e = h1start[p + 1];
+        if (e == b) { d.hasEmptyPerturbation = true; continue; }
+        if (e - b > MAXE) { sc.why = "a perturbation has more than 4 elements (translation-invariant list?)"; return sc; }
+        for (int k = b; k < e; ++k) {
+            used[h1row[k]] = used[h1col[k]] = 1;
+            const int ra = find(h1row[b]);
+            const int rb = find(h1row[k]);
+            if (ra != rb) parent[rb] = ra;
+            const int rc = find(h1col[k]);
+            const int rd = find(h1row[b]);
+            if (rc != rd) parent[rc] = rd;
+        }
+    }
+    std::map<int, int> compOfRoot;
+    std::vector<std::vector<int>> sites;
+    for (int i = 0; i < N; ++i) {
+        if (!used[i]) continue;
+        const int r = find(i);
+        auto itc = compOfRoot.find(r);
+        int c;
+        if (itc == compOfRoot.end()) { c = (int)sites.size(); compOfRoot[r] = c; sites.emplace_back(); }
+        else c = itc->second;
+        sites[c].push_back(i);
+        if ((int)sites[c].size() > RT) { sc.why = "perturbations couple more than 4 sites"; return sc; }
+    }
+    d.nComp = (int)sites.size();
+    d.compSites.assign((size_t)d.nComp * RT, -1);
+    d.compP.assign((size_t)d.nComp * MAXP, -1);
+    d.compEnt.assign((size_t)d.nComp * MAXP * MAXE, 0xFF);
+    d.compNumSites.assign(d.nComp, 0);
+    std::vector<int> np(d.nComp, 0);
+    for (int c = 0; c < d.nComp; ++c) {
+        d.compNumSites[c] = (int)sites[c].size();
+        for (size_t k = 0; k < sites[c].size(); ++k) d.compSites[(size_t)c * RT + k] = sites[c][k];
+    }
+    for (int p = 0; p < P; ++p) {
+        const int b = h1start[p], e = h1start[p + 1];
+        if (e == b) continue;
+        const int c = compOfRoot[find(h1row[b])];
+        if (np[c] >= MAXP) { sc.why = "more than 16 perturbations on one group of sites"; return sc; }
+        const int pl = np[c]++;
+        d.compP[(size_t)c * MAXP + pl] = p;
+        for (int k = b; k < e; ++k) {
+            int rsl = -1, csl = -1;
+            for (int q = 0; q < RT; ++q) {
+                if (d.compSites[(size_t)c * RT + q] == h1row[k]) rsl = q;
+                if (d.compSites[(size_t)c * RT + q] == h1col[k]) csl = q;
+            }
+            d.compEnt[((size_t)c * MAXP + pl) * MAXE + (k - b)] = (unsigned char)(rsl | (csl << 4));
+        }
+    }
+    d.nKc = (d.nv + KC - 1) / KC;
+    d.nOt = (d.no + BN - 1) / BN;
+    sc.ok = true;
+    return sc;
+}
+
+template <typename T>
+int upload(T **dst, const std::vector<T> &src)
+{
+    const size_t n = std::max<size_t>(src.size(), 1);
+    if (cudaMalloc((void **)dst, n * sizeof(T)) != cudaSuccess) {
+        cudaGetLastError();
+        set_error("cudaMalloc failed (DMMA schedule, %zu bytes)", n * sizeof(T));
+        return QCDMET_E_ALLOC;
+    }
+    if (!src.empty()) QC_CUDA(cudaMemcpy(*dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return QCDMET_OK;
+}
+
+}  // namespace
+
+bool dmma_eligible(int N, int P, int F, const int *h1start, const int *h1row, const int *h1col,
+                   const int *rowStart, const int *, bool, std::string *why)
+{
+    Schedule sc = build_schedule(N, N / 2 > 0 ? N / 2 : 1, P, F, h1start, h1row, h1col, rowStart);
+    if (why) *why = sc.why;
+    return sc.ok;
+}
+
+int dmma_plan_build(DmmaPlanData **out, int N, int no, int P, int F, const int *h1start, const int *h1row,
+                    const int *h1col, const int *rowStart, const int *)
+{
+    *out = nullptr;
+    Schedule sc = build_schedule(N, no, P, F, h1start, h1row, h1col, rowStart);
+    QC_CHECK(sc.ok, QCDMET_E_ARG, "DMMA kernel not eligible: %s", sc.why.c_str());
+    DmmaPlanData *d = new DmmaPlanData(std::move(sc.d));
+    int rc = QCDMET_OK;
+    if (!(rc = upload(&d->d_compSites, d->compSites)) && !(rc = upload(&d->d_compP, d->compP)) &&
+        !(rc = upload(&d->d_compEnt, d->compEnt)) && !(rc = upload(&d->d_tileRow, d->tileRow)) &&
+        !(rc = upload(&d->d_tilePartner, d->tilePartner)) && !(rc = upload(&d->d_tileSelf, d->tileSelf)) &&
+        !(rc = upload(&d->d_tileQ, d->tileQ))) {
+        std::vector<int> all(d->nComp);
+        rc = upload(&d->d_launchComps, all);
+    }
+    const size_t wt = (size_t)d->nOt * d->nKc * W_STAGE, pvt = (size_t)d->nTiles * d->nKc * PV_STAGE,
+                 cvt = (size_t)d->nComp * d->nKc * CV_STAGE;
+    if (!rc && (cudaMalloc((void **)&d->d_Wt, wt * 8) != cudaSuccess ||
+                cudaMalloc((void **)&d->d_PVt, pvt * 8) != cudaSuccess ||
+                cudaMalloc((void **)&d->d_CVt, cvt * 8) != cudaSuccess)) {
+        cudaGetLastError();
+        set_error("cudaMalloc of the tiled operand panels failed (%zu bytes)", (wt + pvt + cvt) * 8);
+        rc = QCDMET_E_ALLOC;
+    }
+    if (rc) { dmma_plan_free(d); return rc; }
+    *out = d;
+    return QCDMET_OK;
+}
+
+void dmma_plan_free(DmmaPlanData *d)
+{
+    if (!d) return;
+    cudaFree(d->d_compSites); cudaFree(d->d_compP); cudaFree(d->d_compEnt); cudaFree(d->d_tileRow);
+    cudaFree(d->d_tilePartner); cudaFree(d->d_tileSelf); cudaFree(d->d_tileQ); cudaFree(d->d_launchComps);
+    cudaFree(d->d_Wt); cudaFree(d->d_PVt); cudaFree(d->d_CVt);
+    cudaGetLastError();
+    delete d;
+}
+
+int dmma_prepare_orbitals(DmmaPlanData *d, const JacView &v, cudaStream_t st)
+{
+    const long long wt = (long long)d->nOt * d->nKc * W_STAGE, pvt = (long long)d->nTiles * d->nKc * PV_STAGE,
+                    cvt = (long long)d->nComp * d->nKc * CV_STAGE;
+    build_wt_kernel<<<(unsigned)((wt + 255) / 256), 256, 0, st>>>(v.e, v.no, v.nv, d->nKc, wt, d->d_Wt);
+    QC_CUDA(cudaGetLastError());
+    build_pvt_kernel<<<(unsigned)((pvt + 255) / 256), 256, 0, st>>>(v.PV, v.ldv, v.nv, d->nKc, d->d_tileRow, pvt, d->d_PVt);
+    QC_CUDA(cudaGetLastError());
+    build_cvt_kernel<<<(unsigned)((cvt + 255) / 256), 256, 0, st>>>(v.CvT, v.ldv, v.nv, d->nKc, d->d_compSites, cvt, d->d_CVt);
+    QC_CUDA(cudaGetLastError());
+    return QCDMET_OK;
+}
+
+int launch_jacobian_dmma(DmmaPlanData *d, const JacView &v, cudaStream_t st, int *launches, double *flops,
+                         cudaEvent_t ev0, cudaEvent_t ev1)
+{
+    *launches = 0;
+    *flops = 0.0;
+    const int ncols = v.colEnd - v.colBegin;
+    if (ncols <= 0) return QCDMET_OK;
+    if (!d->attrSet) {
+        QC_CUDA(cudaFuncSetAttribute(jac_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        d->attrSet = true;
+    }
+    if (d->launchBegin != v.colBegin || d->launchEnd != v.colEnd) {
+        d->launchComps.clear();
+        for (int c = 0; c < d->nComp; ++c) {
+            bool hit = false;
+            for (int k = 0; k < MAXP && !hit; ++k) {
+                const int p = d->compP[(size_t)c * MAXP + k];
+                hit = (p >= v.colBegin && p < v.colEnd);
+            }
+            if (hit) d->launchComps.push_back(c);
+        }
+        if (!d->launchComps.empty())
+            QC_CUDA(cudaMemcpyAsync(d->d_launchComps, d->launchComps.data(), d->launchComps.size() * sizeof(int),
+                                    cudaMemcpyHostToDevice, st));
+        d->launchBegin = v.colBegin;
+        d->launchEnd = v.colEnd;
+    }
+    if (d->hasEmptyPerturbation)
+        QC_CUDA(cudaMemsetAsync(v.J, 0, sizeof(double) * (size_t)v.Q * ncols, st));
+    if (d->launchComps.empty()) return QCDMET_OK;
+    DmmaArgs a;
+    a.nKc = d->nKc; a.nOt = d->nOt; a.no = v.no; a.nv = v.nv; a.ldo = v.ldo;
+    a.colBegin = v.colBegin; a.colEnd = v.colEnd; a.Q = v.Q;
+    a.Wt = d->d_Wt; a.PVt = d->d_PVt; a.CVt = d->d_CVt; a.PO = v.PO; a.CoT = v.CoT;
+    a.launchComps = d->d_launchComps; a.compSites = d->d_compSites; a.compP = d->d_compP;
+    a.compEnt = d->d_compEnt; a.tileRow = d->d_tileRow; a.tilePartner = d->d_tilePartner;
+    a.tileSelf = d->d_tileSelf; a.tileQ = d->d_tileQ; a.J = v.J;
+    if (ev0) QC_CUDA(cudaEventRecord(ev0, st));
+    jac_dmma_kernel<<<dim3((unsigned)d->launchComps.size(), d->nTiles), NTHREADS, SMEM_BYTES, st>>>(a);
+    QC_CUDA(cudaGetLastError());
+    if (ev1) QC_CUDA(cudaEventRecord(ev1, st));
+    *launches = 1;
+    // useful FP64 flops executed (padding excluded): mainloop 2 S nv no per site (+ 1 multiply per A
+    // element), epilogue (1 + 2 r_f) n_c flop per accumulator element
+    double sites = 0.0, epi = 0.0;
+    for (int c : d->launchComps) {
+        sites += d->compNumSites[c];
+        epi += (double)d->compNumSites[c] * d->compNumSites[c];
+    }
+    *flops = sites * 2.0 * (double)d->S * d->nv * d->no + sites * (double)d->S * d->nv * d->nOt +
+             epi * (double)d->S * d->no * (1.0 + 2.0 * RF);
+    return QCDMET_OK;
+}
+
+}  // namespace qcdmet

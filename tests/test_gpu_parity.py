@@ -13,6 +13,7 @@ from util import GOLDEN, golden_ids, load_golden
 pytestmark = pytest.mark.gpu
 TOL = 1e-10
 KERNELS = {"general": _lib.KERNEL_GENERAL, "auto": _lib.KERNEL_AUTO}
+GENERAL, DMMA = _lib.KERNEL_GENERAL, _lib.KERNEL_DMMA
 
 
 def run_plan(w, kernel, from_orbitals=None, cols=None):
@@ -105,6 +106,57 @@ def test_jacobian_matches_oracle_on_same_orbitals(shape, kernel):
         blocks = [dfull[np.ix_(w.row_idx[a:b], w.row_idx[a:b])] for a, b in zip(w.row_start[:-1], w.row_start[1:])]
     dref = np.concatenate([b.reshape(-1, order="F") for b in blocks])
     assert np.abs(d - dref).max() < 1e-11
+
+
+DMMA_SHAPES = {
+    # name: (workload factory, kernel AUTO must pick)
+    "sweep64": (lambda: wl.sweep(64), DMMA),
+    "sweep264_no_tile_edge": (lambda: wl.sweep(264), DMMA),            # no = 132: ragged 128-column tile
+    "mixed_small_frags": (lambda: wl.make_workload("mx", 61, 27, [3, 1, 4, 2, 4, 4, 1, 3, 2, 4, 3, 3, 4]), DMMA),
+    "partial_cover": (lambda: wl.make_workload("pc", 90, 40, [4, 4, 2, 3]), DMMA),
+    "many_tiles": (lambda: wl.make_workload("mt", 150, 70, [3] * 50), DMMA),   # 10 + 2/3 fragments per tile
+    "tiny_virtual_space": (lambda: wl.make_workload("tv", 40, 37, [4] * 10), DMMA),
+    "tiny_occupied_space": (lambda: wl.make_workload("to", 40, 2, [4] * 10), DMMA),
+    "bath_rows_m2": (lambda: wl.make_workload("b2", 44, 20, [2, 2, 1, 2], fit_imp_bath=True), DMMA),
+    "frag5_general": (lambda: wl.make_workload("f5", 40, 17, [5, 4, 3]), GENERAL),
+    "ti_general": (lambda: wl.hubbard24(True, l=8), GENERAL),
+    "bath_rows_m4_general": (lambda: wl.make_workload("b4", 44, 20, [4, 4], fit_imp_bath=True), GENERAL),
+}
+
+
+@pytest.mark.parametrize("shape", list(DMMA_SHAPES))
+def test_kernel_selection_and_dmma_parity(shape):
+    """AUTO picks the site-factorised DMMA kernel exactly where its schedule applies (<= 4 coupled
+    sites, <= 4 rows per fragment) and the general kernel elsewhere; both match the oracle."""
+    factory, expect = DMMA_SHAPES[shape]
+    w = factory()
+    jac, c, e, d, used = run_plan(w, _lib.KERNEL_AUTO)
+    assert used == expect
+    assert np.abs(jac - oracle_jac(w, c, e)).max() <= TOL
+    if expect == GENERAL:
+        plan = _lib.Plan(w.norb, w.num_pairs, w.h1start, w.h1row, w.h1col, w.row_start, w.rows, w.row_idx)
+        with pytest.raises(_lib.QcdmetError):
+            plan.set_kernel(_lib.KERNEL_DMMA)
+        plan.close()
+    else:
+        gen, *_ = run_plan(w, _lib.KERNEL_GENERAL, from_orbitals=(c, e))
+        assert np.abs(jac - gen).max() <= TOL
+
+
+def test_dmma_exact_block_symmetry_and_empty_perturbation():
+    w = wl.sweep(128)
+    # an empty perturbation (nnz_p = 0) in the middle of the list: its column must be exactly zero
+    k = 57
+    hs = np.concatenate([w.h1start[:k + 1], w.h1start[k:]]).astype(np.int32)
+    w2 = wl.Workload(**{**w.__dict__})
+    w2.h1start = hs
+    jac, c, e, d, used = run_plan(w2, _lib.KERNEL_AUTO)
+    assert used == DMMA
+    assert np.all(jac[:, k] == 0.0)
+    ref = oracle_jac(w, c, e)
+    assert np.abs(np.delete(jac, k, axis=1) - ref).max() <= TOL
+    blocks = jac.reshape(4, 4, w.norb // 4, -1, order="F")
+    assert np.abs(blocks - blocks.transpose(1, 0, 2, 3)).max() == 0.0
 
 
 @pytest.mark.parametrize("kernel", list(KERNELS))
