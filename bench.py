@@ -212,7 +212,7 @@ class DevArray:
 def run_b200(args):
     import torch
     import torch.distributed as dist
-    from qcdmet_b200 import _lib, workloads
+    from qcdmet_b200 import _lib, sharding, workloads
 
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -225,9 +225,11 @@ def run_b200(args):
     w = workloads.sweep(args.norb, args.nterms)
     P, Q = w.nterms, w.nresid
     # column shard, aligned to whole fragments (10 parameters each) so the ranks do equal work
-    per = -(-(P // 10) // world) * 10 if P % 10 == 0 else -(-P // world)
-    lo, hi = min(rank * per, P), min((rank + 1) * per, P)
-    assert world == 1 or per * world == P, "bench shards need P divisible into equal whole-fragment slices"
+    shards = sharding.column_shards(P, world, 10)
+    lo, hi = shards[rank]
+    per = shards[0][1] - shards[0][0]
+    assert world == 1 or all(e_ - b_ == per for b_, e_ in shards), \
+        "bench shards need P divisible into equal whole-fragment slices"
 
     e, c = np.linalg.eigh(w.h0)     # setup only: the metric takes (C, e) as given (eigensolve excluded)
     plan = _lib.Plan(w.norb, w.num_pairs, w.h1start, w.h1row, w.h1col, w.row_start, w.rows, w.row_idx,
@@ -335,6 +337,11 @@ def run_b200(args):
     if rank == 0:
         peak, peak_burst, peak_src = fp64_peak()
         achieved = flops / (k_ms * 1e-3) * 1e-12 if k_ms > 0 else None
+        # SURVEY.md 8(d) per-perturbation count W_col = 2 S nv no + (2 nnz+1) nv no + 2 no sum r_f^2 + 2 sum r_f^2
+        nv = w.norb - w.num_pairs
+        nnz = np.diff(w.h1start[lo:hi + 1]).astype(float)
+        w_cols = float(np.sum(2.0 * w.nrows * nv * w.num_pairs + (2.0 * nnz + 1.0) * nv * w.num_pairs
+                              + 2.0 * w.num_pairs * Q + 2.0 * Q))
         cpu = None
         if not args.no_cpu_baseline:
             cpu = cpu_reference_rate(w, args.cpu_sample_cols or default_sample_cols(args.norb))
@@ -351,7 +358,10 @@ def run_b200(args):
                          "frac": (achieved / peak) if achieved else None, "traffic": None,
                          "kernel_ms": k_ms, "flops_per_launch": flops,
                          "peak_source": peak_src,
-                         "note": "FP64 flops actually executed by the dominant kernel on this rank / its CUDA-event time"},
+                         "algorithmic_equiv_tflops": (w_cols / (k_ms * 1e-3) * 1e-12) if k_ms > 0 else None,
+                         "note": "achieved = FP64 flops actually executed by the dominant kernel on this rank / its "
+                                 "CUDA-event time (site-factorised algorithm, SURVEY 8d: executed flops disclosed); "
+                                 "algorithmic_equiv = the per-perturbation count W_col x columns / the same time"},
             "cpu_baseline": cpu,
             "e2e": e2e,
             "gpu_launches": int(launches * args.steps),
