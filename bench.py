@@ -17,6 +17,10 @@ from __future__ import annotations
 import argparse
 import json
 import os
+
+# torchrun exports OMP_NUM_THREADS=1 to its children; the reference arm / CPU baseline must use every
+# host core (libgomp reads the variable when it is first loaded, i.e. before `import torch`).
+os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
 import subprocess
 import sys
 import threading
@@ -201,14 +205,6 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------
 # this framework
 # ------------------------------------------------------------------------------------------
-class DevArray:
-    """__cuda_array_interface__ view of a device pointer owned by the plan (for torch/NCCL)."""
-
-    def __init__(self, ptr, nelem):
-        self.__cuda_array_interface__ = {"shape": (nelem,), "typestr": "<f8", "data": (ptr, False),
-                                         "version": 2, "strides": None}
-
-
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -238,30 +234,29 @@ def run_b200(args):
     plan.set_columns(lo, hi)
     plan.set_orbitals(c, e)
 
-    gathered = None
+    gathered = mine = None
     if world > 1:
+        # in-place all-gather: each rank's kernels write straight into its slot of the gathered buffer
         gathered = torch.empty(world * per * Q, dtype=torch.float64, device="cuda")
+        mine = gathered[rank * per * Q:(rank + 1) * per * Q]
+        plan.set_output_device(mine.data_ptr(), mine.numel())
     flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device="cuda")
 
     def step():
         flush.zero_()                       # evict L2 between steps (256 MB > 126 MB L2)
         plan.compute()
         if world > 1:
-            mine = torch.as_tensor(DevArray(plan.device_ptr(), per * Q), device="cuda")
             dist.all_gather_into_tensor(gathered, mine)
 
-    if world > 1:
-        # slices are padded to `per` columns for the collective
-        plan.set_columns(lo, hi)
     for _ in range(args.warmup):
         step()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
         time.sleep(0.3)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()          # after rank 0's sampler start-up, so that all ranks enter together
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     kernel_ms = []
     torch.cuda.synchronize()
@@ -273,6 +268,14 @@ def run_b200(args):
     if world > 1:
         dist.barrier()
     ms_total = ev0.elapsed_time(ev1)
+    if os.environ.get("QCDMET_BENCH_DEBUG"):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter(); plan.compute(); t1 = time.perf_counter(); plan.sync(); t2 = time.perf_counter()
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, mine)
+        torch.cuda.synchronize(); t3 = time.perf_counter()
+        print(f"[rank {rank}] launch {1e3*(t1-t0):.2f} ms, kernel {1e3*(t2-t1):.2f} ms, gather {1e3*(t3-t2):.2f} ms",
+              file=sys.stderr, flush=True)
     clocks = sampler.stop() if rank == 0 else None
     # dominant kernel: events recorded by the library on the launching stream around that launch
     for _ in range(max(1, min(args.steps, 3))):

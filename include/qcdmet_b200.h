@@ -109,6 +109,11 @@ int qcdmet_plan_set_kernel(qcdmet_plan *plan, int kernel);
 /* CUDA stream (cudaStream_t) every launch of this plan goes to; NULL = legacy default stream. */
 int qcdmet_plan_set_stream(qcdmet_plan *plan, void *stream);
 
+/* Write the Jacobian slice into caller-owned device memory (e.g. this rank's slot of an NCCL
+ * all-gather buffer) instead of the plan's own buffer; capacity in doubles.  NULL restores the
+ * plan-owned buffer. */
+int qcdmet_plan_set_output_device(qcdmet_plan *plan, void *device_ptr, long long capacity);
+
 /* Upload H0 (host), run cuSOLVER syevd on the device, build the operand panels. */
 int qcdmet_plan_set_h0(qcdmet_plan *plan, const double *H0);
 /* Upload orbitals (host; layout as in qcdmet_jacobian_from_orbitals), build the panels. */

@@ -42,6 +42,7 @@ SIGNATURES = {
     "qcdmet_plan_set_columns": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]),
     "qcdmet_plan_set_kernel": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "qcdmet_plan_set_stream": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
+    "qcdmet_plan_set_output_device": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_longlong]),
     "qcdmet_plan_set_h0": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     "qcdmet_plan_set_orbitals": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "qcdmet_plan_compute": (ctypes.c_int, [ctypes.c_void_p]),
@@ -142,6 +143,10 @@ class Plan:
 
     def set_stream(self, stream_ptr):
         check(self.lib.qcdmet_plan_set_stream(self.handle, ctypes.c_void_p(stream_ptr)))
+
+    def set_output_device(self, ptr, capacity):
+        """Jacobian slice goes to caller-owned device memory (ptr: int address, capacity in doubles)."""
+        check(self.lib.qcdmet_plan_set_output_device(self.handle, ctypes.c_void_p(ptr), int(capacity)))
 
     def set_h0(self, h0):
         h0 = as_f64(h0)

@@ -40,8 +40,11 @@ struct qcdmet_plan {
     double *d_R = nullptr;
     double *d_C = nullptr, *d_e = nullptr;
     double *d_CoT = nullptr, *d_CvT = nullptr, *d_PO = nullptr, *d_PV = nullptr;
-    double *d_J = nullptr;
-    size_t J_capacity = 0;
+    double *d_J = nullptr;          // where the Jacobian slice is written (own buffer or external)
+    double *d_J_own = nullptr;
+    size_t J_capacity = 0;          // capacity of d_J_own
+    double *d_J_ext = nullptr;
+    size_t J_ext_capacity = 0;
     double *d_D = nullptr;
     double *d_work = nullptr;
     int lwork = 0;
@@ -135,17 +138,24 @@ int validate_lists(int N, int P, int no, const int *h1start, const int *h1row, c
 int ensure_jacobian_buffer(qcdmet_plan *p)
 {
     const size_t need = (size_t)std::max<long long>(p->Q, 1) * std::max(p->colEnd - p->colBegin, 1);
+    if (p->d_J_ext) {
+        QC_CHECK(need <= p->J_ext_capacity, QCDMET_E_ARG,
+                 "external Jacobian buffer too small: %zu doubles needed, %zu given", need, p->J_ext_capacity);
+        p->d_J = p->d_J_ext;
+        return QCDMET_OK;
+    }
     if (need > p->J_capacity) {
-        if (p->d_J) cudaFree(p->d_J);
-        p->d_J = nullptr;
+        if (p->d_J_own) cudaFree(p->d_J_own);
+        p->d_J_own = nullptr;
         p->J_capacity = 0;
-        if (cudaMalloc((void **)&p->d_J, sizeof(double) * need) != cudaSuccess) {
+        if (cudaMalloc((void **)&p->d_J_own, sizeof(double) * need) != cudaSuccess) {
             cudaGetLastError();
             set_error("cudaMalloc of the Jacobian slice (%zu doubles) failed", need);
             return QCDMET_E_ALLOC;
         }
         p->J_capacity = need;
     }
+    p->d_J = p->d_J_own;
     return QCDMET_OK;
 }
 
@@ -305,7 +315,7 @@ int qcdmet_plan_destroy(qcdmet_plan *p)
     cudaFree(p->d_rowStart); cudaFree(p->d_rowFrag); cudaFree(p->d_rowIdx); cudaFree(p->d_qoff);
     cudaFree(p->d_R); cudaFree(p->d_C); cudaFree(p->d_e);
     cudaFree(p->d_CoT); cudaFree(p->d_CvT); cudaFree(p->d_PO); cudaFree(p->d_PV);
-    cudaFree(p->d_J); cudaFree(p->d_D); cudaFree(p->d_work); cudaFree(p->d_info);
+    cudaFree(p->d_J_own); cudaFree(p->d_D); cudaFree(p->d_work); cudaFree(p->d_info);
     if (p->ev0) cudaEventDestroy(p->ev0);
     if (p->ev1) cudaEventDestroy(p->ev1);
     if (p->solver) cusolverDnDestroy(p->solver);
@@ -342,6 +352,16 @@ int qcdmet_plan_set_stream(qcdmet_plan *p, void *stream)
 {
     QC_CHECK(p != nullptr, QCDMET_E_ARG, "plan is NULL");
     p->stream = (cudaStream_t)stream;
+    return QCDMET_OK;
+}
+
+int qcdmet_plan_set_output_device(qcdmet_plan *p, void *device_ptr, long long capacity)
+{
+    QC_CHECK(p != nullptr, QCDMET_E_ARG, "plan is NULL");
+    QC_CHECK(device_ptr == nullptr || capacity > 0, QCDMET_E_ARG, "capacity must be positive");
+    p->d_J_ext = (double *)device_ptr;
+    p->J_ext_capacity = device_ptr ? (size_t)capacity : 0;
+    p->have_jac = false;
     return QCDMET_OK;
 }
 

@@ -18,10 +18,15 @@
 //   * 8 consumer warps (4 sites x 2 column halves), warp tile 32 x 64, 32 DMMA.8x8x4 per k4 step,
 //     accumulators in registers (FP64 has no tcgen05/TMEM path: tcgen05.mma has no f64 kind)
 //   * 1 producer warp, 4-stage mbarrier full/empty pipeline (cp.async.bulk -> UBLKCP)
-//   * epilogue per 128-column tile: accumulators x Co[c,o] x PO[b,o] on the FP64 pipe, warp-shuffle
-//     reduction over the 4 lanes of a row, running sums in shared memory; after the last tile the
-//     CTA assembles G_p, symmetrises, and stores its (32 rows x 4) x (<=16 columns) patch of J with
-//     coalesced stores.  No atomics: every J element is owned by exactly one CTA.
+//   * epilogue per 128-column tile: accumulators x Co[c,o] x PO[b,o] on the FP64 pipe (operands
+//     TMA-prefetched by the producer, each warp runs its epilogue independently so the other warp of
+//     the SM sub-partition keeps the DMMA pipe busy), warp-shuffle reduction over the 4 lanes of a row,
+//     running sums in shared memory; after the last tile the CTA assembles G_p, symmetrises, and stores
+//     its patch of J with coalesced stores.  No atomics: every J element is owned by exactly one CTA.
+//   * symmetric mode: when the fragments are exactly the site groups of the perturbation list
+//     (impurity-only rows, the standard non-TI DMET fit) M_r[a,o] = M_a[r,o], so only block pairs
+//     (g, t) with tile(g) >= t are computed and each CTA also stores the mirrored patch
+//     J[rows of g, columns of the blocks in t] from the same N values: half the flops, exact.
 #include "common.cuh"
 #include <algorithm>
 #include <cstdint>
@@ -53,9 +58,14 @@ constexpr uint32_t STAGE_BYTES = STAGE_DOUBLES * 8;
 constexpr int SM_STAGE_OFF = 0;
 constexpr int SM_POS_OFF = SM_STAGE_OFF + STAGES * STAGE_DOUBLES * 8;
 constexpr int SM_COS_OFF = SM_POS_OFF + (AT + 1) * PSTRIDE * 8;
+constexpr int NSTRIDE = 18;       // running-sum row stride in doubles (16 used; conflict-free 16 B slots)
+constexpr int TP = 128;           // max perturbations over the blocks of one tile
+constexpr int POS_DOUBLES = (AT + 1) * PSTRIDE;
+constexpr int COS_DOUBLES = RT * BN;
+constexpr uint32_t EPI_BYTES = (POS_DOUBLES + COS_DOUBLES) * 8;
 constexpr int SM_NS_OFF = SM_COS_OFF + RT * BN * 8;
-constexpr int SM_BAR_OFF = SM_NS_OFF + 2 * 128 * 16 * 8;
-constexpr int SM_TAB_OFF = SM_BAR_OFF + 2 * STAGES * 8;
+constexpr int SM_BAR_OFF = SM_NS_OFF + 2 * 128 * NSTRIDE * 8;
+constexpr int SM_TAB_OFF = SM_BAR_OFF + (2 * STAGES + 2) * 8;
 // tables: qrow[32] (8B) | tileRow[32] (4B) | compSites[4] (4B) | compP[16] (4B) | partner[32][4] (1B)
 //         | self[32] (1B) | compEnt[16][4] (1B)
 constexpr int TAB_QROW = 0;
@@ -69,12 +79,17 @@ constexpr int TAB_BYTES = TAB_CENT + MAXP * MAXE;
 constexpr int SMEM_BYTES = SM_TAB_OFF + ((TAB_BYTES + 15) / 16) * 16;
 
 struct DmmaArgs {
-    int nKc, nOt, no, nv, ldo;
+    int nKc, nOt;
     int colBegin, colEnd;
+    int sym;                            // symmetric mode: also store the mirrored patch
     long long Q;
-    const double *Wt, *PVt, *CVt;
-    const double *PO, *CoT;
-    const int *launchComps;
+    const double *Wt, *PVt, *CVt, *POt, *COt;
+    const int2 *work;                   // (component, tile) per CTA
+    const int *compTile;                // [nComp] tile holding the component's fragment (sym mode)
+    const long long *compQ;             // [nComp] qoff of that fragment (sym mode)
+    const unsigned char *compLoc;       // [nComp][RT] local row index of site slot | r_f << 4 (sym mode)
+    const int *tileP;                   // [nTiles][TP] perturbations of the blocks in the tile (sym mode)
+    const unsigned char *tileEnt;       // [nTiles][TP][MAXE] a_slot | j << 5, 0xFF = none (sym mode)
     const int *compSites;               // [nComp][RT]   site or -1
     const int *compP;                   // [nComp][MAXP] perturbation index or -1
     const unsigned char *compEnt;       // [nComp][MAXP][MAXE]  rs | cs << 4, 0xFF = none
@@ -149,7 +164,8 @@ __global__ void build_wt_kernel(const double *__restrict__ e, int no, int nv, in
     const int o = ot * BN + (njp * 2 + e2) * 8 + (lane >> 2);
     Wt[idx] = (k < nv && o < no) ? 1.0 / (e[o] - e[no + k]) : 0.0;
 }
-// PVt[(tile*nKc + kc)][k4][lane][mi] = PV[tileRow[tile][mi*8 + (lane>>2)]][kc*KC + k4*4 + (lane&3)]
+// PVt[(tile*nKc + kc)][k4][mi>>1][lane][mi&1] = PV[tileRow[tile][mi*8 + (lane>>2)]][kc*KC + k4*4 + (lane&3)]
+// (two conflict-free LDS.128 per k4 step: a quarter warp reads 128 contiguous bytes)
 __global__ void build_pvt_kernel(const double *__restrict__ PV, int ldv, int nv, int nKc,
                                  const int *__restrict__ tileRow, long long total, double *__restrict__ PVt)
 {
@@ -158,7 +174,7 @@ __global__ void build_pvt_kernel(const double *__restrict__ PV, int ldv, int nv,
     const int within = (int)(idx % PV_STAGE);
     const long long blk = idx / PV_STAGE;
     const int tile = (int)(blk / nKc), kc = (int)(blk % nKc);
-    const int mi = within & 3, lane = (within >> 2) & 31, k4 = within >> 7;
+    const int lane = (within >> 1) & 31, mi = (within & 1) | (((within >> 6) & 1) << 1), k4 = within >> 7;
     const int row = tileRow[tile * AT + mi * 8 + (lane >> 2)];
     const int k = kc * KC + k4 * 4 + (lane & 3);
     PVt[idx] = (row >= 0 && k < nv) ? PV[(size_t)row * ldv + k] : 0.0;
@@ -176,6 +192,38 @@ __global__ void build_cvt_kernel(const double *__restrict__ CvT, int ldv, int nv
     const int site = compSites[comp * RT + r];
     const int k = kc * KC + kk;
     CVt[idx] = (site >= 0 && k < nv) ? CvT[(size_t)site * ldv + k] : 0.0;
+}
+
+// POt[(tile*nOt + ot)][slot 0..AT][PSTRIDE] = PO[tileRow[tile][slot]][ot*BN + o]  (slot AT: zero row)
+__global__ void build_pot_kernel(const double *__restrict__ PO, int ldo, int no, int nOt,
+                                 const int *__restrict__ tileRow, long long total, double *__restrict__ POt)
+{
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int within = (int)(idx % POS_DOUBLES);
+    const long long blk = idx / POS_DOUBLES;
+    const int tile = (int)(blk / nOt), ot = (int)(blk % nOt);
+    const int slot = within / PSTRIDE, oo = within % PSTRIDE;
+    const int o = ot * BN + oo;
+    double val = 0.0;
+    if (slot < AT && oo < BN && o < no) {
+        const int row = tileRow[tile * AT + slot];
+        if (row >= 0) val = PO[(size_t)row * ldo + o];
+    }
+    POt[idx] = val;
+}
+// COt[(comp*nOt + ot)][r][BN] = CoT[compSites[comp][r]][ot*BN + o]
+__global__ void build_cot_kernel(const double *__restrict__ CoT, int ldo, int no, int nOt,
+                                 const int *__restrict__ compSites, long long total, double *__restrict__ COt)
+{
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int within = (int)(idx % COS_DOUBLES);
+    const long long blk = idx / COS_DOUBLES;
+    const int comp = (int)(blk / nOt), ot = (int)(blk % nOt);
+    const int r = within / BN, o = ot * BN + within % BN;
+    const int site = compSites[comp * RT + r];
+    COt[idx] = (site >= 0 && o < no) ? CoT[(size_t)site * ldo + o] : 0.0;
 }
 
 // ------------------------------------------------------------------------------------------
