@@ -42,6 +42,7 @@ extern "C" {
 #define QCDMET_KERNEL_AUTO     0   /* DMMA site-factorised kernel when eligible, else general */
 #define QCDMET_KERNEL_GENERAL  1   /* plain FP64 general kernel (any CSR, any rows)           */
 #define QCDMET_KERNEL_DMMA     2   /* force the DMMA kernel (error if not eligible)           */
+#define QCDMET_KERNEL_DMMA_NOSYM 3 /* DMMA kernel without the symmetric (mirrored-patch) mode */
 
 /* ---------------------------------------------------------------------------------------
  * (1) Compat symbol.  Replaces lib/rhf_response.cc:32-119 one to one:
@@ -140,6 +141,7 @@ int qcdmet_plan_get_full_response(qcdmet_plan *plan, double *rdm_deriv, double *
 long long qcdmet_plan_num_residuals(qcdmet_plan *plan);    /* Q                                  */
 int  qcdmet_plan_kernel_used(qcdmet_plan *plan);           /* QCDMET_KERNEL_GENERAL or _DMMA      */
 int  qcdmet_plan_launches(qcdmet_plan *plan);              /* kernels launched by the last compute */
+int  qcdmet_plan_symmetric_used(qcdmet_plan *plan);        /* 1 if the last compute used the mirrored-patch mode */
 double qcdmet_plan_flops(qcdmet_plan *plan);               /* FP64 flops executed by the last compute */
 /* Device time of the dominant kernel of the last compute (CUDA events recorded on the plan
  * stream around that launch; synchronises the stream).  ms < 0 if nothing was computed. */

@@ -15,7 +15,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("QCDMET_B200_LIB", os.path.join(_HERE, "libqcdmet_b200.so"))
 
-KERNEL_AUTO, KERNEL_GENERAL, KERNEL_DMMA = 0, 1, 2
+KERNEL_AUTO, KERNEL_GENERAL, KERNEL_DMMA, KERNEL_DMMA_NOSYM = 0, 1, 2, 3
 
 c_int_p = ctypes.POINTER(ctypes.c_int)
 c_double_p = ctypes.POINTER(ctypes.c_double)
@@ -56,6 +56,7 @@ SIGNATURES = {
     "qcdmet_plan_num_residuals": (ctypes.c_longlong, [ctypes.c_void_p]),
     "qcdmet_plan_kernel_used": (ctypes.c_int, [ctypes.c_void_p]),
     "qcdmet_plan_launches": (ctypes.c_int, [ctypes.c_void_p]),
+    "qcdmet_plan_symmetric_used": (ctypes.c_int, [ctypes.c_void_p]),
     "qcdmet_plan_flops": (ctypes.c_double, [ctypes.c_void_p]),
     "qcdmet_plan_kernel_time_ms": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     "qcdmet_last_error": (ctypes.c_char_p, []),
@@ -196,6 +197,10 @@ class Plan:
     @property
     def kernel_used(self):
         return self.lib.qcdmet_plan_kernel_used(self.handle)
+
+    @property
+    def symmetric_used(self):
+        return bool(self.lib.qcdmet_plan_symmetric_used(self.handle))
 
     @property
     def launches(self):

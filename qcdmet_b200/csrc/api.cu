@@ -55,6 +55,7 @@ struct qcdmet_plan {
     bool have_orbitals = false, have_jac = false;
     int launches = 0;
     double flops = 0.0;
+    bool symmetric_used = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;   // around the dominant kernel of the last compute
 };
 
@@ -340,9 +341,9 @@ int qcdmet_plan_set_columns(qcdmet_plan *p, int colBegin, int colEnd)
 int qcdmet_plan_set_kernel(qcdmet_plan *p, int kernel)
 {
     QC_CHECK(p != nullptr, QCDMET_E_ARG, "plan is NULL");
-    QC_CHECK(kernel >= QCDMET_KERNEL_AUTO && kernel <= QCDMET_KERNEL_DMMA, QCDMET_E_ARG,
+    QC_CHECK(kernel >= QCDMET_KERNEL_AUTO && kernel <= QCDMET_KERNEL_DMMA_NOSYM, QCDMET_E_ARG,
              "unknown kernel id %d", kernel);
-    QC_CHECK(kernel != QCDMET_KERNEL_DMMA || p->dmma_ok, QCDMET_E_ARG,
+    QC_CHECK((kernel != QCDMET_KERNEL_DMMA && kernel != QCDMET_KERNEL_DMMA_NOSYM) || p->dmma_ok, QCDMET_E_ARG,
              "DMMA kernel not eligible for this plan: %s", p->dmma_why.c_str());
     p->kernel_req = kernel;
     return QCDMET_OK;
@@ -410,19 +411,22 @@ int qcdmet_plan_compute(qcdmet_plan *p)
     DeviceGuard guard(p->device);
     QC_TRY(ensure_jacobian_buffer(p));
     JacView v = make_view(p);
-    const bool use_dmma = (p->kernel_req == QCDMET_KERNEL_DMMA) ||
+    const bool use_dmma = (p->kernel_req == QCDMET_KERNEL_DMMA) || (p->kernel_req == QCDMET_KERNEL_DMMA_NOSYM) ||
                           (p->kernel_req == QCDMET_KERNEL_AUTO && p->dmma_ok);
     if (!p->ev0) {
         QC_CUDA(cudaEventCreate(&p->ev0));
         QC_CUDA(cudaEventCreate(&p->ev1));
     }
     if (use_dmma) {
-        QC_TRY(launch_jacobian_dmma(p->dmma, v, p->stream, &p->launches, &p->flops, p->ev0, p->ev1));
+        QC_TRY(launch_jacobian_dmma(p->dmma, v, p->stream, &p->launches, &p->flops, p->ev0, p->ev1,
+                                    p->kernel_req != QCDMET_KERNEL_DMMA_NOSYM));
+        p->symmetric_used = dmma_last_launch_symmetric(p->dmma);
         p->kernel_used = QCDMET_KERNEL_DMMA;
     } else {
         QC_TRY(launch_jacobian_general(v, p->stream, &p->launches, &p->flops, p->ev0, p->ev1));
         p->flops = count_flops_general(p);
         p->kernel_used = QCDMET_KERNEL_GENERAL;
+        p->symmetric_used = false;
     }
     p->have_jac = true;
     return QCDMET_OK;
@@ -483,6 +487,7 @@ int qcdmet_plan_get_orbitals(qcdmet_plan *p, double *C)
 long long qcdmet_plan_num_residuals(qcdmet_plan *p) { return p ? p->Q : -1; }
 int qcdmet_plan_kernel_used(qcdmet_plan *p) { return p ? p->kernel_used : -1; }
 int qcdmet_plan_launches(qcdmet_plan *p) { return p ? p->launches : -1; }
+int qcdmet_plan_symmetric_used(qcdmet_plan *p) { return p ? (p->symmetric_used ? 1 : 0) : -1; }
 double qcdmet_plan_flops(qcdmet_plan *p) { return p ? p->flops : -1.0; }
 
 int qcdmet_plan_kernel_time_ms(qcdmet_plan *p, double *ms)

@@ -86,6 +86,7 @@ int dmma_plan_build(DmmaPlanData **out, int N, int no, int P, int F, const int *
 void dmma_plan_free(DmmaPlanData *d);
 int dmma_prepare_orbitals(DmmaPlanData *d, const JacView &v, cudaStream_t st);
 int launch_jacobian_dmma(DmmaPlanData *d, const JacView &v, cudaStream_t st, int *launches,
-                         double *flops, cudaEvent_t ev0, cudaEvent_t ev1);
+                         double *flops, cudaEvent_t ev0, cudaEvent_t ev1, bool allowSym);
+bool dmma_last_launch_symmetric(const DmmaPlanData *d);
 
 }  // namespace qcdmet

@@ -240,23 +240,25 @@ __global__ void __launch_bounds__(NTHREADS, 1) jac_dmma_kernel(const DmmaArgs g)
     unsigned char *tab = smem + SM_TAB_OFF;
     long long *qrow = reinterpret_cast<long long *>(tab + TAB_QROW);
     int *trow = reinterpret_cast<int *>(tab + TAB_TROW);
-    int *csite = reinterpret_cast<int *>(tab + TAB_CSITE);
     int *cp = reinterpret_cast<int *>(tab + TAB_CP);
     unsigned char *partner = tab + TAB_PARTNER;
     unsigned char *selfi = tab + TAB_SELF;
     unsigned char *cent = tab + TAB_CENT;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int comp = g.launchComps[blockIdx.x];
-    const int tile = blockIdx.y;
+    const int2 wk = g.work[blockIdx.x];
+    const int comp = wk.x, tile = wk.y;
     const int nKc = g.nKc, nOt = g.nOt;
+    const uint32_t epiFull = smem_u32(&bars[2 * STAGES]), epiEmpty = smem_u32(&bars[2 * STAGES + 1]);
 
-    // ---- set-up: barriers, tables, zeroed accumulators
+    // ---- set-up: barriers, tables, zeroed running sums
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(smem_u32(&bars[s]), 1);              // full: producer's expect_tx arrival
             mbar_init(smem_u32(&bars[STAGES + s]), 8);     // empty: one arrival per consumer warp
         }
+        mbar_init(epiFull, 1);
+        mbar_init(epiEmpty, 8);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (tid < AT) {
@@ -265,11 +267,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) jac_dmma_kernel(const DmmaArgs g)
         selfi[tid] = g.tileSelf[tile * AT + tid];
     }
     if (tid < AT * RF) partner[tid] = g.tilePartner[tile * AT * RF + tid];
-    if (tid < RT) csite[tid] = g.compSites[comp * RT + tid];
     if (tid < MAXP) cp[tid] = g.compP[comp * MAXP + tid];
     if (tid < MAXP * MAXE) cent[tid] = g.compEnt[comp * MAXP * MAXE + tid];
-    for (int i = tid; i < 2 * 128 * 16; i += NTHREADS) Ns[i] = 0.0;
-    for (int i = tid; i < PSTRIDE; i += NTHREADS) POS[AT * PSTRIDE + i] = 0.0;   // the "no partner" row
+    for (int i = tid; i < 2 * 128 * NSTRIDE; i += NTHREADS) Ns[i] = 0.0;
     __syncthreads();
 
     if (warp == 8) {
@@ -277,10 +277,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) jac_dmma_kernel(const DmmaArgs g)
         if (lane == 0) {
             const double *pvsrc = g.PVt + (size_t)tile * nKc * PV_STAGE;
             const double *cvsrc = g.CVt + (size_t)comp * nKc * CV_STAGE;
+            const double *posrc = g.POt + (size_t)tile * nOt * POS_DOUBLES;
+            const double *cosrc = g.COt + (size_t)comp * nOt * COS_DOUBLES;
+            const int epiAt = nKc > 3 ? nKc - 3 : 0;      // prefetch the epilogue operands near the end of a tile
             int it = 0;
             for (int ot = 0; ot < nOt; ++ot) {
                 const double *wsrc = g.Wt + (size_t)ot * nKc * W_STAGE;
                 for (int kc = 0; kc < nKc; ++kc, ++it) {
+                    if (kc == epiAt) {
+                        mbar_wait(epiEmpty, (ot & 1) ^ 1);          // every warp is done with tile ot-1's operands
+                        mbar_expect_tx(epiFull, EPI_BYTES);
+                        tma_bulk_g2s(smem_u32(POS), posrc + (size_t)ot * POS_DOUBLES, POS_DOUBLES * 8, epiFull);
+                        tma_bulk_g2s(smem_u32(CoS), cosrc + (size_t)ot * COS_DOUBLES, COS_DOUBLES * 8, epiFull);
+                    }
                     const int s = it % STAGES;
                     const uint32_t full = smem_u32(&bars[s]), empty = smem_u32(&bars[STAGES + s]);
                     mbar_wait(empty, ((it / STAGES) & 1) ^ 1);
@@ -316,8 +325,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) jac_dmma_kernel(const DmmaArgs g)
             const double *CVs = PVs + PV_STAGE + warp_m * KC;
 #pragma unroll
             for (int k4 = 0; k4 < KC / 4; ++k4) {
-                const double2 p01 = *reinterpret_cast<const double2 *>(PVs + (k4 * 32 + lane) * 4);
-                const double2 p23 = *reinterpret_cast<const double2 *>(PVs + (k4 * 32 + lane) * 4 + 2);
+                const double2 p01 = *reinterpret_cast<const double2 *>(PVs + ((k4 * 2 + 0) * 32 + lane) * 2);
+                const double2 p23 = *reinterpret_cast<const double2 *>(PVs + ((k4 * 2 + 1) * 32 + lane) * 2);
                 const double cv = CVs[k4 * 4 + t4];
                 double a[4], b[8];
                 a[0] = p01.x * cv; a[1] = p01.y * cv; a[2] = p23.x * cv; a[3] = p23.y * cv;
@@ -336,22 +345,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) jac_dmma_kernel(const DmmaArgs g)
             if (lane == 0) mbar_arrive(smem_u32(&bars[STAGES + s]));
         }
 
-        // ---- epilogue for this 128-column tile
-        consumer_sync();                              // previous tile's POS/CoS no longer read
-        {
-            const int o0 = ot * BN;
-            for (int i = tid; i < (AT + RT) * (BN / 2); i += NCONS) {
-                const int rowi = i / (BN / 2), oc = (i % (BN / 2)) * 2;
-                double2 val = make_double2(0.0, 0.0);
-                const double *src = nullptr;
-                if (rowi < AT) { const int r = trow[rowi]; if (r >= 0) src = g.PO + (size_t)r * g.ldo; }
-                else { const int sidx = csite[rowi - AT]; if (sidx >= 0) src = g.CoT + (size_t)sidx * g.ldo; }
-                if (src != nullptr && o0 + oc < g.ldo) val = *reinterpret_cast<const double2 *>(src + o0 + oc);
-                double *dst = (rowi < AT) ? (POS + rowi * PSTRIDE + oc) : (CoS + (rowi - AT) * BN + oc);
-                *reinterpret_cast<double2 *>(dst) = val;
-            }
-        }
-        consumer_sync();
+        // ---- epilogue for this 128-column tile (per warp, no CTA-wide barrier)
+        mbar_wait(epiFull, ot & 1);
 #pragma unroll
         for (int mi = 0; mi < 4; ++mi) {
             const int a_slot = mi * 8 + g4;
@@ -378,8 +373,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) jac_dmma_kernel(const DmmaArgs g)
                     for (int j = 0; j < RF; ++j) nacc[c][j] = fma(t0, po[j].x, fma(t1, po[j].y, nacc[c][j]));
                 }
             }
-            // reduce over the 4 lanes that share this row; lane t4 keeps component site c == t4
-            double *dst = Ns + ((warp_n * 128 + warp_m * AT + a_slot) * 16);
+            // reduce over the 4 lanes that share this row; lane t4 keeps the sums of site slot c == t4
+            double keep[RF];
 #pragma unroll
             for (int c = 0; c < RT; ++c)
 #pragma unroll
@@ -387,13 +382,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) jac_dmma_kernel(const DmmaArgs g)
                     double v = nacc[c][j];
                     v += __shfl_xor_sync(0xffffffffu, v, 1);
                     v += __shfl_xor_sync(0xffffffffu, v, 2);
-                    if (t4 == c) dst[c * RF + j] += v;
+                    if (t4 == c) keep[j] = v;
                 }
+            double2 *dst = reinterpret_cast<double2 *>(Ns + (warp_n * 128 + warp_m * AT + a_slot) * NSTRIDE + t4 * RF);
+            double2 s01 = dst[0], s23 = dst[1];
+            s01.x += keep[0]; s01.y += keep[1]; s23.x += keep[2]; s23.y += keep[3];
+            dst[0] = s01; dst[1] = s23;
         }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(epiEmpty);
     }
 
-    // ---- assemble G_p, symmetrise, store the CTA's patch of J
+    // ---- assemble G_p, symmetrise, store the CTA's patches of J
     consumer_sync();
+    const double *Ns1 = Ns + 128 * NSTRIDE;
+    // patch 1: rows of the tile x perturbations of the component
     for (int idx = tid; idx < MAXP * AT * RF; idx += NCONS) {
         const int pl = idx / (AT * RF), rem = idx % (AT * RF);
         const int a_slot = rem / RF, j = rem % RF;
@@ -409,12 +412,42 @@ __global__ void __launch_bounds__(NTHREADS, 1) jac_dmma_kernel(const DmmaArgs g)
             const unsigned char ent = cent[pl * MAXE + e];
             if (ent == 0xFF) continue;
             const int rs = ent & 15, cs = ent >> 4;
-            const int i1 = (rs * AT + a_slot) * 16 + cs * RF + j;
-            const int i2 = (rs * AT + b_slot) * 16 + cs * RF + a_loc;
-            gab += Ns[i1] + Ns[128 * 16 + i1];
-            gba += Ns[i2] + Ns[128 * 16 + i2];
+            const int i1 = (rs * AT + a_slot) * NSTRIDE + cs * RF + j;
+            const int i2 = (rs * AT + b_slot) * NSTRIDE + cs * RF + a_loc;
+            gab += Ns[i1] + Ns1[i1];
+            gba += Ns[i2] + Ns1[i2];
         }
         g.J[(size_t)g.Q * (p - g.colBegin) + qrow[a_slot] + (long long)rf * j] = 2.0 * (gab + gba);
+    }
+    // patch 2 (symmetric mode, off-diagonal block pairs): rows of the component's own fragment x
+    // perturbations of the blocks in the tile, from M_a[r,o] = M_r[a,o]:
+    //   G_p'[r,c] = sum_{(a,b') in p'} N_r[a; c, b']
+    if (g.sym && g.compTile[comp] != tile) {
+        const long long q0 = g.compQ[comp];
+        const unsigned char *loc = g.compLoc + comp * RT;
+        const int *tp = g.tileP + (size_t)tile * TP;
+        const unsigned char *te = g.tileEnt + (size_t)tile * TP * MAXE;
+        for (int idx = tid; idx < TP * RT * RT; idx += NCONS) {
+            const int pp = idx / (RT * RT), rem = idx % (RT * RT);
+            const int cs = rem / RT, rs = rem % RT;          // site slots of the component: row r, column c
+            const int p = tp[pp];
+            if (p < g.colBegin || p >= g.colEnd) continue;
+            const int lr = loc[rs], lc = loc[cs];
+            if (lr == 0xFF || lc == 0xFF) continue;
+            const int rf = lr >> 4;
+            double grc = 0.0, gcr = 0.0;
+#pragma unroll
+            for (int e = 0; e < MAXE; ++e) {
+                const unsigned char ent = te[pp * MAXE + e];
+                if (ent == 0xFF) continue;
+                const int a_slot = ent & 31, j = ent >> 5;
+                const int i1 = (rs * AT + a_slot) * NSTRIDE + cs * RF + j;
+                const int i2 = (cs * AT + a_slot) * NSTRIDE + rs * RF + j;
+                grc += Ns[i1] + Ns1[i1];
+                gcr += Ns[i2] + Ns1[i2];
+            }
+            g.J[(size_t)g.Q * (p - g.colBegin) + q0 + (lr & 15) + (long long)rf * (lc & 15)] = 2.0 * (grc + gcr);
+        }
     }
 }
 
@@ -427,17 +460,24 @@ struct DmmaPlanData {
     int N = 0, no = 0, nv = 0, P = 0, S = 0;
     int nComp = 0, nTiles = 0, nKc = 0, nOt = 0;
     bool hasEmptyPerturbation = false;
-    std::vector<int> compSites, compP, compFirstP, compLastP, compNumSites;
-    std::vector<unsigned char> compEnt;
-    std::vector<int> tileRow;
-    std::vector<unsigned char> tilePartner, tileSelf;
+    bool symOk = false;                 // fragments == site groups of the perturbation list
+    std::vector<int> compSites, compP, compNumSites, compTile;
+    std::vector<long long> compQ;
+    std::vector<unsigned char> compEnt, compLoc;
+    std::vector<int> tileRow, tileNumRows, tileP;
+    std::vector<unsigned char> tilePartner, tileSelf, tileEnt;
     std::vector<long long> tileQ;
-    std::vector<int> launchComps;
+    std::vector<int2> work;
     int launchBegin = -1, launchEnd = -1;
-    int *d_compSites = nullptr, *d_compP = nullptr, *d_tileRow = nullptr, *d_launchComps = nullptr;
-    unsigned char *d_compEnt = nullptr, *d_tilePartner = nullptr, *d_tileSelf = nullptr;
-    long long *d_tileQ = nullptr;
-    double *d_Wt = nullptr, *d_PVt = nullptr, *d_CVt = nullptr;
+    bool launchSym = false;
+    double launchFlops = 0.0;
+    int *d_compSites = nullptr, *d_compP = nullptr, *d_tileRow = nullptr, *d_compTile = nullptr, *d_tileP = nullptr;
+    int2 *d_work = nullptr;
+    size_t workCapacity = 0;
+    unsigned char *d_compEnt = nullptr, *d_tilePartner = nullptr, *d_tileSelf = nullptr, *d_compLoc = nullptr,
+                  *d_tileEnt = nullptr;
+    long long *d_tileQ = nullptr, *d_compQ = nullptr;
+    double *d_Wt = nullptr, *d_PVt = nullptr, *d_CVt = nullptr, *d_POt = nullptr, *d_COt = nullptr;
     bool attrSet = false;
 };
 
@@ -450,7 +490,7 @@ struct Schedule {
 };
 
 Schedule build_schedule(int N, int no, int P, int F, const int *h1start, const int *h1row, const int *h1col,
-                        const int *rowStart)
+                        const int *rowStart, const int *rowIdx)
 {
     Schedule sc;
     DmmaPlanData &d = sc.d;
@@ -463,6 +503,7 @@ Schedule build_schedule(int N, int no, int P, int F, const int *h1start, const i
         if (rf > RF) { sc.why = "a fragment has more than 4 rows"; return sc; }
         qoff[f + 1] = qoff[f] + (long long)rf * rf;
     }
+    std::vector<int> fragTile(F, -1), fragSlot(F, -1);
     int slot = AT;   // forces a new tile at the first fragment
     for (int f = 0; f < F; ++f) {
         const int rs = rowStart[f], rf = rowStart[f + 1] - rs;
@@ -472,19 +513,22 @@ Schedule build_schedule(int N, int no, int P, int F, const int *h1start, const i
             d.tilePartner.insert(d.tilePartner.end(), AT * RF, (unsigned char)AT);
             d.tileSelf.insert(d.tileSelf.end(), AT, 0);
             d.tileQ.insert(d.tileQ.end(), AT, 0);
+            d.tileNumRows.push_back(0);
             ++d.nTiles;
             slot = 0;
         }
         const int base = (d.nTiles - 1) * AT;
+        fragTile[f] = d.nTiles - 1;
+        fragSlot[f] = slot;
         for (int al = 0; al < rf; ++al) {
             d.tileRow[base + slot + al] = rs + al;
             d.tileSelf[base + slot + al] = (unsigned char)(al | (rf << 4));
             d.tileQ[base + slot + al] = qoff[f] + al;
             for (int j = 0; j < rf; ++j) d.tilePartner[(size_t)(base + slot + al) * RF + j] = (unsigned char)(slot + j);
         }
+        d.tileNumRows.back() += rf;
         slot += rf;
     }
-    if (d.nTiles > 65535) { sc.why = "too many row tiles"; return sc; }
     // components: perturbations connected through shared sites (union-find over sites)
     std::vector<int> parent(N);
     std::iota(parent.begin(), parent.end(), 0);
@@ -526,12 +570,14 @@ Schedule build_schedule(int N, int no, int P, int F, const int *h1start, const i
         d.compNumSites[c] = (int)sites[c].size();
         for (size_t k = 0; k < sites[c].size(); ++k) d.compSites[(size_t)c * RT + k] = sites[c][k];
     }
+    std::vector<int> compOfP(P, -1);
     for (int p = 0; p < P; ++p) {
         const int b = h1start[p], e = h1start[p + 1];
         if (e == b) continue;
         const int c = compOfRoot[find(h1row[b])];
         if (np[c] >= MAXP) { sc.why = "more than 16 perturbations on one group of sites"; return sc; }
         const int pl = np[c]++;
+        compOfP[p] = c;
         d.compP[(size_t)c * MAXP + pl] = p;
         for (int k = b; k < e; ++k) {
             int rsl = -1, csl = -1;
@@ -544,6 +590,62 @@ Schedule build_schedule(int N, int no, int P, int F, const int *h1start, const i
     }
     d.nKc = (d.nv + KC - 1) / KC;
     d.nOt = (d.no + BN - 1) / BN;
+
+    // symmetric mode: impurity-only rows, and the row sites of every non-empty fragment are exactly the
+    // sites of one component (and vice versa).  Then PV/PO rows are C_v/C_o site rows and
+    // M_r[a,o] = M_a[r,o].
+    d.compTile.assign(d.nComp, -1);
+    d.compQ.assign(d.nComp, 0);
+    d.compLoc.assign((size_t)d.nComp * RT, 0xFF);
+    d.tileP.assign((size_t)d.nTiles * TP, -1);
+    d.tileEnt.assign((size_t)d.nTiles * TP * MAXE, 0xFF);
+    bool sym = (rowIdx != nullptr);
+    if (sym) {
+        std::vector<int> siteComp(N, -1), compFrag(d.nComp, -1);
+        for (int c = 0; c < d.nComp; ++c)
+            for (int s : sites[c]) siteComp[s] = c;
+        int matched = 0;
+        for (int f = 0; f < F && sym; ++f) {
+            const int rs = rowStart[f], rf = rowStart[f + 1] - rs;
+            if (rf == 0) continue;
+            const int c = siteComp[rowIdx[rs]];
+            if (c < 0 || compFrag[c] >= 0 || d.compNumSites[c] != rf) { sym = false; break; }
+            for (int al = 0; al < rf && sym; ++al) {
+                int q = -1;
+                for (int k = 0; k < RT; ++k)
+                    if (d.compSites[(size_t)c * RT + k] == rowIdx[rs + al]) q = k;
+                if (q < 0 || d.compLoc[(size_t)c * RT + q] != 0xFF) sym = false;
+                else d.compLoc[(size_t)c * RT + q] = (unsigned char)(al | (rf << 4));
+            }
+            compFrag[c] = f;
+            d.compTile[c] = fragTile[f];
+            d.compQ[c] = qoff[f];
+            ++matched;
+        }
+        if (matched != d.nComp) sym = false;
+        if (sym) {
+            // per tile: the perturbations of its blocks, elements as (row slot of a, local index of b')
+            std::vector<int> ntp(d.nTiles, 0);
+            for (int p = 0; p < P && sym; ++p) {
+                const int c = compOfP[p];
+                if (c < 0) continue;
+                const int f = compFrag[c], t = fragTile[f];
+                if (ntp[t] >= TP) { sym = false; break; }
+                const int pp = ntp[t]++;
+                d.tileP[(size_t)t * TP + pp] = p;
+                for (int k = h1start[p]; k < h1start[p + 1]; ++k) {
+                    int al = -1, bl = -1;
+                    for (int x = rowStart[f]; x < rowStart[f + 1]; ++x) {
+                        if (rowIdx[x] == h1row[k]) al = x - rowStart[f];
+                        if (rowIdx[x] == h1col[k]) bl = x - rowStart[f];
+                    }
+                    d.tileEnt[((size_t)t * TP + pp) * MAXE + (k - h1start[p])] =
+                        (unsigned char)((fragSlot[f] + al) | (bl << 5));
+                }
+            }
+        }
+    }
+    d.symOk = sym;
     sc.ok = true;
     return sc;
 }
@@ -564,38 +666,41 @@ int upload(T **dst, const std::vector<T> &src)
 }  // namespace
 
 bool dmma_eligible(int N, int P, int F, const int *h1start, const int *h1row, const int *h1col,
-                   const int *rowStart, const int *, bool, std::string *why)
+                   const int *rowStart, const int *rowIdx, bool, std::string *why)
 {
-    Schedule sc = build_schedule(N, N / 2 > 0 ? N / 2 : 1, P, F, h1start, h1row, h1col, rowStart);
+    Schedule sc = build_schedule(N, N / 2 > 0 ? N / 2 : 1, P, F, h1start, h1row, h1col, rowStart, rowIdx);
     if (why) *why = sc.why;
     return sc.ok;
 }
 
 int dmma_plan_build(DmmaPlanData **out, int N, int no, int P, int F, const int *h1start, const int *h1row,
-                    const int *h1col, const int *rowStart, const int *)
+                    const int *h1col, const int *rowStart, const int *rowIdx)
 {
     *out = nullptr;
-    Schedule sc = build_schedule(N, no, P, F, h1start, h1row, h1col, rowStart);
+    Schedule sc = build_schedule(N, no, P, F, h1start, h1row, h1col, rowStart, rowIdx);
     QC_CHECK(sc.ok, QCDMET_E_ARG, "DMMA kernel not eligible: %s", sc.why.c_str());
     DmmaPlanData *d = new DmmaPlanData(std::move(sc.d));
     int rc = QCDMET_OK;
-    if (!(rc = upload(&d->d_compSites, d->compSites)) && !(rc = upload(&d->d_compP, d->compP)) &&
-        !(rc = upload(&d->d_compEnt, d->compEnt)) && !(rc = upload(&d->d_tileRow, d->tileRow)) &&
-        !(rc = upload(&d->d_tilePartner, d->tilePartner)) && !(rc = upload(&d->d_tileSelf, d->tileSelf)) &&
-        !(rc = upload(&d->d_tileQ, d->tileQ))) {
-        std::vector<int> all(d->nComp);
-        rc = upload(&d->d_launchComps, all);
+    if ((rc = upload(&d->d_compSites, d->compSites)) || (rc = upload(&d->d_compP, d->compP)) ||
+        (rc = upload(&d->d_compEnt, d->compEnt)) || (rc = upload(&d->d_tileRow, d->tileRow)) ||
+        (rc = upload(&d->d_tilePartner, d->tilePartner)) || (rc = upload(&d->d_tileSelf, d->tileSelf)) ||
+        (rc = upload(&d->d_tileQ, d->tileQ)) || (rc = upload(&d->d_compTile, d->compTile)) ||
+        (rc = upload(&d->d_compQ, d->compQ)) || (rc = upload(&d->d_compLoc, d->compLoc)) ||
+        (rc = upload(&d->d_tileP, d->tileP)) || (rc = upload(&d->d_tileEnt, d->tileEnt))) {
+        dmma_plan_free(d);
+        return rc;
     }
     const size_t wt = (size_t)d->nOt * d->nKc * W_STAGE, pvt = (size_t)d->nTiles * d->nKc * PV_STAGE,
-                 cvt = (size_t)d->nComp * d->nKc * CV_STAGE;
-    if (!rc && (cudaMalloc((void **)&d->d_Wt, wt * 8) != cudaSuccess ||
-                cudaMalloc((void **)&d->d_PVt, pvt * 8) != cudaSuccess ||
-                cudaMalloc((void **)&d->d_CVt, cvt * 8) != cudaSuccess)) {
+                 cvt = (size_t)d->nComp * d->nKc * CV_STAGE, pot = (size_t)d->nTiles * d->nOt * POS_DOUBLES,
+                 cot = (size_t)d->nComp * d->nOt * COS_DOUBLES;
+    if (cudaMalloc((void **)&d->d_Wt, wt * 8) != cudaSuccess || cudaMalloc((void **)&d->d_PVt, pvt * 8) != cudaSuccess ||
+        cudaMalloc((void **)&d->d_CVt, cvt * 8) != cudaSuccess || cudaMalloc((void **)&d->d_POt, pot * 8) != cudaSuccess ||
+        cudaMalloc((void **)&d->d_COt, cot * 8) != cudaSuccess) {
         cudaGetLastError();
-        set_error("cudaMalloc of the tiled operand panels failed (%zu bytes)", (wt + pvt + cvt) * 8);
-        rc = QCDMET_E_ALLOC;
+        set_error("cudaMalloc of the tiled operand panels failed (%zu bytes)", (wt + pvt + cvt + pot + cot) * 8);
+        dmma_plan_free(d);
+        return QCDMET_E_ALLOC;
     }
-    if (rc) { dmma_plan_free(d); return rc; }
     *out = d;
     return QCDMET_OK;
 }
@@ -604,8 +709,9 @@ void dmma_plan_free(DmmaPlanData *d)
 {
     if (!d) return;
     cudaFree(d->d_compSites); cudaFree(d->d_compP); cudaFree(d->d_compEnt); cudaFree(d->d_tileRow);
-    cudaFree(d->d_tilePartner); cudaFree(d->d_tileSelf); cudaFree(d->d_tileQ); cudaFree(d->d_launchComps);
-    cudaFree(d->d_Wt); cudaFree(d->d_PVt); cudaFree(d->d_CVt);
+    cudaFree(d->d_tilePartner); cudaFree(d->d_tileSelf); cudaFree(d->d_tileQ); cudaFree(d->d_work);
+    cudaFree(d->d_compTile); cudaFree(d->d_compQ); cudaFree(d->d_compLoc); cudaFree(d->d_tileP); cudaFree(d->d_tileEnt);
+    cudaFree(d->d_Wt); cudaFree(d->d_PVt); cudaFree(d->d_CVt); cudaFree(d->d_POt); cudaFree(d->d_COt);
     cudaGetLastError();
     delete d;
 }
@@ -613,18 +719,23 @@ void dmma_plan_free(DmmaPlanData *d)
 int dmma_prepare_orbitals(DmmaPlanData *d, const JacView &v, cudaStream_t st)
 {
     const long long wt = (long long)d->nOt * d->nKc * W_STAGE, pvt = (long long)d->nTiles * d->nKc * PV_STAGE,
-                    cvt = (long long)d->nComp * d->nKc * CV_STAGE;
+                    cvt = (long long)d->nComp * d->nKc * CV_STAGE, pot = (long long)d->nTiles * d->nOt * POS_DOUBLES,
+                    cot = (long long)d->nComp * d->nOt * COS_DOUBLES;
     build_wt_kernel<<<(unsigned)((wt + 255) / 256), 256, 0, st>>>(v.e, v.no, v.nv, d->nKc, wt, d->d_Wt);
     QC_CUDA(cudaGetLastError());
     build_pvt_kernel<<<(unsigned)((pvt + 255) / 256), 256, 0, st>>>(v.PV, v.ldv, v.nv, d->nKc, d->d_tileRow, pvt, d->d_PVt);
     QC_CUDA(cudaGetLastError());
     build_cvt_kernel<<<(unsigned)((cvt + 255) / 256), 256, 0, st>>>(v.CvT, v.ldv, v.nv, d->nKc, d->d_compSites, cvt, d->d_CVt);
     QC_CUDA(cudaGetLastError());
+    build_pot_kernel<<<(unsigned)((pot + 255) / 256), 256, 0, st>>>(v.PO, v.ldo, v.no, d->nOt, d->d_tileRow, pot, d->d_POt);
+    QC_CUDA(cudaGetLastError());
+    build_cot_kernel<<<(unsigned)((cot + 255) / 256), 256, 0, st>>>(v.CoT, v.ldo, v.no, d->nOt, d->d_compSites, cot, d->d_COt);
+    QC_CUDA(cudaGetLastError());
     return QCDMET_OK;
 }
 
 int launch_jacobian_dmma(DmmaPlanData *d, const JacView &v, cudaStream_t st, int *launches, double *flops,
-                         cudaEvent_t ev0, cudaEvent_t ev1)
+                         cudaEvent_t ev0, cudaEvent_t ev1, bool allowSym)
 {
     *launches = 0;
     *flops = 0.0;
@@ -634,47 +745,67 @@ int launch_jacobian_dmma(DmmaPlanData *d, const JacView &v, cudaStream_t st, int
         QC_CUDA(cudaFuncSetAttribute(jac_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         d->attrSet = true;
     }
-    if (d->launchBegin != v.colBegin || d->launchEnd != v.colEnd) {
-        d->launchComps.clear();
-        for (int c = 0; c < d->nComp; ++c) {
-            bool hit = false;
-            for (int k = 0; k < MAXP && !hit; ++k) {
+    const bool wantSym = allowSym && d->symOk && v.colBegin == 0 && v.colEnd == d->P;
+    if (d->launchBegin != v.colBegin || d->launchEnd != v.colEnd || d->launchSym != wantSym) {
+        // work list: (component, tile) pairs, tile-major so that co-resident CTAs share a PVt panel.
+        // Symmetric mode (full column range): only pairs with tile(component) >= tile.
+        const bool sym = wantSym;
+        std::vector<char> hit(d->nComp, 0);
+        for (int c = 0; c < d->nComp; ++c)
+            for (int k = 0; k < MAXP && !hit[c]; ++k) {
                 const int p = d->compP[(size_t)c * MAXP + k];
-                hit = (p >= v.colBegin && p < v.colEnd);
+                hit[c] = (p >= v.colBegin && p < v.colEnd);
             }
-            if (hit) d->launchComps.push_back(c);
+        d->work.clear();
+        double fl = 0.0;
+        for (int t = 0; t < d->nTiles; ++t)
+            for (int c = 0; c < d->nComp; ++c) {
+                if (!hit[c] || (sym && d->compTile[c] < t)) continue;
+                d->work.push_back(make_int2(c, t));
+                // useful FP64 flops of this CTA (padding excluded): main loop 2 nv no per (site, row),
+                // one multiply per A element per column tile, epilogue (1 + 2 r_f) n_c per accumulator element
+                const double ns = d->compNumSites[c], nr = d->tileNumRows[t];
+                fl += ns * nr * (2.0 * d->nv * d->no + (double)d->nv * d->nOt + ns * d->no * (1.0 + 2.0 * RF));
+            }
+        if (d->work.size() > d->workCapacity) {
+            cudaFree(d->d_work);
+            d->d_work = nullptr;
+            d->workCapacity = 0;
+            if (cudaMalloc((void **)&d->d_work, d->work.size() * sizeof(int2)) != cudaSuccess) {
+                cudaGetLastError();
+                set_error("cudaMalloc of the DMMA work list failed");
+                return QCDMET_E_ALLOC;
+            }
+            d->workCapacity = d->work.size();
         }
-        if (!d->launchComps.empty())
-            QC_CUDA(cudaMemcpyAsync(d->d_launchComps, d->launchComps.data(), d->launchComps.size() * sizeof(int),
-                                    cudaMemcpyHostToDevice, st));
+        if (!d->work.empty())
+            QC_CUDA(cudaMemcpyAsync(d->d_work, d->work.data(), d->work.size() * sizeof(int2), cudaMemcpyHostToDevice, st));
         d->launchBegin = v.colBegin;
         d->launchEnd = v.colEnd;
+        d->launchSym = sym;
+        d->launchFlops = fl;
     }
     if (d->hasEmptyPerturbation)
         QC_CUDA(cudaMemsetAsync(v.J, 0, sizeof(double) * (size_t)v.Q * ncols, st));
-    if (d->launchComps.empty()) return QCDMET_OK;
+    if (d->work.empty()) return QCDMET_OK;
     DmmaArgs a;
-    a.nKc = d->nKc; a.nOt = d->nOt; a.no = v.no; a.nv = v.nv; a.ldo = v.ldo;
-    a.colBegin = v.colBegin; a.colEnd = v.colEnd; a.Q = v.Q;
-    a.Wt = d->d_Wt; a.PVt = d->d_PVt; a.CVt = d->d_CVt; a.PO = v.PO; a.CoT = v.CoT;
-    a.launchComps = d->d_launchComps; a.compSites = d->d_compSites; a.compP = d->d_compP;
+    a.nKc = d->nKc; a.nOt = d->nOt;
+    a.colBegin = v.colBegin; a.colEnd = v.colEnd; a.sym = d->launchSym ? 1 : 0; a.Q = v.Q;
+    a.Wt = d->d_Wt; a.PVt = d->d_PVt; a.CVt = d->d_CVt; a.POt = d->d_POt; a.COt = d->d_COt;
+    a.work = d->d_work; a.compTile = d->d_compTile; a.compQ = d->d_compQ; a.compLoc = d->d_compLoc;
+    a.tileP = d->d_tileP; a.tileEnt = d->d_tileEnt;
+    a.compSites = d->d_compSites; a.compP = d->d_compP;
     a.compEnt = d->d_compEnt; a.tileRow = d->d_tileRow; a.tilePartner = d->d_tilePartner;
     a.tileSelf = d->d_tileSelf; a.tileQ = d->d_tileQ; a.J = v.J;
     if (ev0) QC_CUDA(cudaEventRecord(ev0, st));
-    jac_dmma_kernel<<<dim3((unsigned)d->launchComps.size(), d->nTiles), NTHREADS, SMEM_BYTES, st>>>(a);
+    jac_dmma_kernel<<<(unsigned)d->work.size(), NTHREADS, SMEM_BYTES, st>>>(a);
     QC_CUDA(cudaGetLastError());
     if (ev1) QC_CUDA(cudaEventRecord(ev1, st));
     *launches = 1;
-    // useful FP64 flops executed (padding excluded): mainloop 2 S nv no per site (+ 1 multiply per A
-    // element), epilogue (1 + 2 r_f) n_c flop per accumulator element
-    double sites = 0.0, epi = 0.0;
-    for (int c : d->launchComps) {
-        sites += d->compNumSites[c];
-        epi += (double)d->compNumSites[c] * d->compNumSites[c];
-    }
-    *flops = sites * 2.0 * (double)d->S * d->nv * d->no + sites * (double)d->S * d->nv * d->nOt +
-             epi * (double)d->S * d->no * (1.0 + 2.0 * RF);
+    *flops = d->launchFlops;
     return QCDMET_OK;
 }
+
+bool dmma_last_launch_symmetric(const DmmaPlanData *d) { return d && d->launchSym; }
 
 }  // namespace qcdmet

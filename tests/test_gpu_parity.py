@@ -28,6 +28,7 @@ def run_plan(w, kernel, from_orbitals=None, cols=None):
     plan.compute()
     jac, c, e, d = plan.jacobian(), plan.orbitals(), plan.eigenvalues(), plan.dblocks()
     used = plan.kernel_used
+    run_plan.last_symmetric = plan.symmetric_used
     plan.close()
     return jac, c, e, d, used
 
@@ -109,18 +110,20 @@ def test_jacobian_matches_oracle_on_same_orbitals(shape, kernel):
 
 
 DMMA_SHAPES = {
-    # name: (workload factory, kernel AUTO must pick)
-    "sweep64": (lambda: wl.sweep(64), DMMA),
-    "sweep264_no_tile_edge": (lambda: wl.sweep(264), DMMA),            # no = 132: ragged 128-column tile
-    "mixed_small_frags": (lambda: wl.make_workload("mx", 61, 27, [3, 1, 4, 2, 4, 4, 1, 3, 2, 4, 3, 3, 4]), DMMA),
-    "partial_cover": (lambda: wl.make_workload("pc", 90, 40, [4, 4, 2, 3]), DMMA),
-    "many_tiles": (lambda: wl.make_workload("mt", 150, 70, [3] * 50), DMMA),   # 10 + 2/3 fragments per tile
-    "tiny_virtual_space": (lambda: wl.make_workload("tv", 40, 37, [4] * 10), DMMA),
-    "tiny_occupied_space": (lambda: wl.make_workload("to", 40, 2, [4] * 10), DMMA),
-    "bath_rows_m2": (lambda: wl.make_workload("b2", 44, 20, [2, 2, 1, 2], fit_imp_bath=True), DMMA),
-    "frag5_general": (lambda: wl.make_workload("f5", 40, 17, [5, 4, 3]), GENERAL),
-    "ti_general": (lambda: wl.hubbard24(True, l=8), GENERAL),
-    "bath_rows_m4_general": (lambda: wl.make_workload("b4", 44, 20, [4, 4], fit_imp_bath=True), GENERAL),
+    # name: (workload factory, kernel AUTO must pick, symmetric (mirrored-patch) mode expected)
+    "sweep64": (lambda: wl.sweep(64), DMMA, True),
+    "sweep264_no_tile_edge": (lambda: wl.sweep(264), DMMA, True),            # no = 132: ragged 128-column tile
+    "sweep400": (lambda: wl.sweep(400), DMMA, True),                         # 13 row tiles: many off-diagonal pairs
+    "mixed_small_frags": (lambda: wl.make_workload("mx", 61, 27, [3, 1, 4, 2, 4, 4, 1, 3, 2, 4, 3, 3, 4]), DMMA, True),
+    "partial_cover": (lambda: wl.make_workload("pc", 90, 40, [4, 4, 2, 3]), DMMA, True),
+    "many_tiles": (lambda: wl.make_workload("mt", 150, 70, [3] * 50), DMMA, True),   # 10 + 2/3 fragments per tile
+    "tiny_virtual_space": (lambda: wl.make_workload("tv", 40, 37, [4] * 10), DMMA, True),
+    "tiny_occupied_space": (lambda: wl.make_workload("to", 40, 2, [4] * 10), DMMA, True),
+    "truncated_list": (lambda: wl.sweep(160, nterms=333), DMMA, False),      # fragments without perturbations
+    "bath_rows_m2": (lambda: wl.make_workload("b2", 44, 20, [2, 2, 1, 2], fit_imp_bath=True), DMMA, False),
+    "frag5_general": (lambda: wl.make_workload("f5", 40, 17, [5, 4, 3]), GENERAL, False),
+    "ti_general": (lambda: wl.hubbard24(True, l=8), GENERAL, False),
+    "bath_rows_m4_general": (lambda: wl.make_workload("b4", 44, 20, [4, 4], fit_imp_bath=True), GENERAL, False),
 }
 
 
@@ -128,10 +131,11 @@ DMMA_SHAPES = {
 def test_kernel_selection_and_dmma_parity(shape):
     """AUTO picks the site-factorised DMMA kernel exactly where its schedule applies (<= 4 coupled
     sites, <= 4 rows per fragment) and the general kernel elsewhere; both match the oracle."""
-    factory, expect = DMMA_SHAPES[shape]
+    factory, expect, expect_sym = DMMA_SHAPES[shape]
     w = factory()
     jac, c, e, d, used = run_plan(w, _lib.KERNEL_AUTO)
     assert used == expect
+    assert run_plan.last_symmetric == expect_sym
     assert np.abs(jac - oracle_jac(w, c, e)).max() <= TOL
     if expect == GENERAL:
         plan = _lib.Plan(w.norb, w.num_pairs, w.h1start, w.h1row, w.h1col, w.row_start, w.rows, w.row_idx)
@@ -141,6 +145,9 @@ def test_kernel_selection_and_dmma_parity(shape):
     else:
         gen, *_ = run_plan(w, _lib.KERNEL_GENERAL, from_orbitals=(c, e))
         assert np.abs(jac - gen).max() <= TOL
+        nosym, *_ = run_plan(w, _lib.KERNEL_DMMA_NOSYM, from_orbitals=(c, e))
+        assert not run_plan.last_symmetric
+        assert np.abs(jac - nosym).max() <= 1e-12
 
 
 def test_dmma_exact_block_symmetry_and_empty_perturbation():
@@ -166,11 +173,20 @@ def test_from_given_orbitals_and_column_slices(kernel):
     full, *_ = run_plan(w, KERNELS[kernel], from_orbitals=(c, e))
     ref = oracle_jac(w, c, e)
     assert np.abs(full - ref).max() <= TOL
-    # column sharding: any slice equals the same columns of the full Jacobian, bit for bit
+    # column sharding: any slice equals the same columns of the full Jacobian -- bit for bit for the
+    # general kernel; the DMMA kernel computes the full range in symmetric mode (mirrored patches), the
+    # slices without it, so those agree to rounding only
     for lo, hi in ((0, 1), (7, 133), (150, 300), (299, 300), (40, 40)):
         part, *_ = run_plan(w, KERNELS[kernel], from_orbitals=(c, e), cols=(lo, hi))
         assert part.shape == (w.nresid, hi - lo)
-        assert np.array_equal(part, full[:, lo:hi])
+        if kernel == "general" or hi == lo:
+            assert np.array_equal(part, full[:, lo:hi])
+        else:
+            assert np.abs(part - full[:, lo:hi]).max() <= 1e-12
+    if kernel != "general":
+        a, *_ = run_plan(w, _lib.KERNEL_DMMA_NOSYM, from_orbitals=(c, e))
+        b, *_ = run_plan(w, _lib.KERNEL_DMMA_NOSYM, from_orbitals=(c, e), cols=(7, 133))
+        assert np.array_equal(b, a[:, 7:133])
 
 
 def test_sn2_like_sampled_columns():
