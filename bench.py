@@ -235,17 +235,41 @@ def run_b200(args):
     plan.set_orbitals(c, e)
 
     gathered = mine = None
+    fused = False
     if world > 1:
-        # in-place all-gather: each rank's kernels write straight into its slot of the gathered buffer
-        gathered = torch.empty(world * per * Q, dtype=torch.float64, device="cuda")
-        mine = gathered[rank * per * Q:(rank + 1) * per * Q]
-        plan.set_output_device(mine.data_ptr(), mine.numel())
+        # preferred: fused compute + all-gather -- every rank maps every rank's full Jacobian (CUDA IPC) and
+        # the kernel stores each element into all of them over NVLink; the block-pair work list (symmetric
+        # mode) is split evenly over the ranks.  Needs peer mapping; otherwise fall back to column shards +
+        # NCCL all-gather.
+        try:
+            plan.set_columns(0, P)
+            handles = [None] * world
+            dist.all_gather_object(handles, plan.export_jacobian())
+            plan.attach_peers(rank, handles)
+            fused = True
+        except _lib.QcdmetError as exc:
+            print(f"[rank {rank}] fused all-gather unavailable ({exc}); falling back to NCCL all-gather", file=sys.stderr)
+        flags = [None] * world
+        dist.all_gather_object(flags, fused)
+        fused = all(flags)
+        if fused:
+            lo, hi = 0, P
+            sync_t = torch.zeros(1, device="cuda")
+        else:
+            plan.detach_peers()
+            plan.set_columns(lo, hi)
+            # in-place all-gather: each rank's kernels write straight into its slot of the gathered buffer
+            gathered = torch.empty(world * per * Q, dtype=torch.float64, device="cuda")
+            mine = gathered[rank * per * Q:(rank + 1) * per * Q]
+            plan.set_output_device(mine.data_ptr(), mine.numel())
     flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device="cuda")
 
     def step():
         flush.zero_()                       # evict L2 between steps (256 MB > 126 MB L2)
         plan.compute()
-        if world > 1:
+        if fused:
+            dist.all_reduce(sync_t)          # cross-rank barrier on the stream: all peer stores have landed
+        elif world > 1:
             dist.all_gather_into_tensor(gathered, mine)
 
     for _ in range(args.warmup):
@@ -271,7 +295,9 @@ def run_b200(args):
     if os.environ.get("QCDMET_BENCH_DEBUG"):
         torch.cuda.synchronize()
         t0 = time.perf_counter(); plan.compute(); t1 = time.perf_counter(); plan.sync(); t2 = time.perf_counter()
-        if world > 1:
+        if fused:
+            dist.all_reduce(sync_t)
+        elif world > 1:
             dist.all_gather_into_tensor(gathered, mine)
         torch.cuda.synchronize(); t3 = time.perf_counter()
         print(f"[rank {rank}] launch {1e3*(t1-t0):.2f} ms, kernel {1e3*(t2-t1):.2f} ms, gather {1e3*(t3-t2):.2f} ms",
@@ -308,13 +334,19 @@ def run_b200(args):
     e2e = None
     if not args.no_e2e:
         h0_pinned = torch.from_numpy(np.ascontiguousarray(w.h0)).pin_memory()
-        out_pinned = torch.empty(Q * max(hi - lo, 1), dtype=torch.float64).pin_memory()
+        need_out = (hi - lo) if (not fused or rank == 0) else 0
+        out_pinned = torch.empty(Q * max(need_out, 1), dtype=torch.float64).pin_memory()
         h0_np = h0_pinned.numpy()
-        out_np = out_pinned.numpy()[:Q * (hi - lo)].reshape((Q, hi - lo), order="F")
+        out_np = out_pinned.numpy()[:Q * need_out].reshape((Q, need_out), order="F")
 
         def e2e_step():
             plan.set_h0(h0_np)              # H2D + cuSOLVER syevd + panels
             plan.compute()
+            if fused:
+                dist.all_reduce(sync_t)
+                if rank != 0:
+                    torch.cuda.synchronize()
+                    return                  # the least-squares update lives on rank 0's host
             plan.jacobian(out=out_np)       # D2H (blocking)
 
         for _ in range(min(args.warmup, 2)):
@@ -333,9 +365,9 @@ def run_b200(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             t_e2e = float(t.item())
         e2e = {"value": P / t_e2e, "unit": UNIT, "h2d_bytes_per_step": int(8 * w.norb * w.norb),
-               "d2h_bytes_per_step": int(8 * Q * (hi - lo)), "ms_per_step": 1e3 * t_e2e,
+               "d2h_bytes_per_step": int(8 * Q * need_out), "ms_per_step": 1e3 * t_e2e,
                "includes": "H2D of H0 from pinned host memory, cuSOLVER syevd, panel build, Jacobian kernels, "
-                           "D2H of the rank's (Q x P/N) slice into pinned host memory"}
+                           "D2H into pinned host memory (rank's slice; fused multi-GPU mode: the full Jacobian on rank 0)"}
 
     if rank == 0:
         peak, peak_burst, peak_src = fp64_peak()
@@ -345,6 +377,8 @@ def run_b200(args):
         nnz = np.diff(w.h1start[lo:hi + 1]).astype(float)
         w_cols = float(np.sum(2.0 * w.nrows * nv * w.num_pairs + (2.0 * nnz + 1.0) * nv * w.num_pairs
                               + 2.0 * w.num_pairs * Q + 2.0 * Q))
+        if fused:
+            w_cols /= world      # this rank executed 1/world of the block-pair list
         cpu = None
         if not args.no_cpu_baseline:
             cpu = cpu_reference_rate(w, args.cpu_sample_cols or default_sample_cols(args.norb))
@@ -355,7 +389,11 @@ def run_b200(args):
             "config": {"workload": f"response sweep Norb={w.norb} Nocc={w.num_pairs} P={P} "
                                    f"(4-site fragments, impurity-only rows, Q={Q})",
                        "kernel": {1: "general", 2: "dmma"}.get(kernel_used, str(kernel_used)),
-                       "sharding": f"{world} x {per} columns (whole fragments), NCCL all-gather of the slices inside the timed region" if world > 1 else "single GPU",
+                       "sharding": ("single GPU" if world == 1 else
+                                    f"{world} ranks, block-pair work list split evenly, fused all-gather: each Jacobian element "
+                                    "stored into every rank's buffer by NVLink peer stores, stream barrier (1-element NCCL all-reduce) "
+                                    "inside the timed region" if fused else
+                                    f"{world} x {per} columns (whole fragments), NCCL all-gather of the slices inside the timed region"),
                        "l2": "256 MB buffer zeroed between steps (L2 flush), inside the timed region"},
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                          "frac": (achieved / peak) if achieved else None, "traffic": None,

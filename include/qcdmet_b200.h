@@ -115,6 +115,21 @@ int qcdmet_plan_set_stream(qcdmet_plan *plan, void *stream);
  * plan-owned buffer. */
 int qcdmet_plan_set_output_device(qcdmet_plan *plan, void *device_ptr, long long capacity);
 
+/* ---- Multi-GPU, one process per GPU on one node: fused compute + all-gather over NVLink --------
+ * Every rank exports the IPC handle of its full (Q x P) Jacobian buffer, the handles are exchanged
+ * by any host transport (bench.py: torch.distributed.all_gather_object), and every rank maps all
+ * peers.  compute() then executes this rank's share of the (equal-cost) block-pair work list and
+ * stores every Jacobian element it produces into ALL ranks' buffers with peer stores; after a
+ * cross-rank barrier placed behind compute() on the stream, every rank holds the complete Jacobian.
+ * Needs the DMMA kernel and the full column range. */
+#define QCDMET_IPC_HANDLE_BYTES 64
+#define QCDMET_MAX_RANKS 8
+int qcdmet_plan_export_jacobian(qcdmet_plan *plan, void *handle /* QCDMET_IPC_HANDLE_BYTES */);
+int qcdmet_plan_attach_peers(qcdmet_plan *plan, int nranks, int rank, const void *handles /* nranks x 64 bytes */);
+/* Same with raw device pointers (single-process multi-plan set-ups and tests); ptrs[rank] may be NULL. */
+int qcdmet_plan_attach_peer_pointers(qcdmet_plan *plan, int nranks, int rank, void *const *ptrs);
+int qcdmet_plan_detach_peers(qcdmet_plan *plan);
+
 /* Upload H0 (host), run cuSOLVER syevd on the device, build the operand panels. */
 int qcdmet_plan_set_h0(qcdmet_plan *plan, const double *H0);
 /* Upload orbitals (host; layout as in qcdmet_jacobian_from_orbitals), build the panels. */

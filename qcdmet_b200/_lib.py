@@ -43,6 +43,10 @@ SIGNATURES = {
     "qcdmet_plan_set_kernel": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "qcdmet_plan_set_stream": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     "qcdmet_plan_set_output_device": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_longlong]),
+    "qcdmet_plan_export_jacobian": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
+    "qcdmet_plan_attach_peers": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
+    "qcdmet_plan_attach_peer_pointers": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
+    "qcdmet_plan_detach_peers": (ctypes.c_int, [ctypes.c_void_p]),
     "qcdmet_plan_set_h0": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     "qcdmet_plan_set_orbitals": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "qcdmet_plan_compute": (ctypes.c_int, [ctypes.c_void_p]),
@@ -148,6 +152,25 @@ class Plan:
     def set_output_device(self, ptr, capacity):
         """Jacobian slice goes to caller-owned device memory (ptr: int address, capacity in doubles)."""
         check(self.lib.qcdmet_plan_set_output_device(self.handle, ctypes.c_void_p(ptr), int(capacity)))
+
+    def export_jacobian(self):
+        """64-byte CUDA IPC handle of this plan's full (Q x P) Jacobian buffer."""
+        buf = ctypes.create_string_buffer(64)
+        check(self.lib.qcdmet_plan_export_jacobian(self.handle, buf))
+        return buf.raw
+
+    def attach_peers(self, rank, handles):
+        """handles: list of the 64-byte IPC handles of all ranks (own entry ignored)."""
+        blob = b"".join(handles)
+        assert len(blob) == 64 * len(handles)
+        check(self.lib.qcdmet_plan_attach_peers(self.handle, len(handles), int(rank), blob))
+
+    def attach_peer_pointers(self, rank, ptrs):
+        arr = (ctypes.c_void_p * len(ptrs))(*[ctypes.c_void_p(p) for p in ptrs])
+        check(self.lib.qcdmet_plan_attach_peer_pointers(self.handle, len(ptrs), int(rank), arr))
+
+    def detach_peers(self):
+        check(self.lib.qcdmet_plan_detach_peers(self.handle))
 
     def set_h0(self, h0):
         h0 = as_f64(h0)

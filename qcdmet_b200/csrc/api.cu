@@ -56,6 +56,9 @@ struct qcdmet_plan {
     int launches = 0;
     double flops = 0.0;
     bool symmetric_used = false;
+    bool peers_on = false;
+    PeerSet peers;
+    void *ipc_opened[QCDMET_MAX_PEERS] = {nullptr};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;   // around the dominant kernel of the last compute
 };
 
@@ -311,6 +314,7 @@ int qcdmet_plan_create(qcdmet_plan **out, int device, int Norb, int Nterms, int 
 int qcdmet_plan_destroy(qcdmet_plan *p)
 {
     if (!p) return QCDMET_OK;
+    qcdmet_plan_detach_peers(p);
     DeviceGuard guard(p->device);
     cudaFree(p->d_h1start); cudaFree(p->d_h1row); cudaFree(p->d_h1col);
     cudaFree(p->d_rowStart); cudaFree(p->d_rowFrag); cudaFree(p->d_rowIdx); cudaFree(p->d_qoff);
@@ -413,13 +417,19 @@ int qcdmet_plan_compute(qcdmet_plan *p)
     JacView v = make_view(p);
     const bool use_dmma = (p->kernel_req == QCDMET_KERNEL_DMMA) || (p->kernel_req == QCDMET_KERNEL_DMMA_NOSYM) ||
                           (p->kernel_req == QCDMET_KERNEL_AUTO && p->dmma_ok);
+    if (p->peers_on) {
+        QC_CHECK(use_dmma, QCDMET_E_STATE, "peer (fused all-gather) mode needs the DMMA kernel: %s", p->dmma_why.c_str());
+        QC_CHECK(p->colBegin == 0 && p->colEnd == p->P && !p->d_J_ext, QCDMET_E_STATE,
+                 "peer mode works on the full column range with the plan-owned buffer");
+        QC_CHECK(p->peers.J[p->peers.rank] == p->d_J, QCDMET_E_STATE, "own Jacobian buffer moved after export");
+    }
     if (!p->ev0) {
         QC_CUDA(cudaEventCreate(&p->ev0));
         QC_CUDA(cudaEventCreate(&p->ev1));
     }
     if (use_dmma) {
         QC_TRY(launch_jacobian_dmma(p->dmma, v, p->stream, &p->launches, &p->flops, p->ev0, p->ev1,
-                                    p->kernel_req != QCDMET_KERNEL_DMMA_NOSYM));
+                                    p->kernel_req != QCDMET_KERNEL_DMMA_NOSYM, p->peers_on ? &p->peers : nullptr));
         p->symmetric_used = dmma_last_launch_symmetric(p->dmma);
         p->kernel_used = QCDMET_KERNEL_DMMA;
     } else {
@@ -430,6 +440,88 @@ int qcdmet_plan_compute(qcdmet_plan *p)
     }
     p->have_jac = true;
     return QCDMET_OK;
+}
+
+int qcdmet_plan_detach_peers(qcdmet_plan *p)
+{
+    QC_CHECK(p != nullptr, QCDMET_E_ARG, "plan is NULL");
+    DeviceGuard guard(p->device);
+    for (int r = 0; r < QCDMET_MAX_PEERS; ++r) {
+        if (p->ipc_opened[r]) cudaIpcCloseMemHandle(p->ipc_opened[r]);
+        p->ipc_opened[r] = nullptr;
+        p->peers.J[r] = nullptr;
+    }
+    cudaGetLastError();
+    p->peers_on = false;
+    p->peers.nranks = 1;
+    p->peers.rank = 0;
+    return QCDMET_OK;
+}
+
+int qcdmet_plan_export_jacobian(qcdmet_plan *p, void *handle)
+{
+    QC_CHECK(p != nullptr && handle != nullptr, QCDMET_E_ARG, "plan or handle is NULL");
+    QC_CHECK(p->colBegin == 0 && p->colEnd == p->P && !p->d_J_ext, QCDMET_E_STATE,
+             "export needs the full column range and the plan-owned buffer");
+    DeviceGuard guard(p->device);
+    QC_TRY(ensure_jacobian_buffer(p));
+    static_assert(sizeof(cudaIpcMemHandle_t) == QCDMET_IPC_HANDLE_BYTES, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    QC_CUDA(cudaIpcGetMemHandle(&h, p->d_J));
+    memcpy(handle, &h, sizeof(h));
+    return QCDMET_OK;
+}
+
+int qcdmet_plan_attach_peer_pointers(qcdmet_plan *p, int nranks, int rank, void *const *ptrs)
+{
+    QC_CHECK(p != nullptr && ptrs != nullptr, QCDMET_E_ARG, "plan or pointer list is NULL");
+    QC_CHECK(nranks >= 1 && nranks <= QCDMET_MAX_PEERS && rank >= 0 && rank < nranks, QCDMET_E_ARG,
+             "invalid rank %d of %d (at most %d ranks)", rank, nranks, QCDMET_MAX_PEERS);
+    QC_CHECK(p->dmma_ok, QCDMET_E_STATE, "peer mode needs the DMMA kernel: %s", p->dmma_why.c_str());
+    QC_CHECK(p->colBegin == 0 && p->colEnd == p->P && !p->d_J_ext, QCDMET_E_STATE,
+             "peer mode needs the full column range and the plan-owned buffer");
+    DeviceGuard guard(p->device);
+    QC_TRY(ensure_jacobian_buffer(p));
+    QC_CHECK(ptrs[rank] == nullptr || ptrs[rank] == (void *)p->d_J, QCDMET_E_ARG,
+             "ptrs[rank] must be this plan's own buffer (or NULL)");
+    for (int r = 0; r < nranks; ++r) {
+        QC_CHECK(r == rank || ptrs[r] != nullptr, QCDMET_E_ARG, "peer pointer %d is NULL", r);
+        p->peers.J[r] = (r == rank) ? p->d_J : (double *)ptrs[r];
+    }
+    p->peers.nranks = nranks;
+    p->peers.rank = rank;
+    p->peers_on = true;
+    p->have_jac = false;
+    return QCDMET_OK;
+}
+
+int qcdmet_plan_attach_peers(qcdmet_plan *p, int nranks, int rank, const void *handles)
+{
+    QC_CHECK(p != nullptr && handles != nullptr, QCDMET_E_ARG, "plan or handle list is NULL");
+    QC_CHECK(nranks >= 1 && nranks <= QCDMET_MAX_PEERS && rank >= 0 && rank < nranks, QCDMET_E_ARG,
+             "invalid rank %d of %d (at most %d ranks)", rank, nranks, QCDMET_MAX_PEERS);
+    QC_TRY(qcdmet_plan_detach_peers(p));
+    DeviceGuard guard(p->device);
+    void *ptrs[QCDMET_MAX_PEERS] = {nullptr};
+    for (int r = 0; r < nranks; ++r) {
+        if (r == rank) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const char *)handles + (size_t)r * QCDMET_IPC_HANDLE_BYTES, sizeof(h));
+        cudaError_t err = cudaIpcOpenMemHandle(&ptrs[r], h, cudaIpcMemLazyEnablePeerAccess);
+        if (err != cudaSuccess) {
+            cudaGetLastError();
+            set_error("cudaIpcOpenMemHandle for rank %d failed: %s", r, cudaGetErrorString(err));
+            for (int q = 0; q < r; ++q)
+                if (ptrs[q]) cudaIpcCloseMemHandle(ptrs[q]);
+            return QCDMET_E_CUDA;
+        }
+    }
+    int rc = qcdmet_plan_attach_peer_pointers(p, nranks, rank, ptrs);
+    for (int r = 0; r < nranks; ++r) {
+        if (rc == QCDMET_OK) p->ipc_opened[r] = ptrs[r];
+        else if (ptrs[r]) cudaIpcCloseMemHandle(ptrs[r]);
+    }
+    return rc;
 }
 
 int qcdmet_plan_sync(qcdmet_plan *p)

@@ -77,6 +77,14 @@ int launch_one_rdm(const double *CoT, int ldo, int N, int no, double *D, cudaStr
 int launch_jacobian_general(const JacView &v, cudaStream_t st, int *launches, double *flops,
                             cudaEvent_t ev0, cudaEvent_t ev1);
 
+// Destinations of the fused all-gather: every rank of a node maps every rank's full Jacobian buffer;
+// the DMMA kernel stores each element it produces into all of them (NVLink peer stores).
+#define QCDMET_MAX_PEERS 8
+struct PeerSet {
+    int nranks = 1, rank = 0;
+    double *J[QCDMET_MAX_PEERS] = {nullptr};
+};
+
 // kernels_dmma.cu
 struct DmmaPlanData;   // site-factorised schedule (device arrays), built once per plan
 bool dmma_eligible(int N, int P, int F, const int *h1start, const int *h1row, const int *h1col,
@@ -86,7 +94,8 @@ int dmma_plan_build(DmmaPlanData **out, int N, int no, int P, int F, const int *
 void dmma_plan_free(DmmaPlanData *d);
 int dmma_prepare_orbitals(DmmaPlanData *d, const JacView &v, cudaStream_t st);
 int launch_jacobian_dmma(DmmaPlanData *d, const JacView &v, cudaStream_t st, int *launches,
-                         double *flops, cudaEvent_t ev0, cudaEvent_t ev1, bool allowSym);
+                         double *flops, cudaEvent_t ev0, cudaEvent_t ev1, bool allowSym,
+                         const PeerSet *peers);
 bool dmma_last_launch_symmetric(const DmmaPlanData *d);
 
 }  // namespace qcdmet

@@ -97,7 +97,8 @@ struct DmmaArgs {
     const unsigned char *tilePartner;   // [nTiles][AT][RF] slot of the j-th row of the fragment, AT = none
     const unsigned char *tileSelf;      // [nTiles][AT]  a_loc | r_f << 4
     const long long *tileQ;             // [nTiles][AT]  qoff[f] + a_loc
-    double *J;
+    int nDest;                          // destinations of every Jacobian store (1, or the ranks of a node)
+    double *J[QCDMET_MAX_PEERS];        // J[0..nDest): own buffer and peer-mapped buffers (NVLink P2P stores)
 };
 
 // ------------------------------------------------------------------------------------------
@@ -224,6 +225,15 @@ __global__ void build_cot_kernel(const double *__restrict__ CoT, int ldo, int no
     const int r = within / BN, o = ot * BN + within % BN;
     const int site = compSites[comp * RT + r];
     COt[idx] = (site >= 0 && o < no) ? CoT[(size_t)site * ldo + o] : 0.0;
+}
+
+// Columns of perturbations without elements (nnz_p = 0) are exactly zero.
+struct ZeroArgs { int nDest; double *J[QCDMET_MAX_PEERS]; };
+__global__ void zero_columns_kernel(ZeroArgs z, const int *__restrict__ cols, int colBegin, long long Q)
+{
+    const size_t base = (size_t)Q * (cols[blockIdx.y] - colBegin);
+    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < Q; q += (long long)gridDim.x * blockDim.x)
+        for (int dst = 0; dst < z.nDest; ++dst) z.J[dst][base + q] = 0.0;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -417,7 +427,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) jac_dmma_kernel(const DmmaArgs g)
             gab += Ns[i1] + Ns1[i1];
             gba += Ns[i2] + Ns1[i2];
         }
-        g.J[(size_t)g.Q * (p - g.colBegin) + qrow[a_slot] + (long long)rf * j] = 2.0 * (gab + gba);
+        const size_t off = (size_t)g.Q * (p - g.colBegin) + qrow[a_slot] + (long long)rf * j;
+        const double val = 2.0 * (gab + gba);
+        for (int dst = 0; dst < g.nDest; ++dst) g.J[dst][off] = val;
     }
     // patch 2 (symmetric mode, off-diagonal block pairs): rows of the component's own fragment x
     // perturbations of the blocks in the tile, from M_a[r,o] = M_r[a,o]:
@@ -446,7 +458,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) jac_dmma_kernel(const DmmaArgs g)
                 grc += Ns[i1] + Ns1[i1];
                 gcr += Ns[i2] + Ns1[i2];
             }
-            g.J[(size_t)g.Q * (p - g.colBegin) + q0 + (lr & 15) + (long long)rf * (lc & 15)] = 2.0 * (grc + gcr);
+            const size_t off = (size_t)g.Q * (p - g.colBegin) + q0 + (lr & 15) + (long long)rf * (lc & 15);
+            const double val = 2.0 * (grc + gcr);
+            for (int dst = 0; dst < g.nDest; ++dst) g.J[dst][off] = val;
         }
     }
 }
@@ -459,7 +473,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) jac_dmma_kernel(const DmmaArgs g)
 struct DmmaPlanData {
     int N = 0, no = 0, nv = 0, P = 0, S = 0;
     int nComp = 0, nTiles = 0, nKc = 0, nOt = 0;
-    bool hasEmptyPerturbation = false;
+    std::vector<int> emptyP;            // perturbations without elements: zero columns
+    int *d_emptyCols = nullptr;
+    std::vector<int> emptyInRange;
     bool symOk = false;                 // fragments == site groups of the perturbation list
     std::vector<int> compSites, compP, compNumSites, compTile;
     std::vector<long long> compQ;
@@ -468,7 +484,7 @@ struct DmmaPlanData {
     std::vector<unsigned char> tilePartner, tileSelf, tileEnt;
     std::vector<long long> tileQ;
     std::vector<int2> work;
-    int launchBegin = -1, launchEnd = -1;
+    int launchBegin = -1, launchEnd = -1, launchRank = -1, launchRanks = -1;
     bool launchSym = false;
     double launchFlops = 0.0;
     int *d_compSites = nullptr, *d_compP = nullptr, *d_tileRow = nullptr, *d_compTile = nullptr, *d_tileP = nullptr;
@@ -536,7 +552,7 @@ Schedule build_schedule(int N, int no, int P, int F, const int *h1start, const i
     std::vector<char> used(N, 0);
     for (int p = 0; p < P; ++p) {
         const int b = h1start[p], e = h1start[p + 1];
-        if (e == b) { d.hasEmptyPerturbation = true; continue; }
+        if (e == b) { d.emptyP.push_back(p); continue; }
         if (e - b > MAXE) { sc.why = "a perturbation has more than 4 elements (translation-invariant list?)"; return sc; }
         for (int k = b; k < e; ++k) {
             used[h1row[k]] = used[h1col[k]] = 1;
@@ -712,6 +728,7 @@ void dmma_plan_free(DmmaPlanData *d)
     cudaFree(d->d_tilePartner); cudaFree(d->d_tileSelf); cudaFree(d->d_tileQ); cudaFree(d->d_work);
     cudaFree(d->d_compTile); cudaFree(d->d_compQ); cudaFree(d->d_compLoc); cudaFree(d->d_tileP); cudaFree(d->d_tileEnt);
     cudaFree(d->d_Wt); cudaFree(d->d_PVt); cudaFree(d->d_CVt); cudaFree(d->d_POt); cudaFree(d->d_COt);
+    cudaFree(d->d_emptyCols);
     cudaGetLastError();
     delete d;
 }
@@ -735,7 +752,7 @@ int dmma_prepare_orbitals(DmmaPlanData *d, const JacView &v, cudaStream_t st)
 }
 
 int launch_jacobian_dmma(DmmaPlanData *d, const JacView &v, cudaStream_t st, int *launches, double *flops,
-                         cudaEvent_t ev0, cudaEvent_t ev1, bool allowSym)
+                         cudaEvent_t ev0, cudaEvent_t ev1, bool allowSym, const PeerSet *peers)
 {
     *launches = 0;
     *flops = 0.0;
@@ -746,7 +763,9 @@ int launch_jacobian_dmma(DmmaPlanData *d, const JacView &v, cudaStream_t st, int
         d->attrSet = true;
     }
     const bool wantSym = allowSym && d->symOk && v.colBegin == 0 && v.colEnd == d->P;
-    if (d->launchBegin != v.colBegin || d->launchEnd != v.colEnd || d->launchSym != wantSym) {
+    const int shareRank = peers ? peers->rank : 0, shareN = peers ? peers->nranks : 1;
+    if (d->launchBegin != v.colBegin || d->launchEnd != v.colEnd || d->launchSym != wantSym ||
+        d->launchRank != shareRank || d->launchRanks != shareN) {
         // work list: (component, tile) pairs, tile-major so that co-resident CTAs share a PVt panel.
         // Symmetric mode (full column range): only pairs with tile(component) >= tile.
         const bool sym = wantSym;
@@ -756,17 +775,35 @@ int launch_jacobian_dmma(DmmaPlanData *d, const JacView &v, cudaStream_t st, int
                 const int p = d->compP[(size_t)c * MAXP + k];
                 hit[c] = (p >= v.colBegin && p < v.colEnd);
             }
-        d->work.clear();
-        double fl = 0.0;
+        std::vector<int2> all;
         for (int t = 0; t < d->nTiles; ++t)
             for (int c = 0; c < d->nComp; ++c) {
                 if (!hit[c] || (sym && d->compTile[c] < t)) continue;
-                d->work.push_back(make_int2(c, t));
-                // useful FP64 flops of this CTA (padding excluded): main loop 2 nv no per (site, row),
-                // one multiply per A element per column tile, epilogue (1 + 2 r_f) n_c per accumulator element
-                const double ns = d->compNumSites[c], nr = d->tileNumRows[t];
-                fl += ns * nr * (2.0 * d->nv * d->no + (double)d->nv * d->nOt + ns * d->no * (1.0 + 2.0 * RF));
+                all.push_back(make_int2(c, t));
             }
+        // this rank's share: a contiguous slice of the (equal-cost) block-pair list
+        const size_t wb = all.size() * (size_t)shareRank / shareN, we = all.size() * (size_t)(shareRank + 1) / shareN;
+        d->work.assign(all.begin() + wb, all.begin() + we);
+        double fl = 0.0;
+        for (const int2 &wk : d->work) {
+            // useful FP64 flops of this CTA (padding excluded): main loop 2 nv no per (site, row),
+            // one multiply per A element per column tile, epilogue (1 + 2 r_f) n_c per accumulator element
+            const double ns = d->compNumSites[wk.x], nr = d->tileNumRows[wk.y];
+            fl += ns * nr * (2.0 * d->nv * d->no + (double)d->nv * d->nOt + ns * d->no * (1.0 + 2.0 * RF));
+        }
+        d->emptyInRange.clear();
+        if (shareRank == 0)
+            for (int p : d->emptyP)
+                if (p >= v.colBegin && p < v.colEnd) d->emptyInRange.push_back(p);
+        if (!d->emptyInRange.empty()) {
+            if (!d->d_emptyCols && cudaMalloc((void **)&d->d_emptyCols, std::max<size_t>(d->emptyP.size(), 1) * sizeof(int)) != cudaSuccess) {
+                cudaGetLastError();
+                set_error("cudaMalloc failed (empty-column list)");
+                return QCDMET_E_ALLOC;
+            }
+            QC_CUDA(cudaMemcpyAsync(d->d_emptyCols, d->emptyInRange.data(), d->emptyInRange.size() * sizeof(int),
+                                    cudaMemcpyHostToDevice, st));
+        }
         if (d->work.size() > d->workCapacity) {
             cudaFree(d->d_work);
             d->d_work = nullptr;
@@ -784,9 +821,18 @@ int launch_jacobian_dmma(DmmaPlanData *d, const JacView &v, cudaStream_t st, int
         d->launchEnd = v.colEnd;
         d->launchSym = sym;
         d->launchFlops = fl;
+        d->launchRank = shareRank;
+        d->launchRanks = shareN;
     }
-    if (d->hasEmptyPerturbation)
-        QC_CUDA(cudaMemsetAsync(v.J, 0, sizeof(double) * (size_t)v.Q * ncols, st));
+    ZeroArgs z;
+    z.nDest = peers ? peers->nranks : 1;
+    for (int r = 0; r < QCDMET_MAX_PEERS; ++r) z.J[r] = (peers && r < peers->nranks) ? peers->J[r] : (r == 0 ? v.J : nullptr);
+    if (!d->emptyInRange.empty()) {
+        const unsigned gx = (unsigned)std::min<long long>((v.Q + 255) / 256, 1024);
+        zero_columns_kernel<<<dim3(gx, (unsigned)d->emptyInRange.size()), 256, 0, st>>>(z, d->d_emptyCols, v.colBegin, v.Q);
+        QC_CUDA(cudaGetLastError());
+        *launches += 1;
+    }
     if (d->work.empty()) return QCDMET_OK;
     DmmaArgs a;
     a.nKc = d->nKc; a.nOt = d->nOt;
@@ -796,12 +842,14 @@ int launch_jacobian_dmma(DmmaPlanData *d, const JacView &v, cudaStream_t st, int
     a.tileP = d->d_tileP; a.tileEnt = d->d_tileEnt;
     a.compSites = d->d_compSites; a.compP = d->d_compP;
     a.compEnt = d->d_compEnt; a.tileRow = d->d_tileRow; a.tilePartner = d->d_tilePartner;
-    a.tileSelf = d->d_tileSelf; a.tileQ = d->d_tileQ; a.J = v.J;
+    a.tileSelf = d->d_tileSelf; a.tileQ = d->d_tileQ;
+    a.nDest = z.nDest;
+    for (int r = 0; r < QCDMET_MAX_PEERS; ++r) a.J[r] = z.J[r];
     if (ev0) QC_CUDA(cudaEventRecord(ev0, st));
     jac_dmma_kernel<<<(unsigned)d->work.size(), NTHREADS, SMEM_BYTES, st>>>(a);
     QC_CUDA(cudaGetLastError());
     if (ev1) QC_CUDA(cudaEventRecord(ev1, st));
-    *launches = 1;
+    *launches += 1;
     *flops = d->launchFlops;
     return QCDMET_OK;
 }

@@ -189,6 +189,35 @@ def test_from_given_orbitals_and_column_slices(kernel):
         assert np.array_equal(b, a[:, 7:133])
 
 
+@pytest.mark.parametrize("nranks", [2, 3])
+def test_fused_allgather_ranks_emulated_on_one_device(nranks):
+    """The multi-GPU path (each rank executes its share of the block-pair list and stores every element
+    into ALL ranks' Jacobian buffers) with the ranks emulated as plans on one device and plain device
+    pointers in place of IPC-mapped peers: every buffer must end up holding the complete Jacobian."""
+    w = wl.sweep(200)
+    w.h1start = np.concatenate([w.h1start[:31], w.h1start[30:]]).astype(np.int32)   # + one empty perturbation
+    e, c = ro.eigh_sorted(w.h0)
+    ref, *_ = run_plan(w, _lib.KERNEL_AUTO, from_orbitals=(c, e))
+    plans = []
+    for r in range(nranks):
+        p = _lib.Plan(w.norb, w.num_pairs, w.h1start, w.h1row, w.h1col, w.row_start, w.rows, w.row_idx)
+        p.set_orbitals(c, e)
+        assert len(p.export_jacobian()) == 64
+        plans.append(p)
+    ptrs = [p.device_ptr() for p in plans]
+    for r, p in enumerate(plans):
+        p.attach_peer_pointers(r, ptrs)
+    for p in plans:
+        p.compute()
+    for p in plans:
+        p.sync()
+    assert sum(p.flops for p in plans) == pytest.approx(plans[0].flops * nranks, rel=0.02)
+    for p in plans:
+        assert p.symmetric_used
+        assert np.array_equal(p.jacobian(), ref)
+        p.close()
+
+
 def test_sn2_like_sampled_columns():
     w = wl.sn2_like()
     e, c = ro.eigh_sorted(w.h0)
