@@ -32,6 +32,7 @@ if ROOT not in sys.path:
 
 import numpy as np  # noqa: E402
 
+print_json = None
 METRIC = "umat_jacobian_columns_per_s"
 UNIT = "columns/s"
 
@@ -182,7 +183,7 @@ def run_reference(args):
     for i in range(warm + args.steps):
         info = cpu_reference_rate(w, cols)
         if info is None:
-            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libqcdmet_ref_mkl.so not built"}))
+            print_json({"impl": "reference", "unavailable": "oracle/_ref/libqcdmet_ref_mkl.so not built"})
             return
         if i >= warm:
             rates.append(info)
@@ -199,7 +200,7 @@ def run_reference(args):
                                    f"(4-site fragments, Q={w.nresid})", "sample_cols_per_step": cols},
             "cpu_baseline": info,
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    print_json(line)
 
 
 # ------------------------------------------------------------------------------------------
@@ -409,7 +410,7 @@ def run_b200(args):
             "clocks": clocks,
             "parity_check_max_abs_err": check,
         }
-        print(json.dumps(line))
+        print_json(line)
     plan.close()
     if world > 1:
         dist.destroy_process_group()
@@ -417,6 +418,14 @@ def run_b200(args):
 
 def main():
     args = parse()
+    # stdout carries exactly ONE JSON line: everything libraries print (e.g. NCCL's version banner, written
+    # to fd 1 from C) is routed to stderr while the benchmark runs.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    out = os.fdopen(real_stdout, "w")
+    global print_json
+    print_json = lambda line: (out.write(json.dumps(line) + "\n"), out.flush())
     if args.impl == "reference":
         run_reference(args)
     else:
