@@ -77,6 +77,33 @@ class qcdmethelper:
         eigenvecs = eigenvecs[:, idx]
         return 2 * np.dot(eigenvecs[:, :myNumPairs], eigenvecs[:, :myNumPairs].T)
 
+    # ---------------------------------------------------------------- src/qcdmethelper.py:124-168
+    def constructbath(self, OneDM, impurityOrbs, numBathOrbs, threshold=1e-13):
+        """Schmidt bath from the environment block of the mean-field 1-RDM.  Returns
+        (numBathOrbs, loc2dmet [N x N: impurity | bath | environment], coreOccupations)."""
+        impurityOrbs = np.abs(np.asarray(impurityOrbs).reshape(-1)).astype(int)
+        imp = np.flatnonzero(impurityOrbs)
+        env = np.flatnonzero(1 - impurityOrbs)
+        numImpOrbs, numTotalOrbs = len(imp), len(impurityOrbs)
+        embedding1RDM = OneDM[np.ix_(env, env)]
+        eigenvals, eigenvecs = np.linalg.eigh(embedding1RDM)
+        closeness = np.maximum(-eigenvals, eigenvals - 2.0)
+        idx = closeness.argsort()                       # occupation numbers closest to 1 come first
+        tokeep = int(np.sum(-closeness[idx] > threshold))
+        numBathOrbs = min(tokeep, int(numBathOrbs))
+        eigenvals, eigenvecs = eigenvals[idx], eigenvecs[:, idx]
+        pureEnvironEigVals = -eigenvals[numBathOrbs:]
+        pureEnvironEigVecs = eigenvecs[:, numBathOrbs:]
+        idx = pureEnvironEigVals.argsort()
+        eigenvecs[:, numBathOrbs:] = pureEnvironEigVecs[:, idx]
+        pureEnvironEigVals = -pureEnvironEigVals[idx]
+        coreOccupations = np.hstack((np.zeros([numImpOrbs + numBathOrbs]), pureEnvironEigVals))
+        loc2dmet = np.zeros((numTotalOrbs, numTotalOrbs))
+        loc2dmet[imp, np.arange(numImpOrbs)] = 1.0
+        loc2dmet[np.ix_(env, numImpOrbs + np.arange(len(env)))] = eigenvecs
+        assert np.linalg.norm(np.dot(loc2dmet.T, loc2dmet) - np.identity(numTotalOrbs)) < 1e-12
+        return (numBathOrbs, loc2dmet, coreOccupations)
+
     def _oei(self, doSCF, umat_loc, NOrotation):
         if doSCF:
             raise NotImplementedError("doSCF=True is outside the response hot path (src/dmet.py:44)")

@@ -1,0 +1,68 @@
+"""DMET self-consistency loop: CPU sanity checks of the restated host orchestration, and (GPU) parity of
+the converged energy / umat between the oracle-driven and the GPU-driven loop: 1e-8 Hartree on energies
+(BASELINE.json north_star)."""
+import numpy as np
+import pytest
+
+from qcdmet_b200 import dmet as dmet_mod, fci_solver, localintegrals_hubbard as lh
+from dmet_harness import CASES, OracleDmet, build, chain_clusters
+
+
+def test_fci_standin_known_answers():
+    u = 4.0
+    h = np.array([[0.0, -1.0], [-1.0, 0.0]])
+    tei = np.zeros((2, 2, 2, 2))
+    tei[0, 0, 0, 0] = tei[1, 1, 1, 1] = u
+    e, d = fci_solver.solve(0.0, h, h, tei, 2, 2, 2)
+    assert abs(e - (u / 2 - np.sqrt((u / 2) ** 2 + 4.0))) < 1e-12      # Hubbard dimer ground state
+    assert abs(np.trace(d) - 2.0) < 1e-12
+    # non-interacting 4-orbital system: energy = 2 * sum of the two lowest levels
+    h4 = lh.hubbard_chain(4)
+    e4, d4 = fci_solver.solve(0.0, h4, h4, np.zeros((4, 4, 4, 4)), 4, 4, 4)
+    assert abs(e4 - 2 * np.sort(np.linalg.eigvalsh(h4))[:2].sum()) < 1e-12
+
+
+def test_bath_construction_properties():
+    ints = lh.localintegrals_hubbard(lh.hubbard_chain(12), 4.0, 12)
+    d = OracleDmet(ints, chain_clusters(12, 2), False)
+    one = d.helper.construct1RDM_loc(False, d.umat)
+    nb, loc2dmet, core = d.helper.constructbath(one, d.impClust[1], 2)
+    assert nb == 2
+    assert np.allclose(loc2dmet.T @ loc2dmet, np.eye(12), atol=1e-12)
+    assert np.allclose(loc2dmet[[2, 3], :2], np.eye(2))                 # impurity orbitals first
+    rot = loc2dmet.T @ one @ loc2dmet
+    assert np.abs(rot[4:, :4]).max() < 1e-10                             # environment decouples (Schmidt)
+    assert np.all((np.abs(core[4:]) < 1e-10) | (np.abs(core[4:] - 2) < 1e-10))
+    assert abs(np.trace(rot[:4, :4]) - 4.0) < 1e-10                      # half-filled embedded problem
+
+
+def test_noninteracting_limit_is_exact():
+    """U = 0: the impurity 1-RDM equals the mean-field one, so umat stays zero and E = E_RHF."""
+    ints = lh.localintegrals_hubbard(lh.hubbard_chain(12), 0.0, 12)
+    d = OracleDmet(ints, chain_clusters(12, 2), False, fitImpBath=False)
+    e = d.doselfconsistent()
+    assert abs(e - ints.fullEhf) < 1e-9
+    assert np.abs(d.umat).max() < 1e-7
+    assert d.iterations == 1
+
+
+def test_oracle_loop_converges_and_lowers_energy():
+    d = build("chain12_U4_imp_only", OracleDmet)
+    e = d.doselfconsistent()
+    assert d.iterations < 50
+    assert e < d.ints.fullEhf - 1.0                                       # correlation energy recovered
+    assert abs(np.trace(d.umat)) < 1e-9                                   # chemical-potential gauge removed
+    assert abs(d.numeleccostfunction(d.mu_imp)) < 1e-6
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", list(CASES))
+def test_converged_energy_matches_oracle_loop(case):
+    ref = build(case, OracleDmet)
+    e_ref = ref.doselfconsistent()
+    gpu = build(case, dmet_mod.dmet)
+    e_gpu = gpu.doselfconsistent()
+    assert gpu.iterations == ref.iterations
+    assert abs(e_gpu - e_ref) <= 1e-8                                     # 1e-8 Hartree
+    assert np.abs(gpu.umat - ref.umat).max() <= 1e-7
+    assert gpu.time_grad > 0.0
