@@ -37,46 +37,51 @@ namespace qcdmet {
 
 namespace {
 
-constexpr int BN = 128;       // occupied orbitals per output tile
 constexpr int KC = 16;        // virtual orbitals per pipeline stage
 constexpr int STAGES = 4;
 constexpr int RT = 4;         // site slots per component  (= M-warps)
 constexpr int AT = 32;        // row slots per a-tile
-constexpr int RF = 4;         // max rows per fragment
+constexpr int MAXRF = 8;      // max rows per fragment over all variants
 constexpr int MAXP = 16;      // max perturbations per component
 constexpr int MAXE = 4;       // max elements per perturbation
 constexpr int NCONS = 256;    // consumer threads (8 warps)
 constexpr int NTHREADS = NCONS + 32;
-constexpr int PSTRIDE = BN + 8;   // POS row stride in doubles (bank-conflict padding)
-
-constexpr int W_STAGE = KC * BN;          // doubles
+constexpr int TP = 128;       // max perturbations over the blocks of one tile
 constexpr int PV_STAGE = KC * AT;
 constexpr int CV_STAGE = KC * RT;
-constexpr int STAGE_DOUBLES = W_STAGE + PV_STAGE + CV_STAGE;
-constexpr uint32_t STAGE_BYTES = STAGE_DOUBLES * 8;
 
-constexpr int SM_STAGE_OFF = 0;
-constexpr int SM_POS_OFF = SM_STAGE_OFF + STAGES * STAGE_DOUBLES * 8;
-constexpr int SM_COS_OFF = SM_POS_OFF + (AT + 1) * PSTRIDE * 8;
-constexpr int NSTRIDE = 18;       // running-sum row stride in doubles (16 used; conflict-free 16 B slots)
-constexpr int TP = 128;           // max perturbations over the blocks of one tile
-constexpr int POS_DOUBLES = (AT + 1) * PSTRIDE;
-constexpr int COS_DOUBLES = RT * BN;
-constexpr uint32_t EPI_BYTES = (POS_DOUBLES + COS_DOUBLES) * 8;
-constexpr int SM_NS_OFF = SM_COS_OFF + RT * BN * 8;
-constexpr int SM_BAR_OFF = SM_NS_OFF + 2 * 128 * NSTRIDE * 8;
-constexpr int SM_TAB_OFF = SM_BAR_OFF + (2 * STAGES + 2) * 8;
-// tables: qrow[32] (8B) | tileRow[32] (4B) | compSites[4] (4B) | compP[16] (4B) | partner[32][4] (1B)
-//         | self[32] (1B) | compEnt[16][4] (1B)
-constexpr int TAB_QROW = 0;
-constexpr int TAB_TROW = TAB_QROW + AT * 8;
-constexpr int TAB_CSITE = TAB_TROW + AT * 4;
-constexpr int TAB_CP = TAB_CSITE + RT * 4;
-constexpr int TAB_PARTNER = TAB_CP + MAXP * 4;
-constexpr int TAB_SELF = TAB_PARTNER + AT * RF;
-constexpr int TAB_CENT = TAB_SELF + AT;
-constexpr int TAB_BYTES = TAB_CENT + MAXP * MAXE;
-constexpr int SMEM_BYTES = SM_TAB_OFF + ((TAB_BYTES + 15) / 16) * 16;
+// Kernel variant: RF = max rows per fragment (4: impurity-only 2x2 fits; 8: impurity+bath rows of a
+// 4-orbital impurity), NJ = 8-column DMMA fragments per warp (column tile BN = 16 NJ: 128 / 96 / 64,
+// picked to minimise the padding of the occupied dimension).
+template <int RF_, int NJ_>
+struct Cfg {
+    static constexpr int RF = RF_, NJ = NJ_;
+    static constexpr int BN = 16 * NJ;                  // occupied orbitals per output tile
+    static constexpr int PSTRIDE = BN + 8;              // POS row stride in doubles (bank-conflict padding)
+    static constexpr int W_STAGE = KC * BN;             // doubles
+    static constexpr int STAGE_DOUBLES = W_STAGE + PV_STAGE + CV_STAGE;
+    static constexpr uint32_t STAGE_BYTES = STAGE_DOUBLES * 8;
+    static constexpr int POS_DOUBLES = (AT + 1) * PSTRIDE;
+    static constexpr int COS_DOUBLES = RT * BN;
+    static constexpr uint32_t EPI_BYTES = (POS_DOUBLES + COS_DOUBLES) * 8;
+    static constexpr int NSTRIDE = RT * RF + 2;         // running-sum row stride (conflict-free 16 B slots)
+    static constexpr int SM_STAGE_OFF = 0;
+    static constexpr int SM_POS_OFF = SM_STAGE_OFF + STAGES * STAGE_DOUBLES * 8;
+    static constexpr int SM_COS_OFF = SM_POS_OFF + POS_DOUBLES * 8;
+    static constexpr int SM_NS_OFF = SM_COS_OFF + COS_DOUBLES * 8;
+    static constexpr int SM_BAR_OFF = SM_NS_OFF + 2 * 128 * NSTRIDE * 8;
+    static constexpr int SM_TAB_OFF = SM_BAR_OFF + (2 * STAGES + 2) * 8;
+    // tables: qrow[32] (8B) | tileRow[32] (4B) | compP[16] (4B) | partner[32][RF] (1B) | self[32] (1B)
+    //         | compEnt[16][4] (1B)
+    static constexpr int TAB_QROW = 0;
+    static constexpr int TAB_TROW = TAB_QROW + AT * 8;
+    static constexpr int TAB_CP = TAB_TROW + AT * 4;
+    static constexpr int TAB_PARTNER = TAB_CP + MAXP * 4;
+    static constexpr int TAB_SELF = TAB_PARTNER + AT * RF;
+    static constexpr int TAB_CENT = TAB_SELF + AT;
+    static constexpr int TAB_BYTES = TAB_CENT + MAXP * MAXE;
+    static constexpr int SMEM_BYTES = SM_TAB_OFF + ((TAB_BYTES + 15) / 16) * 16;
+};
 
 struct DmmaArgs {
     int nKc, nOt;
@@ -94,7 +99,7 @@ struct DmmaArgs {
     const int *compP;                   // [nComp][MAXP] perturbation index or -1
     const unsigned char *compEnt;       // [nComp][MAXP][MAXE]  rs | cs << 4, 0xFF = none
     const int *tileRow;                 // [nTiles][AT]  fragment-row index or -1
-    const unsigned char *tilePartner;   // [nTiles][AT][RF] slot of the j-th row of the fragment, AT = none
+    const unsigned char *tilePartner;   // [nTiles][AT][RF] slot of the j-th row of the fragment, AT = none (RF of the variant)
     const unsigned char *tileSelf;      // [nTiles][AT]  a_loc | r_f << 4
     const long long *tileQ;             // [nTiles][AT]  qoff[f] + a_loc
     int nDest;                          // destinations of every Jacobian store (1, or the ranks of a node)
@@ -152,15 +157,17 @@ __device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double
 // operand tiling (once per set of orbitals)
 // ------------------------------------------------------------------------------------------
 // Wt[(ot*nKc + kc)][k4][njp][lane][2] = W[kc*KC + k4*4 + (lane&3)][ot*BN + (2 njp + e)*8 + (lane>>2)]
-__global__ void build_wt_kernel(const double *__restrict__ e, int no, int nv, int nKc, long long total,
+__global__ void build_wt_kernel(const double *__restrict__ e, int no, int nv, int nKc, int BN, long long total,
                                 double *__restrict__ Wt)
 {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
-    const int within = (int)(idx % W_STAGE);
-    const long long blk = idx / W_STAGE;
+    const int wstage = KC * BN, perK4 = 4 * BN;      // doubles per stage / per k4 step (BN/16 pairs x 32 lanes x 2)
+    const int within = (int)(idx % wstage);
+    const long long blk = idx / wstage;
     const int ot = (int)(blk / nKc), kc = (int)(blk % nKc);
-    const int e2 = within & 1, lane = (within >> 1) & 31, njp = (within >> 6) & 7, k4 = within >> 9;
+    const int k4 = within / perK4, r4 = within % perK4;
+    const int e2 = r4 & 1, lane = (r4 >> 1) & 31, njp = r4 >> 6;
     const int k = kc * KC + k4 * 4 + (lane & 3);
     const int o = ot * BN + (njp * 2 + e2) * 8 + (lane >> 2);
     Wt[idx] = (k < nv && o < no) ? 1.0 / (e[o] - e[no + k]) : 0.0;
@@ -196,11 +203,12 @@ __global__ void build_cvt_kernel(const double *__restrict__ CvT, int ldv, int nv
 }
 
 // POt[(tile*nOt + ot)][slot 0..AT][PSTRIDE] = PO[tileRow[tile][slot]][ot*BN + o]  (slot AT: zero row)
-__global__ void build_pot_kernel(const double *__restrict__ PO, int ldo, int no, int nOt,
+__global__ void build_pot_kernel(const double *__restrict__ PO, int ldo, int no, int nOt, int BN,
                                  const int *__restrict__ tileRow, long long total, double *__restrict__ POt)
 {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
+    const int PSTRIDE = BN + 8, POS_DOUBLES = (AT + 1) * PSTRIDE;
     const int within = (int)(idx % POS_DOUBLES);
     const long long blk = idx / POS_DOUBLES;
     const int tile = (int)(blk / nOt), ot = (int)(blk % nOt);
@@ -214,11 +222,12 @@ __global__ void build_pot_kernel(const double *__restrict__ PO, int ldo, int no,
     POt[idx] = val;
 }
 // COt[(comp*nOt + ot)][r][BN] = CoT[compSites[comp][r]][ot*BN + o]
-__global__ void build_cot_kernel(const double *__restrict__ CoT, int ldo, int no, int nOt,
+__global__ void build_cot_kernel(const double *__restrict__ CoT, int ldo, int no, int nOt, int BN,
                                  const int *__restrict__ compSites, long long total, double *__restrict__ COt)
 {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
+    const int COS_DOUBLES = RT * BN;
     const int within = (int)(idx % COS_DOUBLES);
     const long long blk = idx / COS_DOUBLES;
     const int comp = (int)(blk / nOt), ot = (int)(blk % nOt);
@@ -239,21 +248,25 @@ __global__ void zero_columns_kernel(ZeroArgs z, const int *__restrict__ cols, in
 // ------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------
+template <class C>
 __global__ void __launch_bounds__(NTHREADS, 1) jac_dmma_kernel(const DmmaArgs g)
 {
+    constexpr int RF = C::RF, NJ = C::NJ, BN = C::BN, PSTRIDE = C::PSTRIDE, NSTRIDE = C::NSTRIDE;
+    constexpr int W_STAGE = C::W_STAGE, STAGE_DOUBLES = C::STAGE_DOUBLES;
+    constexpr int POS_DOUBLES = C::POS_DOUBLES, COS_DOUBLES = C::COS_DOUBLES;
     extern __shared__ __align__(128) unsigned char smem[];
-    double *stageBase = reinterpret_cast<double *>(smem + SM_STAGE_OFF);
-    double *POS = reinterpret_cast<double *>(smem + SM_POS_OFF);
-    double *CoS = reinterpret_cast<double *>(smem + SM_COS_OFF);
-    double *Ns = reinterpret_cast<double *>(smem + SM_NS_OFF);
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + SM_BAR_OFF);
-    unsigned char *tab = smem + SM_TAB_OFF;
-    long long *qrow = reinterpret_cast<long long *>(tab + TAB_QROW);
-    int *trow = reinterpret_cast<int *>(tab + TAB_TROW);
-    int *cp = reinterpret_cast<int *>(tab + TAB_CP);
-    unsigned char *partner = tab + TAB_PARTNER;
-    unsigned char *selfi = tab + TAB_SELF;
-    unsigned char *cent = tab + TAB_CENT;
+    double *stageBase = reinterpret_cast<double *>(smem + C::SM_STAGE_OFF);
+    double *POS = reinterpret_cast<double *>(smem + C::SM_POS_OFF);
+    double *CoS = reinterpret_cast<double *>(smem + C::SM_COS_OFF);
+    double *Ns = reinterpret_cast<double *>(smem + C::SM_NS_OFF);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + C::SM_BAR_OFF);
+    unsigned char *tab = smem + C::SM_TAB_OFF;
+    long long *qrow = reinterpret_cast<long long *>(tab + C::TAB_QROW);
+    int *trow = reinterpret_cast<int *>(tab + C::TAB_TROW);
+    int *cp = reinterpret_cast<int *>(tab + C::TAB_CP);
+    unsigned char *partner = tab + C::TAB_PARTNER;
+    unsigned char *selfi = tab + C::TAB_SELF;
+    unsigned char *cent = tab + C::TAB_CENT;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int2 wk = g.work[blockIdx.x];
@@ -296,14 +309,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) jac_dmma_kernel(const DmmaArgs g)
                 for (int kc = 0; kc < nKc; ++kc, ++it) {
                     if (kc == epiAt) {
                         mbar_wait(epiEmpty, (ot & 1) ^ 1);          // every warp is done with tile ot-1's operands
-                        mbar_expect_tx(epiFull, EPI_BYTES);
+                        mbar_expect_tx(epiFull, C::EPI_BYTES);
                         tma_bulk_g2s(smem_u32(POS), posrc + (size_t)ot * POS_DOUBLES, POS_DOUBLES * 8, epiFull);
                         tma_bulk_g2s(smem_u32(CoS), cosrc + (size_t)ot * COS_DOUBLES, COS_DOUBLES * 8, epiFull);
                     }
                     const int s = it % STAGES;
                     const uint32_t full = smem_u32(&bars[s]), empty = smem_u32(&bars[STAGES + s]);
                     mbar_wait(empty, ((it / STAGES) & 1) ^ 1);
-                    mbar_expect_tx(full, STAGE_BYTES);
+                    mbar_expect_tx(full, C::STAGE_BYTES);
                     double *dst = stageBase + (size_t)s * STAGE_DOUBLES;
                     tma_bulk_g2s(smem_u32(dst), wsrc + (size_t)kc * W_STAGE, W_STAGE * 8, full);
                     tma_bulk_g2s(smem_u32(dst + W_STAGE), pvsrc + (size_t)kc * PV_STAGE, PV_STAGE * 8, full);
@@ -316,16 +329,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) jac_dmma_kernel(const DmmaArgs g)
 
     // ================= consumer warps =================
     const int warp_m = warp >> 1;     // site slot r
-    const int warp_n = warp & 1;      // 64-column half
+    const int warp_n = warp & 1;      // column half: NJ fragments of 8 columns
     const int g4 = lane >> 2, t4 = lane & 3;
 
-    double acc[4][8][2];
+    double acc[4][NJ][2];
     int it = 0;
     for (int ot = 0; ot < nOt; ++ot) {
 #pragma unroll
         for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
-            for (int nj = 0; nj < 8; ++nj) { acc[mi][nj][0] = 0.0; acc[mi][nj][1] = 0.0; }
+            for (int nj = 0; nj < NJ; ++nj) { acc[mi][nj][0] = 0.0; acc[mi][nj][1] = 0.0; }
 
         for (int kc = 0; kc < nKc; ++kc, ++it) {
             const int s = it % STAGES;
@@ -338,66 +351,71 @@ __global__ void __launch_bounds__(NTHREADS, 1) jac_dmma_kernel(const DmmaArgs g)
                 const double2 p01 = *reinterpret_cast<const double2 *>(PVs + ((k4 * 2 + 0) * 32 + lane) * 2);
                 const double2 p23 = *reinterpret_cast<const double2 *>(PVs + ((k4 * 2 + 1) * 32 + lane) * 2);
                 const double cv = CVs[k4 * 4 + t4];
-                double a[4], b[8];
+                double a[4], b[NJ];
                 a[0] = p01.x * cv; a[1] = p01.y * cv; a[2] = p23.x * cv; a[3] = p23.y * cv;
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
+                for (int j = 0; j < NJ / 2; ++j) {
                     const double2 bb = *reinterpret_cast<const double2 *>(
-                        Ws + ((k4 * 8 + warp_n * 4 + j) * 32 + lane) * 2);
+                        Ws + ((k4 * NJ + warp_n * (NJ / 2) + j) * 32 + lane) * 2);
                     b[2 * j] = bb.x; b[2 * j + 1] = bb.y;
                 }
 #pragma unroll
                 for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
-                    for (int nj = 0; nj < 8; ++nj) dmma884(acc[mi][nj][0], acc[mi][nj][1], a[mi], b[nj]);
+                    for (int nj = 0; nj < NJ; ++nj) dmma884(acc[mi][nj][0], acc[mi][nj][1], a[mi], b[nj]);
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&bars[STAGES + s]));
         }
 
-        // ---- epilogue for this 128-column tile (per warp, no CTA-wide barrier)
+        // ---- epilogue for this column tile (per warp, no CTA-wide barrier)
         mbar_wait(epiFull, ot & 1);
 #pragma unroll
         for (int mi = 0; mi < 4; ++mi) {
             const int a_slot = mi * 8 + g4;
-            const double *pb[RF];
+            const double *pc = CoS + warp_n * (BN / 2) + t4 * 2;
+            double *nsrow = Ns + (warp_n * 128 + warp_m * AT + a_slot) * NSTRIDE + t4 * RF;
 #pragma unroll
-            for (int j = 0; j < RF; ++j) pb[j] = POS + (int)partner[a_slot * RF + j] * PSTRIDE + warp_n * 64 + t4 * 2;
-            const double *pc = CoS + warp_n * 64 + t4 * 2;
-            double nacc[RT][RF];
+            for (int jh = 0; jh < RF / 4; ++jh) {            // partners in groups of 4 (register budget)
+                const double *pb[4];
 #pragma unroll
-            for (int c = 0; c < RT; ++c)
+                for (int j = 0; j < 4; ++j)
+                    pb[j] = POS + (int)partner[a_slot * RF + jh * 4 + j] * PSTRIDE + warp_n * (BN / 2) + t4 * 2;
+                double nacc[RT][4];
 #pragma unroll
-                for (int j = 0; j < RF; ++j) nacc[c][j] = 0.0;
+                for (int c = 0; c < RT; ++c)
 #pragma unroll
-            for (int nj = 0; nj < 8; ++nj) {
-                double2 po[RF];
+                    for (int j = 0; j < 4; ++j) nacc[c][j] = 0.0;
 #pragma unroll
-                for (int j = 0; j < RF; ++j) po[j] = *reinterpret_cast<const double2 *>(pb[j] + nj * 8);
-                const double m0 = acc[mi][nj][0], m1 = acc[mi][nj][1];
+                for (int nj = 0; nj < NJ; ++nj) {
+                    double2 po[4];
 #pragma unroll
-                for (int c = 0; c < RT; ++c) {
-                    const double2 co = *reinterpret_cast<const double2 *>(pc + c * BN + nj * 8);
-                    const double t0 = m0 * co.x, t1 = m1 * co.y;
+                    for (int j = 0; j < 4; ++j) po[j] = *reinterpret_cast<const double2 *>(pb[j] + nj * 8);
+                    const double m0 = acc[mi][nj][0], m1 = acc[mi][nj][1];
 #pragma unroll
-                    for (int j = 0; j < RF; ++j) nacc[c][j] = fma(t0, po[j].x, fma(t1, po[j].y, nacc[c][j]));
+                    for (int c = 0; c < RT; ++c) {
+                        const double2 co = *reinterpret_cast<const double2 *>(pc + c * BN + nj * 8);
+                        const double t0 = m0 * co.x, t1 = m1 * co.y;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) nacc[c][j] = fma(t0, po[j].x, fma(t1, po[j].y, nacc[c][j]));
+                    }
                 }
+                // reduce over the 4 lanes that share this row; lane t4 keeps the sums of site slot c == t4
+                double keep[4];
+#pragma unroll
+                for (int c = 0; c < RT; ++c)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        double v = nacc[c][j];
+                        v += __shfl_xor_sync(0xffffffffu, v, 1);
+                        v += __shfl_xor_sync(0xffffffffu, v, 2);
+                        if (t4 == c) keep[j] = v;
+                    }
+                double2 *dst = reinterpret_cast<double2 *>(nsrow + jh * 4);
+                double2 s01 = dst[0], s23 = dst[1];
+                s01.x += keep[0]; s01.y += keep[1]; s23.x += keep[2]; s23.y += keep[3];
+                dst[0] = s01; dst[1] = s23;
             }
-            // reduce over the 4 lanes that share this row; lane t4 keeps the sums of site slot c == t4
-            double keep[RF];
-#pragma unroll
-            for (int c = 0; c < RT; ++c)
-#pragma unroll
-                for (int j = 0; j < RF; ++j) {
-                    double v = nacc[c][j];
-                    v += __shfl_xor_sync(0xffffffffu, v, 1);
-                    v += __shfl_xor_sync(0xffffffffu, v, 2);
-                    if (t4 == c) keep[j] = v;
-                }
-            double2 *dst = reinterpret_cast<double2 *>(Ns + (warp_n * 128 + warp_m * AT + a_slot) * NSTRIDE + t4 * RF);
-            double2 s01 = dst[0], s23 = dst[1];
-            s01.x += keep[0]; s01.y += keep[1]; s23.x += keep[2]; s23.y += keep[3];
-            dst[0] = s01; dst[1] = s23;
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(epiEmpty);
@@ -473,6 +491,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) jac_dmma_kernel(const DmmaArgs g)
 struct DmmaPlanData {
     int N = 0, no = 0, nv = 0, P = 0, S = 0;
     int nComp = 0, nTiles = 0, nKc = 0, nOt = 0;
+    int rf = 4, nj = 8;                 // kernel variant: rows per fragment (4|8), 8-column fragments per warp (8|6|4)
+    int bn() const { return 16 * nj; }
+    size_t wStage() const { return (size_t)KC * bn(); }
+    size_t posDoubles() const { return (size_t)(AT + 1) * (bn() + 8); }
+    size_t cosDoubles() const { return (size_t)RT * bn(); }
     std::vector<int> emptyP;            // perturbations without elements: zero columns
     int *d_emptyCols = nullptr;
     std::vector<int> emptyInRange;
@@ -512,12 +535,26 @@ Schedule build_schedule(int N, int no, int P, int F, const int *h1start, const i
     DmmaPlanData &d = sc.d;
     d.N = N; d.no = no; d.nv = N - no; d.P = P; d.S = F > 0 ? rowStart[F] : 0;
     if (P == 0 || d.S == 0) { sc.why = "empty problem"; return sc; }
-    // fragments: <= RF rows each, packed whole into tiles of AT row slots
+    // fragments: <= 8 rows each, packed whole into tiles of AT row slots
     std::vector<long long> qoff(F + 1, 0);
+    int maxRf = 0;
     for (int f = 0; f < F; ++f) {
         const int rf = rowStart[f + 1] - rowStart[f];
-        if (rf > RF) { sc.why = "a fragment has more than 4 rows"; return sc; }
+        if (rf > MAXRF) { sc.why = "a fragment has more than 8 rows"; return sc; }
+        maxRf = std::max(maxRf, rf);
         qoff[f + 1] = qoff[f] + (long long)rf * rf;
+    }
+    const int RF = maxRf <= 4 ? 4 : 8;
+    d.rf = RF;
+    // column tile: the width (128 / 96 / 64) that pads the occupied dimension least
+    {
+        int best = 8;
+        long long bestPad = -1;
+        for (int nj : {8, 6, 4}) {
+            const long long bn = 16 * nj, pad = (no + bn - 1) / bn * bn;
+            if (bestPad < 0 || pad < bestPad) { bestPad = pad; best = nj; }
+        }
+        d.nj = best;
     }
     std::vector<int> fragTile(F, -1), fragSlot(F, -1);
     int slot = AT;   // forces a new tile at the first fragment
@@ -605,7 +642,7 @@ Schedule build_schedule(int N, int no, int P, int F, const int *h1start, const i
         }
     }
     d.nKc = (d.nv + KC - 1) / KC;
-    d.nOt = (d.no + BN - 1) / BN;
+    d.nOt = (d.no + d.bn() - 1) / d.bn();
 
     // symmetric mode: impurity-only rows, and the row sites of every non-empty fragment are exactly the
     // sites of one component (and vice versa).  Then PV/PO rows are C_v/C_o site rows and
@@ -615,7 +652,7 @@ Schedule build_schedule(int N, int no, int P, int F, const int *h1start, const i
     d.compLoc.assign((size_t)d.nComp * RT, 0xFF);
     d.tileP.assign((size_t)d.nTiles * TP, -1);
     d.tileEnt.assign((size_t)d.nTiles * TP * MAXE, 0xFF);
-    bool sym = (rowIdx != nullptr);
+    bool sym = (rowIdx != nullptr) && RF == 4;
     if (sym) {
         std::vector<int> siteComp(N, -1), compFrag(d.nComp, -1);
         for (int c = 0; c < d.nComp; ++c)
@@ -706,9 +743,9 @@ int dmma_plan_build(DmmaPlanData **out, int N, int no, int P, int F, const int *
         dmma_plan_free(d);
         return rc;
     }
-    const size_t wt = (size_t)d->nOt * d->nKc * W_STAGE, pvt = (size_t)d->nTiles * d->nKc * PV_STAGE,
-                 cvt = (size_t)d->nComp * d->nKc * CV_STAGE, pot = (size_t)d->nTiles * d->nOt * POS_DOUBLES,
-                 cot = (size_t)d->nComp * d->nOt * COS_DOUBLES;
+    const size_t wt = (size_t)d->nOt * d->nKc * d->wStage(), pvt = (size_t)d->nTiles * d->nKc * PV_STAGE,
+                 cvt = (size_t)d->nComp * d->nKc * CV_STAGE, pot = (size_t)d->nTiles * d->nOt * d->posDoubles(),
+                 cot = (size_t)d->nComp * d->nOt * d->cosDoubles();
     if (cudaMalloc((void **)&d->d_Wt, wt * 8) != cudaSuccess || cudaMalloc((void **)&d->d_PVt, pvt * 8) != cudaSuccess ||
         cudaMalloc((void **)&d->d_CVt, cvt * 8) != cudaSuccess || cudaMalloc((void **)&d->d_POt, pot * 8) != cudaSuccess ||
         cudaMalloc((void **)&d->d_COt, cot * 8) != cudaSuccess) {
@@ -735,18 +772,18 @@ void dmma_plan_free(DmmaPlanData *d)
 
 int dmma_prepare_orbitals(DmmaPlanData *d, const JacView &v, cudaStream_t st)
 {
-    const long long wt = (long long)d->nOt * d->nKc * W_STAGE, pvt = (long long)d->nTiles * d->nKc * PV_STAGE,
-                    cvt = (long long)d->nComp * d->nKc * CV_STAGE, pot = (long long)d->nTiles * d->nOt * POS_DOUBLES,
-                    cot = (long long)d->nComp * d->nOt * COS_DOUBLES;
-    build_wt_kernel<<<(unsigned)((wt + 255) / 256), 256, 0, st>>>(v.e, v.no, v.nv, d->nKc, wt, d->d_Wt);
+    const long long wt = (long long)d->nOt * d->nKc * d->wStage(), pvt = (long long)d->nTiles * d->nKc * PV_STAGE,
+                    cvt = (long long)d->nComp * d->nKc * CV_STAGE, pot = (long long)d->nTiles * d->nOt * d->posDoubles(),
+                    cot = (long long)d->nComp * d->nOt * d->cosDoubles();
+    build_wt_kernel<<<(unsigned)((wt + 255) / 256), 256, 0, st>>>(v.e, v.no, v.nv, d->nKc, d->bn(), wt, d->d_Wt);
     QC_CUDA(cudaGetLastError());
     build_pvt_kernel<<<(unsigned)((pvt + 255) / 256), 256, 0, st>>>(v.PV, v.ldv, v.nv, d->nKc, d->d_tileRow, pvt, d->d_PVt);
     QC_CUDA(cudaGetLastError());
     build_cvt_kernel<<<(unsigned)((cvt + 255) / 256), 256, 0, st>>>(v.CvT, v.ldv, v.nv, d->nKc, d->d_compSites, cvt, d->d_CVt);
     QC_CUDA(cudaGetLastError());
-    build_pot_kernel<<<(unsigned)((pot + 255) / 256), 256, 0, st>>>(v.PO, v.ldo, v.no, d->nOt, d->d_tileRow, pot, d->d_POt);
+    build_pot_kernel<<<(unsigned)((pot + 255) / 256), 256, 0, st>>>(v.PO, v.ldo, v.no, d->nOt, d->bn(), d->d_tileRow, pot, d->d_POt);
     QC_CUDA(cudaGetLastError());
-    build_cot_kernel<<<(unsigned)((cot + 255) / 256), 256, 0, st>>>(v.CoT, v.ldo, v.no, d->nOt, d->d_compSites, cot, d->d_COt);
+    build_cot_kernel<<<(unsigned)((cot + 255) / 256), 256, 0, st>>>(v.CoT, v.ldo, v.no, d->nOt, d->bn(), d->d_compSites, cot, d->d_COt);
     QC_CUDA(cudaGetLastError());
     return QCDMET_OK;
 }
@@ -758,10 +795,6 @@ int launch_jacobian_dmma(DmmaPlanData *d, const JacView &v, cudaStream_t st, int
     *flops = 0.0;
     const int ncols = v.colEnd - v.colBegin;
     if (ncols <= 0) return QCDMET_OK;
-    if (!d->attrSet) {
-        QC_CUDA(cudaFuncSetAttribute(jac_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        d->attrSet = true;
-    }
     const bool wantSym = allowSym && d->symOk && v.colBegin == 0 && v.colEnd == d->P;
     const int shareRank = peers ? peers->rank : 0, shareN = peers ? peers->nranks : 1;
     if (d->launchBegin != v.colBegin || d->launchEnd != v.colEnd || d->launchSym != wantSym ||
@@ -789,7 +822,7 @@ int launch_jacobian_dmma(DmmaPlanData *d, const JacView &v, cudaStream_t st, int
             // useful FP64 flops of this CTA (padding excluded): main loop 2 nv no per (site, row),
             // one multiply per A element per column tile, epilogue (1 + 2 r_f) n_c per accumulator element
             const double ns = d->compNumSites[wk.x], nr = d->tileNumRows[wk.y];
-            fl += ns * nr * (2.0 * d->nv * d->no + (double)d->nv * d->nOt + ns * d->no * (1.0 + 2.0 * RF));
+            fl += ns * nr * (2.0 * d->nv * d->no + (double)d->nv * d->nOt + ns * d->no * (1.0 + 2.0 * d->rf));
         }
         d->emptyInRange.clear();
         if (shareRank == 0)
@@ -846,7 +879,23 @@ int launch_jacobian_dmma(DmmaPlanData *d, const JacView &v, cudaStream_t st, int
     a.nDest = z.nDest;
     for (int r = 0; r < QCDMET_MAX_PEERS; ++r) a.J[r] = z.J[r];
     if (ev0) QC_CUDA(cudaEventRecord(ev0, st));
-    jac_dmma_kernel<<<(unsigned)d->work.size(), NTHREADS, SMEM_BYTES, st>>>(a);
+    const unsigned grid = (unsigned)d->work.size();
+    int rc = QCDMET_E_STATE;
+#define QC_LAUNCH_VARIANT(RFV, NJV)                                                                           \
+    if (d->rf == RFV && d->nj == NJV) {                                                                       \
+        using K = Cfg<RFV, NJV>;                                                                              \
+        if (!d->attrSet) {                                                                                    \
+            QC_CUDA(cudaFuncSetAttribute(jac_dmma_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
+                                         K::SMEM_BYTES));                                                     \
+            d->attrSet = true;                                                                                \
+        }                                                                                                     \
+        jac_dmma_kernel<K><<<grid, NTHREADS, K::SMEM_BYTES, st>>>(a);                                         \
+        rc = QCDMET_OK;                                                                                       \
+    }
+    QC_LAUNCH_VARIANT(4, 8) QC_LAUNCH_VARIANT(4, 6) QC_LAUNCH_VARIANT(4, 4)
+    QC_LAUNCH_VARIANT(8, 8) QC_LAUNCH_VARIANT(8, 6) QC_LAUNCH_VARIANT(8, 4)
+#undef QC_LAUNCH_VARIANT
+    QC_CHECK(rc == QCDMET_OK, QCDMET_E_STATE, "no DMMA kernel variant for rf=%d nj=%d", d->rf, d->nj);
     QC_CUDA(cudaGetLastError());
     if (ev1) QC_CUDA(cudaEventRecord(ev1, st));
     *launches += 1;

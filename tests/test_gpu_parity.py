@@ -123,7 +123,12 @@ DMMA_SHAPES = {
     "bath_rows_m2": (lambda: wl.make_workload("b2", 44, 20, [2, 2, 1, 2], fit_imp_bath=True), DMMA, False),
     "frag5_general": (lambda: wl.make_workload("f5", 40, 17, [5, 4, 3]), GENERAL, False),
     "ti_general": (lambda: wl.hubbard24(True, l=8), GENERAL, False),
-    "bath_rows_m4_general": (lambda: wl.make_workload("b4", 44, 20, [4, 4], fit_imp_bath=True), GENERAL, False),
+    "bath_rows_m4": (lambda: wl.make_workload("b4", 44, 20, [4, 4], fit_imp_bath=True), DMMA, False),   # 8-row fragments
+    "bath_rows_mixed": (lambda: wl.make_workload("bm", 70, 31, [4, 3, 1, 4, 2, 4, 4, 3], fit_imp_bath=True), DMMA, False),
+    "hubbard8x8_bath": (lambda: wl.hubbard24(False, fit_imp_bath=True, l=8), DMMA, False),
+    "sweep192_tile96": (lambda: wl.sweep(192), DMMA, True),                  # no = 96: 96-column tiles
+    "frag9_general": (lambda: wl.make_workload("f9", 60, 25, [4, 4, 4, 4, 1], fit_imp_bath=False, nterms=None)
+                      if False else wl.make_workload("f9", 48, 21, [9, 4]), GENERAL, False),
 }
 
 
