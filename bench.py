@@ -43,6 +43,11 @@ def parse():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="sweep",
+                    choices=["sweep", "hubbard24", "hubbard24_bath", "hubbard24_ti", "hubbard24_ti_bath", "polyyne", "sn2"],
+                    help="sweep: BASELINE configs[4] (default, the north-star target at --norb 4000); hubbard24*: "
+                         "configs[1] 24x24 Hubbard, 2x2 impurities (non-TI / TI, impurity-only / impurity+bath rows); "
+                         "polyyne / sn2: the shapes of configs[2] / configs[3]")
     ap.add_argument("--norb", type=int, default=int(os.environ.get("QCDMET_BENCH_NORB", 4000)))
     ap.add_argument("--nterms", type=int, default=None, help="default 2.5*norb")
     ap.add_argument("--kernel", default="auto", choices=["auto", "general", "dmma"])
@@ -170,13 +175,32 @@ def default_sample_cols(norb):
     return max(cols, 1)
 
 
+def make_workload(args):
+    from qcdmet_b200 import workloads
+    if args.workload == "sweep":
+        w = workloads.sweep(args.norb, args.nterms)
+        desc = (f"response sweep Norb={w.norb} Nocc={w.num_pairs} P={w.nterms} "
+                f"(4-site fragments, impurity-only rows, Q={w.nresid})")
+    elif args.workload.startswith("hubbard24"):
+        ti, bath = "_ti" in args.workload, args.workload.endswith("_bath")
+        w = workloads.hubbard24(trans_inv=ti, fit_imp_bath=bath)
+        desc = (f"2D Hubbard 24x24 half filling (PBC x APBC), 2x2 impurities, {'TI' if ti else 'non-TI'}, "
+                f"{'impurity+bath' if bath else 'impurity-only'} rows: Norb=576 Nocc=288 P={w.nterms} Q={w.nresid}")
+    elif args.workload == "polyyne":
+        w = workloads.polyyne_like()
+        desc = f"polyyne-like shape Norb=168 Nocc=36, 12 fragments of 14: P={w.nterms} Q={w.nresid}"
+    else:
+        w = workloads.sn2_like()
+        desc = f"sn2-like shape Norb=321 Nocc=58, fragments [52, 24x10, 29]: P={w.nterms} Q={w.nresid}"
+    return w, desc
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
-    from qcdmet_b200 import workloads
-    w = workloads.sweep(args.norb, args.nterms)
-    cols = args.cpu_sample_cols or default_sample_cols(args.norb)
+    w, desc = make_workload(args)
+    cols = args.cpu_sample_cols or default_sample_cols(w.norb)
     rates = []
     info = None
     warm = min(args.warmup, 1)    # each call is tens of seconds of CPU work: one warm-up is enough
@@ -196,8 +220,7 @@ def run_reference(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / len(rates),
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": f"response sweep Norb={w.norb} Nocc={w.num_pairs} P={w.nterms} "
-                                   f"(4-site fragments, Q={w.nresid})", "sample_cols_per_step": cols},
+            "config": {"workload": desc, "sample_cols_per_step": cols},
             "cpu_baseline": info,
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print_json(line)
@@ -219,7 +242,7 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
 
-    w = workloads.sweep(args.norb, args.nterms)
+    w, desc = make_workload(args)
     P, Q = w.nterms, w.nresid
     # column shard, aligned to whole fragments (10 parameters each) so the ranks do equal work
     shards = sharding.column_shards(P, world, 10)
@@ -382,13 +405,12 @@ def run_b200(args):
             w_cols /= world      # this rank executed 1/world of the block-pair list
         cpu = None
         if not args.no_cpu_baseline:
-            cpu = cpu_reference_rate(w, args.cpu_sample_cols or default_sample_cols(args.norb))
+            cpu = cpu_reference_rate(w, args.cpu_sample_cols or default_sample_cols(w.norb))
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"response sweep Norb={w.norb} Nocc={w.num_pairs} P={P} "
-                                   f"(4-site fragments, impurity-only rows, Q={Q})",
+            "config": {"workload": desc,
                        "kernel": {1: "general", 2: "dmma"}.get(kernel_used, str(kernel_used)),
                        "sharding": ("single GPU" if world == 1 else
                                     f"{world} ranks, block-pair work list split evenly, fused all-gather: each Jacobian element "

@@ -30,6 +30,7 @@
 #include "common.cuh"
 #include <algorithm>
 #include <cstdint>
+#include <functional>
 #include <map>
 #include <numeric>
 
@@ -243,6 +244,22 @@ __global__ void zero_columns_kernel(ZeroArgs z, const int *__restrict__ cols, in
     const size_t base = (size_t)Q * (cols[blockIdx.y] - colBegin);
     for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < Q; q += (long long)gridDim.x * blockDim.x)
         for (int dst = 0; dst < z.nDest; ++dst) z.J[dst][base + q] = 0.0;
+}
+
+// Perturbations whose elements fall into several disconnected site groups (translation-invariant
+// lists: the same element replicated in every cell, src/dmet.py:139-148) are split into one
+// sub-perturbation per group; dD is linear in H1, so J[:,p] = sum over its sub-perturbations
+// (fixed order: deterministic).
+__global__ void sum_subcolumns_kernel(const double *__restrict__ Jsub, const int *__restrict__ subStart,
+                                      int colBegin, int subBegin, long long Q, double *__restrict__ J)
+{
+    const int p = colBegin + blockIdx.y;
+    const int sb = subStart[p], se = subStart[p + 1];
+    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < Q; q += (long long)gridDim.x * blockDim.x) {
+        double acc = 0.0;
+        for (int k = sb; k < se; ++k) acc += Jsub[(size_t)Q * (k - subBegin) + q];
+        J[(size_t)Q * blockIdx.y + q] = acc;
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -496,6 +513,12 @@ struct DmmaPlanData {
     size_t wStage() const { return (size_t)KC * bn(); }
     size_t posDoubles() const { return (size_t)(AT + 1) * (bn() + 8); }
     size_t cosDoubles() const { return (size_t)RT * bn(); }
+    bool expanded = false;              // perturbations were split into connected sub-perturbations
+    int P2 = 0;                         // number of sub-perturbations (internal columns)
+    std::vector<int> subStart;          // [P+1] sub-perturbations of p: [subStart[p], subStart[p+1])
+    int *d_subStart = nullptr;
+    double *d_Jsub = nullptr;           // scratch (Q x internal columns) when expanded
+    size_t JsubCapacity = 0;
     std::vector<int> emptyP;            // perturbations without elements: zero columns
     int *d_emptyCols = nullptr;
     std::vector<int> emptyInRange;
@@ -528,13 +551,49 @@ struct Schedule {
     DmmaPlanData d;
 };
 
-Schedule build_schedule(int N, int no, int P, int F, const int *h1start, const int *h1row, const int *h1col,
+Schedule build_schedule(int N, int no, int Porig, int F, const int *h1start0, const int *h1row0, const int *h1col0,
                         const int *rowStart, const int *rowIdx)
 {
     Schedule sc;
     DmmaPlanData &d = sc.d;
-    d.N = N; d.no = no; d.nv = N - no; d.P = P; d.S = F > 0 ? rowStart[F] : 0;
-    if (P == 0 || d.S == 0) { sc.why = "empty problem"; return sc; }
+    d.N = N; d.no = no; d.nv = N - no; d.P = Porig; d.S = F > 0 ? rowStart[F] : 0;
+    if (Porig == 0 || d.S == 0) { sc.why = "empty problem"; return sc; }
+    // split every perturbation into the connected groups of its own elements (sites linked by an element)
+    std::vector<int> xs(1, 0), xr, xc;
+    d.subStart.assign(1, 0);
+    {
+        std::map<int, int> par;
+        std::function<int(int)> fnd = [&](int x) { while (par[x] != x) { par[x] = par[par[x]]; x = par[x]; } return x; };
+        for (int p = 0; p < Porig; ++p) {
+            par.clear();
+            for (int k = h1start0[p]; k < h1start0[p + 1]; ++k) {
+                if (!par.count(h1row0[k])) par[h1row0[k]] = h1row0[k];
+                if (!par.count(h1col0[k])) par[h1col0[k]] = h1col0[k];
+            }
+            for (int k = h1start0[p]; k < h1start0[p + 1]; ++k) {
+                const int ra = fnd(h1row0[k]), rb = fnd(h1col0[k]);
+                if (ra != rb) par[rb] = ra;
+            }
+            std::map<int, std::vector<int>> groups;      // root -> element indices, in original order
+            std::vector<int> order;
+            for (int k = h1start0[p]; k < h1start0[p + 1]; ++k) {
+                const int r = fnd(h1row0[k]);
+                if (!groups.count(r)) order.push_back(r);
+                groups[r].push_back(k);
+            }
+            for (int r : order) {
+                for (int k : groups[r]) { xr.push_back(h1row0[k]); xc.push_back(h1col0[k]); }
+                xs.push_back((int)xr.size());
+            }
+            d.subStart.push_back((int)xs.size() - 1);
+            if (order.size() > 1) d.expanded = true;
+        }
+    }
+    const int P = d.expanded ? (int)xs.size() - 1 : Porig;
+    const int *h1start = d.expanded ? xs.data() : h1start0;
+    const int *h1row = d.expanded ? xr.data() : h1row0;
+    const int *h1col = d.expanded ? xc.data() : h1col0;
+    d.P2 = P;
     // fragments: <= 8 rows each, packed whole into tiles of AT row slots
     std::vector<long long> qoff(F + 1, 0);
     int maxRf = 0;
@@ -652,7 +711,7 @@ Schedule build_schedule(int N, int no, int P, int F, const int *h1start, const i
     d.compLoc.assign((size_t)d.nComp * RT, 0xFF);
     d.tileP.assign((size_t)d.nTiles * TP, -1);
     d.tileEnt.assign((size_t)d.nTiles * TP * MAXE, 0xFF);
-    bool sym = (rowIdx != nullptr) && RF == 4;
+    bool sym = (rowIdx != nullptr) && RF == 4 && !d.expanded;
     if (sym) {
         std::vector<int> siteComp(N, -1), compFrag(d.nComp, -1);
         for (int c = 0; c < d.nComp; ++c)
@@ -739,7 +798,8 @@ int dmma_plan_build(DmmaPlanData **out, int N, int no, int P, int F, const int *
         (rc = upload(&d->d_tilePartner, d->tilePartner)) || (rc = upload(&d->d_tileSelf, d->tileSelf)) ||
         (rc = upload(&d->d_tileQ, d->tileQ)) || (rc = upload(&d->d_compTile, d->compTile)) ||
         (rc = upload(&d->d_compQ, d->compQ)) || (rc = upload(&d->d_compLoc, d->compLoc)) ||
-        (rc = upload(&d->d_tileP, d->tileP)) || (rc = upload(&d->d_tileEnt, d->tileEnt))) {
+        (rc = upload(&d->d_tileP, d->tileP)) || (rc = upload(&d->d_tileEnt, d->tileEnt)) ||
+        (rc = upload(&d->d_subStart, d->subStart))) {
         dmma_plan_free(d);
         return rc;
     }
@@ -765,7 +825,7 @@ void dmma_plan_free(DmmaPlanData *d)
     cudaFree(d->d_tilePartner); cudaFree(d->d_tileSelf); cudaFree(d->d_tileQ); cudaFree(d->d_work);
     cudaFree(d->d_compTile); cudaFree(d->d_compQ); cudaFree(d->d_compLoc); cudaFree(d->d_tileP); cudaFree(d->d_tileEnt);
     cudaFree(d->d_Wt); cudaFree(d->d_PVt); cudaFree(d->d_CVt); cudaFree(d->d_POt); cudaFree(d->d_COt);
-    cudaFree(d->d_emptyCols);
+    cudaFree(d->d_emptyCols); cudaFree(d->d_subStart); cudaFree(d->d_Jsub);
     cudaGetLastError();
     delete d;
 }
@@ -795,6 +855,11 @@ int launch_jacobian_dmma(DmmaPlanData *d, const JacView &v, cudaStream_t st, int
     *flops = 0.0;
     const int ncols = v.colEnd - v.colBegin;
     if (ncols <= 0) return QCDMET_OK;
+    QC_CHECK(!(d->expanded && peers), QCDMET_E_STATE,
+             "peer mode is not available for split (translation-invariant) perturbation lists");
+    // internal column range: sub-perturbations when the list was split
+    const int cb = d->expanded ? d->subStart[v.colBegin] : v.colBegin;
+    const int ce = d->expanded ? d->subStart[v.colEnd] : v.colEnd;
     const bool wantSym = allowSym && d->symOk && v.colBegin == 0 && v.colEnd == d->P;
     const int shareRank = peers ? peers->rank : 0, shareN = peers ? peers->nranks : 1;
     if (d->launchBegin != v.colBegin || d->launchEnd != v.colEnd || d->launchSym != wantSym ||
@@ -806,7 +871,7 @@ int launch_jacobian_dmma(DmmaPlanData *d, const JacView &v, cudaStream_t st, int
         for (int c = 0; c < d->nComp; ++c)
             for (int k = 0; k < MAXP && !hit[c]; ++k) {
                 const int p = d->compP[(size_t)c * MAXP + k];
-                hit[c] = (p >= v.colBegin && p < v.colEnd);
+                hit[c] = (p >= cb && p < ce);
             }
         std::vector<int2> all;
         for (int t = 0; t < d->nTiles; ++t)
@@ -825,7 +890,7 @@ int launch_jacobian_dmma(DmmaPlanData *d, const JacView &v, cudaStream_t st, int
             fl += ns * nr * (2.0 * d->nv * d->no + (double)d->nv * d->nOt + ns * d->no * (1.0 + 2.0 * d->rf));
         }
         d->emptyInRange.clear();
-        if (shareRank == 0)
+        if (shareRank == 0 && !d->expanded)
             for (int p : d->emptyP)
                 if (p >= v.colBegin && p < v.colEnd) d->emptyInRange.push_back(p);
         if (!d->emptyInRange.empty()) {
@@ -857,49 +922,73 @@ int launch_jacobian_dmma(DmmaPlanData *d, const JacView &v, cudaStream_t st, int
         d->launchRank = shareRank;
         d->launchRanks = shareN;
     }
+    double *target = v.J;
+    if (d->expanded) {
+        const size_t need = (size_t)v.Q * std::max(ce - cb, 1);
+        if (need > d->JsubCapacity) {
+            cudaFree(d->d_Jsub);
+            d->d_Jsub = nullptr;
+            d->JsubCapacity = 0;
+            if (cudaMalloc((void **)&d->d_Jsub, need * sizeof(double)) != cudaSuccess) {
+                cudaGetLastError();
+                set_error("cudaMalloc of the sub-perturbation scratch (%zu doubles) failed", need);
+                return QCDMET_E_ALLOC;
+            }
+            d->JsubCapacity = need;
+        }
+        target = d->d_Jsub;
+    }
     ZeroArgs z;
     z.nDest = peers ? peers->nranks : 1;
-    for (int r = 0; r < QCDMET_MAX_PEERS; ++r) z.J[r] = (peers && r < peers->nranks) ? peers->J[r] : (r == 0 ? v.J : nullptr);
+    for (int r = 0; r < QCDMET_MAX_PEERS; ++r) z.J[r] = (peers && r < peers->nranks) ? peers->J[r] : (r == 0 ? target : nullptr);
     if (!d->emptyInRange.empty()) {
         const unsigned gx = (unsigned)std::min<long long>((v.Q + 255) / 256, 1024);
         zero_columns_kernel<<<dim3(gx, (unsigned)d->emptyInRange.size()), 256, 0, st>>>(z, d->d_emptyCols, v.colBegin, v.Q);
         QC_CUDA(cudaGetLastError());
         *launches += 1;
     }
-    if (d->work.empty()) return QCDMET_OK;
-    DmmaArgs a;
-    a.nKc = d->nKc; a.nOt = d->nOt;
-    a.colBegin = v.colBegin; a.colEnd = v.colEnd; a.sym = d->launchSym ? 1 : 0; a.Q = v.Q;
-    a.Wt = d->d_Wt; a.PVt = d->d_PVt; a.CVt = d->d_CVt; a.POt = d->d_POt; a.COt = d->d_COt;
-    a.work = d->d_work; a.compTile = d->d_compTile; a.compQ = d->d_compQ; a.compLoc = d->d_compLoc;
-    a.tileP = d->d_tileP; a.tileEnt = d->d_tileEnt;
-    a.compSites = d->d_compSites; a.compP = d->d_compP;
-    a.compEnt = d->d_compEnt; a.tileRow = d->d_tileRow; a.tilePartner = d->d_tilePartner;
-    a.tileSelf = d->d_tileSelf; a.tileQ = d->d_tileQ;
-    a.nDest = z.nDest;
-    for (int r = 0; r < QCDMET_MAX_PEERS; ++r) a.J[r] = z.J[r];
-    if (ev0) QC_CUDA(cudaEventRecord(ev0, st));
-    const unsigned grid = (unsigned)d->work.size();
-    int rc = QCDMET_E_STATE;
+    if (!d->work.empty()) {
+        DmmaArgs a;
+        a.nKc = d->nKc; a.nOt = d->nOt;
+        a.colBegin = cb; a.colEnd = ce; a.sym = d->launchSym ? 1 : 0; a.Q = v.Q;
+        a.Wt = d->d_Wt; a.PVt = d->d_PVt; a.CVt = d->d_CVt; a.POt = d->d_POt; a.COt = d->d_COt;
+        a.work = d->d_work; a.compTile = d->d_compTile; a.compQ = d->d_compQ; a.compLoc = d->d_compLoc;
+        a.tileP = d->d_tileP; a.tileEnt = d->d_tileEnt;
+        a.compSites = d->d_compSites; a.compP = d->d_compP;
+        a.compEnt = d->d_compEnt; a.tileRow = d->d_tileRow; a.tilePartner = d->d_tilePartner;
+        a.tileSelf = d->d_tileSelf; a.tileQ = d->d_tileQ;
+        a.nDest = z.nDest;
+        for (int r = 0; r < QCDMET_MAX_PEERS; ++r) a.J[r] = z.J[r];
+        if (ev0) QC_CUDA(cudaEventRecord(ev0, st));
+        const unsigned grid = (unsigned)d->work.size();
+        int rc = QCDMET_E_STATE;
 #define QC_LAUNCH_VARIANT(RFV, NJV)                                                                           \
-    if (d->rf == RFV && d->nj == NJV) {                                                                       \
-        using K = Cfg<RFV, NJV>;                                                                              \
-        if (!d->attrSet) {                                                                                    \
-            QC_CUDA(cudaFuncSetAttribute(jac_dmma_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
-                                         K::SMEM_BYTES));                                                     \
-            d->attrSet = true;                                                                                \
-        }                                                                                                     \
-        jac_dmma_kernel<K><<<grid, NTHREADS, K::SMEM_BYTES, st>>>(a);                                         \
-        rc = QCDMET_OK;                                                                                       \
-    }
-    QC_LAUNCH_VARIANT(4, 8) QC_LAUNCH_VARIANT(4, 6) QC_LAUNCH_VARIANT(4, 4)
-    QC_LAUNCH_VARIANT(8, 8) QC_LAUNCH_VARIANT(8, 6) QC_LAUNCH_VARIANT(8, 4)
+        if (d->rf == RFV && d->nj == NJV) {                                                                   \
+            using K = Cfg<RFV, NJV>;                                                                          \
+            if (!d->attrSet) {                                                                                \
+                QC_CUDA(cudaFuncSetAttribute(jac_dmma_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                             K::SMEM_BYTES));                                                 \
+                d->attrSet = true;                                                                            \
+            }                                                                                                 \
+            jac_dmma_kernel<K><<<grid, NTHREADS, K::SMEM_BYTES, st>>>(a);                                     \
+            rc = QCDMET_OK;                                                                                   \
+        }
+        QC_LAUNCH_VARIANT(4, 8) QC_LAUNCH_VARIANT(4, 6) QC_LAUNCH_VARIANT(4, 4)
+        QC_LAUNCH_VARIANT(8, 8) QC_LAUNCH_VARIANT(8, 6) QC_LAUNCH_VARIANT(8, 4)
 #undef QC_LAUNCH_VARIANT
-    QC_CHECK(rc == QCDMET_OK, QCDMET_E_STATE, "no DMMA kernel variant for rf=%d nj=%d", d->rf, d->nj);
-    QC_CUDA(cudaGetLastError());
-    if (ev1) QC_CUDA(cudaEventRecord(ev1, st));
-    *launches += 1;
-    *flops = d->launchFlops;
+        QC_CHECK(rc == QCDMET_OK, QCDMET_E_STATE, "no DMMA kernel variant for rf=%d nj=%d", d->rf, d->nj);
+        QC_CUDA(cudaGetLastError());
+        if (ev1) QC_CUDA(cudaEventRecord(ev1, st));
+        *launches += 1;
+        *flops = d->launchFlops;
+    }
+    if (d->expanded) {
+        // every sub-column in [cb, ce) has been written by exactly one CTA (each sub-perturbation is non-empty)
+        const unsigned gx = (unsigned)std::min<long long>((v.Q + 255) / 256, 1024);
+        sum_subcolumns_kernel<<<dim3(gx, (unsigned)ncols), 256, 0, st>>>(d->d_Jsub, d->d_subStart, v.colBegin, cb, v.Q, v.J);
+        QC_CUDA(cudaGetLastError());
+        *launches += 1;
+    }
     return QCDMET_OK;
 }
 

@@ -122,7 +122,11 @@ DMMA_SHAPES = {
     "truncated_list": (lambda: wl.sweep(160, nterms=333), DMMA, False),      # fragments without perturbations
     "bath_rows_m2": (lambda: wl.make_workload("b2", 44, 20, [2, 2, 1, 2], fit_imp_bath=True), DMMA, False),
     "frag5_general": (lambda: wl.make_workload("f5", 40, 17, [5, 4, 3]), GENERAL, False),
-    "ti_general": (lambda: wl.hubbard24(True, l=8), GENERAL, False),
+    "ti_split": (lambda: wl.hubbard24(True, l=8), DMMA, False),              # TI list split per cell, columns summed
+    "ti_split_bath": (lambda: wl.hubbard24(True, fit_imp_bath=True, l=8), DMMA, False),
+    "ti_m2_bath": (lambda: wl.make_workload("ti2", 24, 11, [2] * 12, trans_inv=True, fit_imp_bath=True), DMMA, False),
+    "ti_m3": (lambda: wl.make_workload("ti3", 36, 16, [3] * 12, trans_inv=True), DMMA, False),
+    "ti_m5_general": (lambda: wl.make_workload("ti5", 40, 18, [5] * 8, trans_inv=True), GENERAL, False),
     "bath_rows_m4": (lambda: wl.make_workload("b4", 44, 20, [4, 4], fit_imp_bath=True), DMMA, False),   # 8-row fragments
     "bath_rows_mixed": (lambda: wl.make_workload("bm", 70, 31, [4, 3, 1, 4, 2, 4, 4, 3], fit_imp_bath=True), DMMA, False),
     "hubbard8x8_bath": (lambda: wl.hubbard24(False, fit_imp_bath=True, l=8), DMMA, False),
@@ -143,6 +147,7 @@ def test_kernel_selection_and_dmma_parity(shape):
     assert run_plan.last_symmetric == expect_sym
     assert np.abs(jac - oracle_jac(w, c, e)).max() <= TOL
     if expect == GENERAL:
+        assert np.abs(jac - oracle_jac(w, c, e)).max() <= TOL
         plan = _lib.Plan(w.norb, w.num_pairs, w.h1start, w.h1row, w.h1col, w.row_start, w.rows, w.row_idx)
         with pytest.raises(_lib.QcdmetError):
             plan.set_kernel(_lib.KERNEL_DMMA)
