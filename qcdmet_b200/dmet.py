@@ -57,6 +57,7 @@ class dmet:
             assert self.fitImpBath is False
             assert self.SCmethod in ('BFGS', 'NONE')
         self.solver = solver
+        self.gpu_residual = True      # residual blocks from the device eigensolve shared with the Jacobian
 
         self.print_u = True
         self.print_rdm = True
@@ -260,6 +261,28 @@ class dmet:
 
     # ------------------------------------------------------------------ src/dmet.py:395-439
     def rdm_differences(self, newumatflat):
+        """Residual of the fit.  With gpu_residual (default) the mean-field blocks come from the device
+        eigensolve that the Jacobian at the same umat reuses; otherwise the reference's
+        host route (numpy eigh of the full matrix, src/qcdmethelper.py:114-122) is followed line by line."""
+        if self.gpu_residual and not self.altcostfunc:
+            start_func = time.time()
+            row_start, rows, row_idx = self._fragment_rows()
+            mf = self.helper.construct1RDM_blocks(self.flat2square(newumatflat), row_start, rows=rows,
+                                                  row_idx=row_idx, NOrotation=self.NOrotation)
+            pieces = []
+            for count in range(len(self.imp_size)):
+                if self.fitImpBath:
+                    ed_1RDM = self.imp_1RDM[count]
+                else:
+                    m = int(self.imp_size[count])
+                    ed_1RDM = self.imp_1RDM[count][:m, :m]
+                pieces.append(np.reshape(ed_1RDM, ed_1RDM.size, order='F'))
+            errors = mf - np.concatenate(pieces)
+            self.time_func += time.time() - start_func
+            return errors
+        return self.rdm_differences_host(newumatflat)
+
+    def rdm_differences_host(self, newumatflat):
         start_func = time.time()
         newumatsquare_loc = self.flat2square(newumatflat)
         OneRDM_loc = self.helper.construct1RDM_loc(self.doSCF, newumatsquare_loc)

@@ -154,16 +154,35 @@ class qcdmethelper:
             self._plans[key] = plan
         return plan
 
+    def _plan_with_orbitals(self, umat_loc, row_start, rows, row_idx, NOrotation):
+        """Plan whose device orbitals are those of Fock + umat.  The Levenberg-Marquardt driver evaluates
+        the residual and the Jacobian at the same umat (src/dmet.py:631): the eigensolve (one cuSOLVER
+        syevd) is shared between the two calls instead of being repeated as in the reference
+        (numpy eigh in construct1RDM_base + dsyev in rhf_response)."""
+        plan = self._plan(row_start, rows, row_idx)
+        oei = self._oei(False, umat_loc, NOrotation)
+        cached = getattr(plan, "_oei_cache", None)
+        if cached is None or not np.array_equal(cached, oei):
+            plan.set_h0(oei)
+            plan._oei_cache = np.array(oei, copy=True)
+            self.num_eigensolves = getattr(self, "num_eigensolves", 0) + 1
+        return plan
+
     def response_jacobian(self, umat_loc, row_start, rows=None, row_idx=None, NOrotation=None,
                           want_dblocks=False):
         """Fragment blocks of every dD_p, written directly as Jacobian columns.
 
         Replaces construct1RDM_response + the assembly loop of src/dmet.py:496-520.
         Returns a Fortran-ordered (Q, Nterms) float64 array (and the mean-field 1-RDM blocks)."""
-        plan = self._plan(row_start, rows, row_idx)
-        plan.set_h0(self._oei(False, umat_loc, NOrotation))
+        plan = self._plan_with_orbitals(umat_loc, row_start, rows, row_idx, NOrotation)
         plan.compute()
         jac = plan.jacobian()
         if want_dblocks:
             return jac, plan.dblocks()
         return jac
+
+    def construct1RDM_blocks(self, umat_loc, row_start, rows=None, row_idx=None, NOrotation=None):
+        """Fragment blocks R_f (2 C_o C_o^T) R_f^T of the mean-field 1-RDM, flattened like the residual
+        (column-major per fragment): the model part of dmet.rdm_differences (src/dmet.py:416-421,432),
+        from the device eigensolve shared with response_jacobian."""
+        return self._plan_with_orbitals(umat_loc, row_start, rows, row_idx, NOrotation).dblocks()

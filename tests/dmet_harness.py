@@ -10,6 +10,10 @@ class OracleDmet(dmet_mod.dmet):
     """dmet whose Jacobian comes from the CPU oracle (restatement of src/dmet.py:477-525 on top of
     lib/rhf_response.cc) instead of libqcdmet_b200."""
 
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.gpu_residual = False          # reference's host route for the residual: no device in this loop
+
     def rdm_differences_derivative(self, newumatflat):
         rs, rows, idx = self._fragment_rows()
         h0 = self.ints.loc_rhf_fock() + self.flat2square(newumatflat)

@@ -334,6 +334,33 @@ def test_dmet_class_jacobian_and_gradient(case):
     assert d.time_grad > 0.0
 
 
+@pytest.mark.parametrize("case", ["imp_only", "imp_bath", "ti_bath"])
+def test_gpu_residual_matches_host_and_shares_eigensolve(case):
+    """dmet.rdm_differences from the device eigensolve (f-2) against the reference's host route and the
+    oracle; one syevd serves the residual and the Jacobian at the same umat."""
+    w = {"imp_only": lambda: wl.make_workload("m", 40, 17, [4, 6, 3, 5]),
+         "imp_bath": lambda: wl.make_workload("b", 36, 15, [3, 4, 2], fit_imp_bath=True),
+         "ti_bath": lambda: wl.hubbard24(True, fit_imp_bath=True, l=6)}[case]()
+    d = dmet_mod.dmet(Ints(w.h0, 2 * w.num_pairs), w.imp_clust, w.trans_inv, fitImpBath=w.fit_imp_bath)
+    if w.fit_imp_bath:
+        d.dmetOrbs = w.dmet_orbs
+    rng = np.random.default_rng(11)
+    nfit = len(d.imp_size)
+    sizes = [b.shape[1] for b in w.dmet_orbs] if w.fit_imp_bath else [2 * int(m) for m in d.imp_size]
+    d.imp_1RDM = [(lambda a: a + a.T)(rng.standard_normal((s, s))) for s in sizes[:nfit]]
+    x = rng.standard_normal(d.helper.Nterms) * 0.02
+    r_gpu = d.rdm_differences(x)
+    assert d.helper.num_eigensolves == 1
+    jac = d.rdm_differences_derivative(x)
+    assert d.helper.num_eigensolves == 1                 # same umat: the eigensolve is reused
+    r_host = d.rdm_differences_host(x)
+    r_ref = ro.rdm_differences(w.h0, x, w.num_pairs, w.imp_clust, w.trans_inv, w.fit_imp_bath, d.imp_1RDM, w.dmet_orbs)
+    assert np.abs(r_gpu - r_ref).max() <= TOL and np.abs(r_host - r_ref).max() <= TOL
+    d.rdm_differences(x + 1e-3)
+    assert d.helper.num_eigensolves == 2
+    assert jac.shape == (r_gpu.size, d.helper.Nterms)
+
+
 def test_helper_full_response_api():
     w = wl.make_workload("m", 24, 10, [4, 4, 4])
     d = dmet_mod.dmet(Ints(w.h0, 20), w.imp_clust, False, fitImpBath=False)

@@ -62,7 +62,7 @@ def test_fragment_rows_and_residual():
     rng = np.random.default_rng(0)
     d.imp_1RDM = [rng.standard_normal((2 * m, 2 * m)) for m in (3, 5, 2)]
     x = rng.standard_normal(d.helper.Nterms) * 0.1
-    r = d.rdm_differences(x)
+    r = d.rdm_differences_host(x)
     r_ref = ro.rdm_differences(w.h0, x, w.num_pairs, w.imp_clust, False, False, d.imp_1RDM)
     assert np.abs(r - r_ref).max() < 1e-13
     wb = wl.make_workload("b", 16, 6, [2, 3], fit_imp_bath=True)
