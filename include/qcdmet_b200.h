@@ -152,6 +152,14 @@ int qcdmet_plan_get_orbitals(qcdmet_plan *plan, double *C);
  * the 1-RDM (N*N) if one_rdm != NULL. */
 int qcdmet_plan_get_full_response(qcdmet_plan *plan, double *rdm_deriv, double *one_rdm);
 
+/* Levenberg-Marquardt step from the Jacobian resident on the device (no 8 Q P byte D2H):
+ *   (J^T J + lambda diag(J^T J)) step = -J^T resid        resid: Q doubles (host), step: ncols doubles (host)
+ * cuBLAS DSYRK/DGEMV + cuSOLVER potrf/potrs; J^T J is kept until the next compute, so retries with a
+ * different lambda cost one Cholesky.  info (optional, 2 doubles): max|J^T resid|, (J^T resid).step.
+ * Replaces the MINPACK lmder iteration behind scipy.optimize.leastsq (src/dmet.py:631) for large fits.
+ * QCDMET_E_SOLVER if the damped matrix is not positive definite (raise lambda). */
+int qcdmet_plan_lm_step(qcdmet_plan *plan, const double *resid, double lambda, double *step, double *info);
+
 /* Introspection (bench / tests). */
 long long qcdmet_plan_num_residuals(qcdmet_plan *plan);    /* Q                                  */
 int  qcdmet_plan_kernel_used(qcdmet_plan *plan);           /* QCDMET_KERNEL_GENERAL or _DMMA      */

@@ -57,6 +57,8 @@ SIGNATURES = {
     "qcdmet_plan_get_eigenvalues": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     "qcdmet_plan_get_orbitals": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     "qcdmet_plan_get_full_response": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "qcdmet_plan_lm_step": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_double, ctypes.c_void_p,
+                                           ctypes.c_void_p]),
     "qcdmet_plan_num_residuals": (ctypes.c_longlong, [ctypes.c_void_p]),
     "qcdmet_plan_kernel_used": (ctypes.c_int, [ctypes.c_void_p]),
     "qcdmet_plan_launches": (ctypes.c_int, [ctypes.c_void_p]),
@@ -198,6 +200,15 @@ class Plan:
         assert out.flags.f_contiguous and out.shape == (self.nresid, ncols)
         check(self.lib.qcdmet_plan_get_jacobian(self.handle, _ptr(out)))
         return out
+
+    def lm_step(self, resid, lam):
+        """Damped normal-equation step from the device-resident Jacobian.  Returns (step, max|J^T r|, g.step)."""
+        resid = as_f64(resid)
+        assert resid.size == self.nresid
+        step = np.empty(self.col_end - self.col_begin, dtype=np.float64)
+        info = np.zeros(2, dtype=np.float64)
+        check(self.lib.qcdmet_plan_lm_step(self.handle, _ptr(resid), float(lam), _ptr(step), _ptr(info)))
+        return step, float(info[0]), float(info[1])
 
     def dblocks(self):
         out = np.empty(self.nresid, dtype=np.float64)

@@ -56,6 +56,11 @@ struct qcdmet_plan {
     int launches = 0;
     double flops = 0.0;
     bool symmetric_used = false;
+    // Levenberg-Marquardt normal equations on the device (qcdmet_plan_lm_step)
+    double *d_A = nullptr, *d_Awork = nullptr, *d_g = nullptr, *d_r = nullptr, *d_potrf = nullptr;
+    int potrf_lwork = 0;
+    bool normal_valid = false;          // d_A = J^T J of the Jacobian in memory
+    bool jac_in_memory = false;         // d_J holds a complete Jacobian (possibly of earlier orbitals)
     bool peers_on = false;
     PeerSet peers;
     void *ipc_opened[QCDMET_MAX_PEERS] = {nullptr};
@@ -320,6 +325,7 @@ int qcdmet_plan_destroy(qcdmet_plan *p)
     cudaFree(p->d_rowStart); cudaFree(p->d_rowFrag); cudaFree(p->d_rowIdx); cudaFree(p->d_qoff);
     cudaFree(p->d_R); cudaFree(p->d_C); cudaFree(p->d_e);
     cudaFree(p->d_CoT); cudaFree(p->d_CvT); cudaFree(p->d_PO); cudaFree(p->d_PV);
+    cudaFree(p->d_A); cudaFree(p->d_Awork); cudaFree(p->d_g); cudaFree(p->d_r); cudaFree(p->d_potrf);
     cudaFree(p->d_J_own); cudaFree(p->d_D); cudaFree(p->d_work); cudaFree(p->d_info);
     if (p->ev0) cudaEventDestroy(p->ev0);
     if (p->ev1) cudaEventDestroy(p->ev1);
@@ -339,6 +345,7 @@ int qcdmet_plan_set_columns(qcdmet_plan *p, int colBegin, int colEnd)
     p->colBegin = colBegin;
     p->colEnd = colEnd;
     p->have_jac = false;
+    p->jac_in_memory = false;
     return QCDMET_OK;
 }
 
@@ -367,6 +374,7 @@ int qcdmet_plan_set_output_device(qcdmet_plan *p, void *device_ptr, long long ca
     p->d_J_ext = (double *)device_ptr;
     p->J_ext_capacity = device_ptr ? (size_t)capacity : 0;
     p->have_jac = false;
+    p->jac_in_memory = false;
     return QCDMET_OK;
 }
 
@@ -439,6 +447,98 @@ int qcdmet_plan_compute(qcdmet_plan *p)
         p->symmetric_used = false;
     }
     p->have_jac = true;
+    p->jac_in_memory = true;
+    p->normal_valid = false;
+    return QCDMET_OK;
+}
+
+// (A + lambda diag(A)) with a floor on the diagonal so that the system stays positive definite along
+// directions the residual does not depend on (the chemical-potential gauge of umat, src/dmet.py:636)
+__global__ void lm_damp_kernel(const double *__restrict__ A, double *__restrict__ W, int n, double lambda, double floor_)
+{
+    const size_t total = (size_t)n * n;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int r = (int)(i % n), c = (int)(i / n);
+        double v = A[i];
+        if (r == c) v += lambda * fmax(v, floor_);
+        W[i] = v;
+    }
+}
+__global__ void lm_negate_kernel(const double *__restrict__ g, double *__restrict__ x, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) x[i] = -g[i];
+}
+
+extern "C" int qcdmet_plan_lm_step(qcdmet_plan *p, const double *resid, double lambda, double *step, double *info)
+{
+    QC_CHECK(p != nullptr && resid != nullptr && step != nullptr, QCDMET_E_ARG, "plan, resid or step is NULL");
+    // the Jacobian stays in device memory when new orbitals are set (set_h0 for a trial residual), so a
+    // rejected trial step can be retried with a larger lambda without recomputing it
+    QC_CHECK(p->jac_in_memory, QCDMET_E_STATE, "no Jacobian computed yet");
+    QC_CHECK(lambda >= 0.0, QCDMET_E_ARG, "lambda must be >= 0");
+    DeviceGuard guard(p->device);
+    const int n = p->colEnd - p->colBegin;
+    const long long Q = p->Q;
+    QC_CHECK(n > 0 && Q > 0 && Q < (1LL << 31), QCDMET_E_ARG, "empty or oversized least-squares problem");
+    if (!p->d_A) {
+        QC_TRY(dev_alloc(&p->d_A, (size_t)p->P * p->P));
+        QC_TRY(dev_alloc(&p->d_Awork, (size_t)p->P * p->P));
+        QC_TRY(dev_alloc(&p->d_g, (size_t)p->P));
+        QC_TRY(dev_alloc(&p->d_r, (size_t)Q));
+    }
+    cublasSetStream(p->blas, p->stream);
+    cusolverDnSetStream(p->solver, p->stream);
+    const double one = 1.0, zero = 0.0;
+    if (!p->normal_valid) {
+        // A = J^T J  (upper triangle), one DSYRK on the column-major (Q x n) Jacobian
+        cublasStatus_t cs = cublasDsyrk(p->blas, CUBLAS_FILL_MODE_UPPER, CUBLAS_OP_T, n, (int)Q, &one, p->d_J, (int)Q,
+                                        &zero, p->d_A, n);
+        QC_CHECK(cs == CUBLAS_STATUS_SUCCESS, QCDMET_E_CUDA, "cublasDsyrk failed: %d", (int)cs);
+        p->normal_valid = true;
+    }
+    QC_CUDA(cudaMemcpyAsync(p->d_r, resid, sizeof(double) * (size_t)Q, cudaMemcpyHostToDevice, p->stream));
+    cublasStatus_t cs = cublasDgemv(p->blas, CUBLAS_OP_T, (int)Q, n, &one, p->d_J, (int)Q, p->d_r, 1, &zero, p->d_g, 1);
+    QC_CHECK(cs == CUBLAS_STATUS_SUCCESS, QCDMET_E_CUDA, "cublasDgemv failed: %d", (int)cs);
+    lm_damp_kernel<<<1024, 256, 0, p->stream>>>(p->d_A, p->d_Awork, n, lambda, 1e-12);
+    QC_CUDA(cudaGetLastError());
+    int lwork = 0;
+    cusolverStatus_t ss = cusolverDnDpotrf_bufferSize(p->solver, CUBLAS_FILL_MODE_UPPER, n, p->d_Awork, n, &lwork);
+    QC_CHECK(ss == CUSOLVER_STATUS_SUCCESS, QCDMET_E_SOLVER, "cusolverDnDpotrf_bufferSize failed: %d", (int)ss);
+    if (lwork > p->potrf_lwork) {
+        cudaFree(p->d_potrf);
+        p->d_potrf = nullptr;
+        p->potrf_lwork = 0;
+        QC_TRY(dev_alloc(&p->d_potrf, (size_t)lwork));
+        p->potrf_lwork = lwork;
+    }
+    ss = cusolverDnDpotrf(p->solver, CUBLAS_FILL_MODE_UPPER, n, p->d_Awork, n, p->d_potrf, p->potrf_lwork, p->d_info);
+    QC_CHECK(ss == CUSOLVER_STATUS_SUCCESS, QCDMET_E_SOLVER, "cusolverDnDpotrf failed: %d", (int)ss);
+    int hinfo = 0;
+    QC_CUDA(cudaMemcpyAsync(&hinfo, p->d_info, sizeof(int), cudaMemcpyDeviceToHost, p->stream));
+    QC_CUDA(cudaStreamSynchronize(p->stream));
+    QC_CHECK(hinfo == 0, QCDMET_E_SOLVER, "damped normal matrix not positive definite (potrf info %d): raise lambda", hinfo);
+    // step = -(A + lambda D)^-1 g   (reuse d_r's head as the right-hand side when it is long enough)
+    double *d_x = p->d_potrf;   // lwork >= n for potrf workspaces; fall back to d_r otherwise
+    if (p->potrf_lwork < n) d_x = p->d_r;
+    QC_CHECK(p->potrf_lwork >= n || Q >= n, QCDMET_E_STATE, "no scratch for the right-hand side");
+    lm_negate_kernel<<<(n + 255) / 256, 256, 0, p->stream>>>(p->d_g, d_x, n);
+    QC_CUDA(cudaGetLastError());
+    ss = cusolverDnDpotrs(p->solver, CUBLAS_FILL_MODE_UPPER, n, 1, p->d_Awork, n, d_x, n, p->d_info);
+    QC_CHECK(ss == CUSOLVER_STATUS_SUCCESS, QCDMET_E_SOLVER, "cusolverDnDpotrs failed: %d", (int)ss);
+    QC_CUDA(cudaMemcpyAsync(step, d_x, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, p->stream));
+    if (info) {
+        // info[0] = max |J^T r|, info[1] = g . step  (the linear model's slope along the step)
+        int imax = 0;
+        cublasIdamax(p->blas, n, p->d_g, 1, &imax);
+        double gmax = 0.0, gdots = 0.0;
+        QC_CUDA(cudaMemcpyAsync(&gmax, p->d_g + (imax - 1), sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+        cublasDdot(p->blas, n, p->d_g, 1, d_x, 1, &gdots);
+        QC_CUDA(cudaStreamSynchronize(p->stream));
+        info[0] = fabs(gmax);
+        info[1] = gdots;
+    }
+    QC_CUDA(cudaStreamSynchronize(p->stream));
     return QCDMET_OK;
 }
 

@@ -58,6 +58,7 @@ class dmet:
             assert self.SCmethod in ('BFGS', 'NONE')
         self.solver = solver
         self.gpu_residual = True      # residual blocks from the device eigensolve shared with the Jacobian
+        self.fit_on_gpu = False       # LSTSQ: Levenberg-Marquardt with the normal equations solved on the device
 
         self.print_u = True
         self.print_rdm = True
@@ -348,12 +349,64 @@ class dmet:
         hessian = 0.5 * (hessian + hessian.T)
         return np.sort(np.linalg.eigvalsh(hessian))
 
+    # ------------------------------------------------------------------ SURVEY.md 8 f-3
+    def leastsq_gpu(self, x0, xtol=1e-13, gtol=1e-13, max_iter=100, verbose=False):
+        """Levenberg-Marquardt minimisation of |rdm_differences(x)|^2 with every O(Q P^2) step on the device:
+        the Jacobian never leaves HBM, J^T J / J^T r come from cuBLAS, the damped normal equations from a
+        cuSOLVER Cholesky (qcdmet_plan_lm_step).  Stands in for scipy.optimize.leastsq / MINPACK lmder
+        (src/dmet.py:631) when the (Q, P) Jacobian is too large to ship to the host every iteration.
+        An accepted trial point costs one eigensolve (shared by its residual and its Jacobian); a rejected
+        one costs one eigensolve and one Cholesky."""
+        from ._lib import QcdmetError
+        row_start, rows, row_idx = self._fragment_rows()
+        x = np.array(x0, dtype=float, copy=True)
+        r = self.rdm_differences(x)
+        cost = float(np.dot(r, r))
+        lam = 1e-3
+        self.lm_iterations = 0
+        for it in range(max_iter):
+            start_grad = time.time()
+            plan = self.helper.response_jacobian_device(self.flat2square(x), row_start, rows=rows, row_idx=row_idx,
+                                                        NOrotation=self.NOrotation)
+            self.time_grad += time.time() - start_grad
+            self.lm_iterations += 1
+            accepted = False
+            for _ in range(40):
+                try:
+                    step, gmax, gdots = plan.lm_step(r, lam)
+                except QcdmetError as exc:
+                    if exc.code != -3:
+                        raise
+                    lam *= 10.0
+                    continue
+                if gmax < gtol:
+                    return x
+                x_new = x + step
+                r_new = self.rdm_differences(x_new)
+                cost_new = float(np.dot(r_new, r_new))
+                if verbose:
+                    print(f"   LM {it}: cost {cost:.6e} -> {cost_new:.6e}  lambda {lam:.1e}  |step| {np.abs(step).max():.2e}")
+                if cost_new <= cost:
+                    small = np.abs(step).max() < xtol * (1.0 + np.abs(x).max())
+                    x, r, cost = x_new, r_new, cost_new
+                    lam = max(lam / 10.0, 1e-15)
+                    accepted = True
+                    if small:
+                        return x
+                    break
+                lam *= 10.0
+            if not accepted:
+                return x
+        return x
+
     # ------------------------------------------------------------------ src/dmet.py:626-636
     def fit_umat(self):
         """The umat solve of one DMET iteration (the SCmethod dispatch of doselfconsistent)."""
         from scipy import optimize
         start_cf = time.time()
-        if self.SCmethod == 'LSTSQ':
+        if self.SCmethod == 'LSTSQ' and self.fit_on_gpu:
+            self.umat = self.flat2square(self.leastsq_gpu(self.square2flat(self.umat)))
+        elif self.SCmethod == 'LSTSQ':
             result = optimize.leastsq(self.rdm_differences, self.square2flat(self.umat),
                                       Dfun=self.rdm_differences_derivative, factor=0.1)
             self.umat = self.flat2square(result[0])

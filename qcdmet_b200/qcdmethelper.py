@@ -181,6 +181,12 @@ class qcdmethelper:
             return jac, plan.dblocks()
         return jac
 
+    def response_jacobian_device(self, umat_loc, row_start, rows=None, row_idx=None, NOrotation=None):
+        """Compute the Jacobian and leave it on the device (for Plan.lm_step); returns the plan."""
+        plan = self._plan_with_orbitals(umat_loc, row_start, rows, row_idx, NOrotation)
+        plan.compute()
+        return plan
+
     def construct1RDM_blocks(self, umat_loc, row_start, rows=None, row_idx=None, NOrotation=None):
         """Fragment blocks R_f (2 C_o C_o^T) R_f^T of the mean-field 1-RDM, flattened like the residual
         (column-major per fragment): the model part of dmet.rdm_differences (src/dmet.py:416-421,432),
