@@ -170,6 +170,13 @@ double qcdmet_plan_flops(qcdmet_plan *plan);               /* FP64 flops execute
  * stream around that launch; synchronises the stream).  ms < 0 if nothing was computed. */
 int  qcdmet_plan_kernel_time_ms(qcdmet_plan *plan, double *ms);
 
+/* Host-only (no device needed): the schedule the DMMA kernel would use for these lists.
+ * info[10] = { eligible, rows-per-fragment variant (4|8), 8-column fragments per warp (8|6|4), components,
+ *              row tiles, symmetric mode possible, list was split (TI), internal columns, block pairs of a
+ *              full-range launch, column tiles }.  rowIdx == NULL means dense projector rows. */
+int qcdmet_schedule_info(int Norb, int Nterms, int numPairs, const int *H1start, const int *H1row,
+                         const int *H1col, int Nfrag, const int *rowStart, const int *rowIdx, int *info);
+
 const char *qcdmet_last_error(void);
 const char *qcdmet_version(void);
 int qcdmet_device_count(void);

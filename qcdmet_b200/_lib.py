@@ -65,6 +65,8 @@ SIGNATURES = {
     "qcdmet_plan_symmetric_used": (ctypes.c_int, [ctypes.c_void_p]),
     "qcdmet_plan_flops": (ctypes.c_double, [ctypes.c_void_p]),
     "qcdmet_plan_kernel_time_ms": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
+    "qcdmet_schedule_info": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
+                                            ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "qcdmet_last_error": (ctypes.c_char_p, []),
     "qcdmet_version": (ctypes.c_char_p, []),
     "qcdmet_device_count": (ctypes.c_int, []),
@@ -111,6 +113,22 @@ def as_i32(a):
 
 def as_f64(a):
     return None if a is None else np.ascontiguousarray(a, dtype=np.float64)
+
+
+def schedule_info(norb, num_pairs, h1start, h1row, h1col, row_start, row_idx=None):
+    """Host-only: how the DMMA kernel would schedule these lists (dict); no device needed."""
+    lib = load()
+    hs, hr, hc, rs, ri = as_i32(h1start), as_i32(h1row), as_i32(h1col), as_i32(row_start), as_i32(row_idx)
+    if hr.size == 0:
+        hr = hc = np.zeros(1, dtype=np.int32)
+    info = np.zeros(10, dtype=np.int32)
+    check(lib.qcdmet_schedule_info(int(norb), len(hs) - 1, int(num_pairs), _ptr(hs), _ptr(hr), _ptr(hc),
+                                   len(rs) - 1, _ptr(rs), _ptr(ri), _ptr(info)))
+    keys = ("eligible", "rows_per_fragment", "nj", "components", "row_tiles", "symmetric", "split", "internal_columns",
+            "block_pairs", "column_tiles")
+    out = dict(zip(keys, (int(v) for v in info)))
+    out["why"] = lib.qcdmet_last_error().decode() if not out["eligible"] else ""
+    return out
 
 
 class Plan:

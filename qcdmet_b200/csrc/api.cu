@@ -224,6 +224,19 @@ extern "C" {
 const char *qcdmet_last_error(void) { return g_err; }
 const char *qcdmet_version(void) { return "qcdmet_b200 0.1 (sm_100a)"; }
 
+int qcdmet_schedule_info(int Norb, int Nterms, int numPairs, const int *H1start, const int *H1row,
+                         const int *H1col, int Nfrag, const int *rowStart, const int *rowIdx, int *info)
+{
+    QC_CHECK(info != nullptr, QCDMET_E_ARG, "info is NULL");
+    static const double dummyR = 0.0;
+    QC_TRY(validate_lists(Norb, Nterms, numPairs, H1start, H1row, H1col, Nfrag, rowStart,
+                          rowIdx ? nullptr : &dummyR, rowIdx));
+    std::string why;
+    dmma_schedule_info(Norb, numPairs, Nterms, Nfrag, H1start, H1row, H1col, rowStart, rowIdx, info, &why);
+    if (!info[0]) set_error("DMMA kernel not eligible: %s", why.c_str());
+    return QCDMET_OK;
+}
+
 int qcdmet_device_count(void)
 {
     int n = 0;

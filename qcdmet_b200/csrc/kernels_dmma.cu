@@ -994,4 +994,24 @@ int launch_jacobian_dmma(DmmaPlanData *d, const JacView &v, cudaStream_t st, int
 
 bool dmma_last_launch_symmetric(const DmmaPlanData *d) { return d && d->launchSym; }
 
+// Host-only description of the schedule the DMMA kernel would use (no device needed): tests and tooling.
+void dmma_schedule_info(int N, int no, int P, int F, const int *h1start, const int *h1row, const int *h1col,
+                        const int *rowStart, const int *rowIdx, int *info, std::string *why)
+{
+    Schedule sc = build_schedule(N, no, P, F, h1start, h1row, h1col, rowStart, rowIdx);
+    const DmmaPlanData &d = sc.d;
+    info[0] = sc.ok ? 1 : 0;
+    info[1] = d.rf; info[2] = d.nj; info[3] = d.nComp; info[4] = d.nTiles;
+    info[5] = d.symOk ? 1 : 0; info[6] = d.expanded ? 1 : 0; info[7] = d.P2;
+    // block pairs the full-range launch would execute (symmetric mode halves them)
+    long long pairs = 0;
+    if (sc.ok)
+        for (int t = 0; t < d.nTiles; ++t)
+            for (int c = 0; c < d.nComp; ++c)
+                if (!(d.symOk && d.compTile[c] < t)) ++pairs;
+    info[8] = (int)std::min<long long>(pairs, 2147483647LL);
+    info[9] = d.nOt;
+    if (why) *why = sc.why;
+}
+
 }  // namespace qcdmet

@@ -70,3 +70,35 @@ def test_fragment_rows_and_residual():
     db.dmetOrbs = wb.dmet_orbs
     rs, rows, idx = db._fragment_rows()
     assert idx is None and np.array_equal(rows, wb.rows) and (rs == wb.row_start).all()
+
+
+def test_dmma_schedule_host_logic():
+    """Schedule builder of the DMMA kernel (host code inside the shared library; no device needed)."""
+    from qcdmet_b200 import _lib
+
+    def info(w):
+        return _lib.schedule_info(w.norb, w.num_pairs, w.h1start, w.h1row, w.h1col, w.row_start, w.row_idx)
+
+    s = info(wl.sweep(4000))                       # the north-star shape
+    assert s["eligible"] and s["symmetric"] and not s["split"]
+    assert (s["rows_per_fragment"], s["nj"]) == (4, 6)          # 96-column tiles: no = 2000 -> 2016
+    assert s["components"] == 1000 and s["row_tiles"] == 125 and s["column_tiles"] == 21
+    assert s["block_pairs"] == 8 * 125 * 126 // 2               # tile(g) >= t: half of 125000 (+ diagonal)
+    s = info(wl.sweep(576))
+    assert s["nj"] == 6 and s["column_tiles"] == 3              # no = 288 = 3 x 96
+    s = info(wl.sweep(160, nterms=333))                         # fragments without perturbations: no mirror mode
+    assert s["eligible"] and not s["symmetric"]
+    s = info(wl.hubbard24(True))                                # TI: one sub-perturbation per cell
+    assert s["eligible"] and s["split"] and s["internal_columns"] == 1440 and s["components"] == 144
+    assert s["row_tiles"] == 1 and not s["symmetric"]
+    s = info(wl.hubbard24(False, fit_imp_bath=True))            # dense 8-row fragments
+    assert s["eligible"] and s["rows_per_fragment"] == 8 and not s["symmetric"] and s["row_tiles"] == 36
+    s = info(wl.hydrogen_like())
+    assert s["eligible"] and s["split"] and s["rows_per_fragment"] == 4
+    s = info(wl.polyyne_like())
+    assert not s["eligible"] and "more than" in s["why"]
+    s = info(wl.sn2_like())
+    assert not s["eligible"]
+    mixed = wl.make_workload("mx", 61, 27, [3, 1, 4, 2, 4, 4, 1, 3, 2, 4, 3, 3, 4])
+    s = info(mixed)
+    assert s["eligible"] and s["symmetric"] and s["components"] == 13 and s["row_tiles"] == 2
