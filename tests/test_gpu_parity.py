@@ -283,6 +283,33 @@ def test_linearity_in_perturbation():
     assert np.abs(jt - summed).max() <= TOL
 
 
+def test_state_errors_of_the_multi_gpu_and_lm_entry_points():
+    w = wl.polyyne_like()                          # general kernel only
+    plan = _lib.Plan(w.norb, w.num_pairs, w.h1start, w.h1row, w.h1col, w.row_start, w.rows, w.row_idx)
+    plan.set_h0(w.h0)
+    with pytest.raises(_lib.QcdmetError) as ei:
+        plan.lm_step(np.zeros(w.nresid), 1.0)      # no Jacobian yet
+    assert ei.value.code == -5
+    plan.export_jacobian()
+    with pytest.raises(_lib.QcdmetError) as ei:
+        plan.attach_peer_pointers(0, [plan.device_ptr(), plan.device_ptr()])    # needs the DMMA kernel
+    assert ei.value.code == -5
+    plan.close()
+    w = wl.sweep(32)
+    plan = _lib.Plan(w.norb, w.num_pairs, w.h1start, w.h1row, w.h1col, w.row_start, w.rows, w.row_idx)
+    plan.set_h0(w.h0)
+    plan.set_columns(0, 10)
+    with pytest.raises(_lib.QcdmetError) as ei:
+        plan.export_jacobian()                     # peer mode works on the full column range
+    assert ei.value.code == -5
+    plan.set_columns(0, w.nterms)
+    plan.export_jacobian()
+    with pytest.raises(_lib.QcdmetError) as ei:
+        plan.attach_peer_pointers(3, [plan.device_ptr()] * 2)
+    assert ei.value.code == -1
+    plan.close()
+
+
 def test_gap_error_is_reported():
     w = wl.sweep(16)
     h0 = np.zeros((16, 16))    # fully degenerate: no HOMO-LUMO gap
