@@ -18,9 +18,15 @@ import argparse
 import json
 import os
 
-# torchrun exports OMP_NUM_THREADS=1 to its children; the reference arm / CPU baseline must use every
-# host core (libgomp reads the variable when it is first loaded, i.e. before `import torch`).
-os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
+# torchrun exports OMP_NUM_THREADS=1 to its children; the reference arm / CPU baseline (rank 0 only) must
+# use every host core (libgomp reads the variable when it is first loaded, i.e. before `import torch`).
+# The other ranks do no heavy host work (rank 0 builds the inputs and broadcasts them): keep them at one
+# thread so that 8 ranks do not oversubscribe the box with spinning BLAS threads.
+_RANK0 = int(os.environ.get("RANK", "0")) == 0
+os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1) if _RANK0 else "1"
+if not _RANK0:
+    os.environ["OPENBLAS_NUM_THREADS"] = "1"
+    os.environ["MKL_NUM_THREADS"] = "1"
 import subprocess
 import sys
 import threading
@@ -175,10 +181,23 @@ def default_sample_cols(norb):
     return max(cols, 1)
 
 
-def make_workload(args):
+def log(msg):
+    if os.environ.get("QCDMET_BENCH_VERBOSE", "1") != "0":
+        print(f"[bench rank {os.environ.get('RANK', '0')} t={time.perf_counter() - _T0:7.1f}s] {msg}", file=sys.stderr, flush=True)
+
+
+_T0 = time.perf_counter()
+
+
+def make_workload(args, placeholder_h0=False):
     from qcdmet_b200 import workloads
     if args.workload == "sweep":
-        w = workloads.sweep(args.norb, args.nterms)
+        if placeholder_h0:      # non-zero ranks: H0 arrives by broadcast from rank 0 (skips the N^3 host set-up)
+            m = 4
+            w = workloads.make_workload(f"sweep_N{args.norb}", args.norb, args.norb // 2, [m] * (args.norb // m),
+                                        nterms=args.nterms, h0=np.zeros((args.norb, args.norb)))
+        else:
+            w = workloads.sweep(args.norb, args.nterms)
         desc = (f"response sweep Norb={w.norb} Nocc={w.num_pairs} P={w.nterms} "
                 f"(4-site fragments, impurity-only rows, Q={w.nresid})")
     elif args.workload.startswith("hubbard24"):
@@ -242,8 +261,11 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
 
-    w, desc = make_workload(args)
+    log("start")
+    bcast = world > 1 and args.workload == "sweep"
+    w, desc = make_workload(args, placeholder_h0=(bcast and rank != 0))
     P, Q = w.nterms, w.nresid
+    log(f"workload built: {desc}")
     # column shard, aligned to whole fragments (10 parameters each) so the ranks do equal work
     shards = sharding.column_shards(P, world, 10)
     lo, hi = shards[rank]
@@ -251,7 +273,24 @@ def run_b200(args):
     assert world == 1 or all(e_ - b_ == per for b_, e_ in shards), \
         "bench shards need P divisible into equal whole-fragment slices"
 
-    e, c = np.linalg.eigh(w.h0)     # setup only: the metric takes (C, e) as given (eigensolve excluded)
+    # setup only: the metric takes (C, e) as given (eigensolve excluded).  Multi-rank: rank 0 diagonalises and
+    # broadcasts, so every rank works on bit-identical orbitals.
+    if bcast:
+        n = w.norb
+        h0_t = torch.from_numpy(np.ascontiguousarray(w.h0)).cuda() if rank == 0 else torch.empty((n, n), dtype=torch.float64, device="cuda")
+        if rank == 0:
+            e, c = np.linalg.eigh(w.h0)
+            c_t, e_t = torch.from_numpy(np.ascontiguousarray(c)).cuda(), torch.from_numpy(e).cuda()
+        else:
+            c_t = torch.empty((n, n), dtype=torch.float64, device="cuda")
+            e_t = torch.empty(n, dtype=torch.float64, device="cuda")
+        for t in (h0_t, c_t, e_t):
+            dist.broadcast(t, 0)
+        w.h0, c, e = h0_t.cpu().numpy(), c_t.cpu().numpy(), e_t.cpu().numpy()
+        del h0_t, c_t, e_t
+    else:
+        e, c = np.linalg.eigh(w.h0)
+    log("orbitals ready")
     plan = _lib.Plan(w.norb, w.num_pairs, w.h1start, w.h1row, w.h1col, w.row_start, w.rows, w.row_idx,
                      device=local)
     plan.set_kernel({"auto": _lib.KERNEL_AUTO, "general": _lib.KERNEL_GENERAL, "dmma": _lib.KERNEL_DMMA}[args.kernel])
@@ -296,8 +335,11 @@ def run_b200(args):
         elif world > 1:
             dist.all_gather_into_tensor(gathered, mine)
 
+    log(f"plan ready (fused={fused})")
     for _ in range(args.warmup):
         step()
+    torch.cuda.synchronize()
+    log("warm-up done")
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -316,6 +358,7 @@ def run_b200(args):
     if world > 1:
         dist.barrier()
     ms_total = ev0.elapsed_time(ev1)
+    log(f"timed region done: {ms_total / args.steps:.2f} ms/step")
     if os.environ.get("QCDMET_BENCH_DEBUG"):
         torch.cuda.synchronize()
         t0 = time.perf_counter(); plan.compute(); t1 = time.perf_counter(); plan.sync(); t2 = time.perf_counter()
