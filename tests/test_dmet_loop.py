@@ -71,16 +71,29 @@ def test_converged_energy_matches_oracle_loop(case):
 @pytest.mark.gpu
 @pytest.mark.parametrize("case", ["chain12_U4_imp_only", "chain8_U2_bath", "chain12_U4_TI_bath"])
 def test_gpu_levenberg_marquardt_reaches_the_same_fit(case):
-    """f-3: the device-side LM (Jacobian never leaves HBM) converges to the same umat and DMET energy as
-    scipy.optimize.leastsq (MINPACK) driving the same residual/Jacobian."""
-    ref = build(case, dmet_mod.dmet)
-    e_ref = ref.doselfconsistent()
-    gpu = build(case, dmet_mod.dmet)
-    gpu.fit_on_gpu = True
-    e_gpu = gpu.doselfconsistent()
-    assert abs(e_gpu - e_ref) <= 1e-7
-    assert np.abs(gpu.umat - ref.umat).max() <= 1e-5
-    assert gpu.lm_iterations >= 1
+    """f-3: for one DMET iteration (fixed impurity 1-RDMs) the device-side LM (Jacobian never leaves HBM)
+    finds the same minimiser as scipy.optimize.leastsq (MINPACK) run to tight tolerances, up to the
+    chemical-potential gauge that src/dmet.py:636 removes."""
+    from scipy import optimize
+    d = build(case, dmet_mod.dmet)
+    d.mu_imp = optimize.newton(d.numeleccostfunction, 0.0)
+    x0 = d.square2flat(d.umat)
+    ref = optimize.leastsq(d.rdm_differences, x0, Dfun=d.rdm_differences_derivative, factor=0.1,
+                           ftol=1e-15, xtol=1e-15, gtol=0.0)[0]
+    got = d.leastsq_gpu(x0)
+    gauge = lambda u: u - np.eye(u.shape[0]) * np.average(np.diag(u))
+    u_ref, u_got = gauge(d.flat2square(ref)), gauge(d.flat2square(got))
+    assert abs(d.costfunction(got) - d.costfunction(ref)) <= 1e-12
+    assert np.abs(u_got - u_ref).max() <= 1e-6
+    assert d.lm_iterations >= 1
+    # whole loop: both optimisers stop the outer iteration at |du| < 1e-5 (src/dmet.py:600), so the
+    # energies agree to that level
+    a = build(case, dmet_mod.dmet)
+    e_ref = a.doselfconsistent()
+    b = build(case, dmet_mod.dmet)
+    b.fit_on_gpu = True
+    e_gpu = b.doselfconsistent()
+    assert abs(e_gpu - e_ref) <= 5e-5
 
 
 @pytest.mark.gpu
