@@ -407,7 +407,10 @@ def run_b200(args):
         out_np = out_pinned.numpy()[:Q * need_out].reshape((Q, need_out), order="F")
 
         def e2e_step():
+            t_a = time.perf_counter()
             plan.set_h0(h0_np)              # H2D + cuSOLVER syevd + panels
+            if os.environ.get("QCDMET_BENCH_DEBUG") and rank == 0:
+                print(f"[e2e] set_h0 (H2D + syevd + panels) {1e3 * (time.perf_counter() - t_a):.1f} ms", file=sys.stderr)
             plan.compute()
             if fused:
                 dist.all_reduce(sync_t)
@@ -449,6 +452,14 @@ def run_b200(args):
         cpu = None
         if not args.no_cpu_baseline:
             cpu = cpu_reference_rate(w, args.cpu_sample_cols or default_sample_cols(w.norb))
+        traffic = alg_bytes = None
+        try:
+            key = (f"sweep_N{w.norb}_P{P}_g{world}" if args.workload == "sweep" else f"{args.workload}_g{world}")
+            tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(key)
+            if tr:
+                traffic, alg_bytes = tr["traffic_bytes"], tr["algorithmic_bytes"]
+        except (OSError, ValueError, KeyError):
+            pass
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
@@ -462,7 +473,8 @@ def run_b200(args):
                                     f"{world} x {per} columns (whole fragments), NCCL all-gather of the slices inside the timed region"),
                        "l2": "256 MB buffer zeroed between steps (L2 flush), inside the timed region"},
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                         "frac": (achieved / peak) if achieved else None, "traffic": None,
+                         "frac": (achieved / peak) if achieved else None, "traffic": traffic,
+                         "algorithmic_bytes": alg_bytes,
                          "kernel_ms": k_ms, "flops_per_launch": flops,
                          "peak_source": peak_src,
                          "algorithmic_equiv_tflops": (w_cols / (k_ms * 1e-3) * 1e-12) if k_ms > 0 else None,
