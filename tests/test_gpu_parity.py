@@ -228,6 +228,75 @@ def test_fused_allgather_ranks_emulated_on_one_device(nranks):
         p.close()
 
 
+def _random_list_workload(seed, symmetric_mode):
+    """Arbitrary CSR perturbations (lib/rhf_response.cc takes any list of unit elements): single
+    unsymmetric elements E_rc, duplicated elements, 3- and 4-element perturbations, all inside 4-site groups."""
+    rng = np.random.default_rng(seed)
+    n, m = 72, 4
+    w = wl.sweep(n)
+    hs, hr, hc = [0], [], []
+    groups = range(n // m) if symmetric_mode else list(range(0, n // m, 2))
+    for g in groups:
+        sites = np.arange(m * g, m * g + m)
+        for _ in range(int(rng.integers(1, 7))):
+            k = int(rng.integers(1, 5))
+            r, c = rng.choice(sites, size=k), rng.choice(sites, size=k)
+            hr += list(map(int, r)); hc += list(map(int, c)); hs.append(len(hr))
+    w.h1start, w.h1row, w.h1col = (np.array(hs, dtype=np.int32), np.array(hr, dtype=np.int32),
+                                   np.array(hc, dtype=np.int32))
+    return w
+
+
+@pytest.mark.parametrize("symmetric_mode", [True, False])
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_arbitrary_element_lists(seed, symmetric_mode):
+    w = _random_list_workload(seed, symmetric_mode)
+    jac, c, e, d, used = run_plan(w, _lib.KERNEL_AUTO)
+    assert used == DMMA and run_plan.last_symmetric == symmetric_mode
+    ref = oracle_jac(w, c, e)
+    assert np.abs(jac - ref).max() <= TOL
+    gen, *_ = run_plan(w, _lib.KERNEL_GENERAL, from_orbitals=(c, e))
+    assert np.abs(gen - ref).max() <= TOL
+    # and through the compat symbol: the full response of the same list against the oracle's
+    lib = _lib.load()
+    n, p = w.norb, w.nterms
+    h0 = np.array(w.h0.reshape(n * n), dtype=np.float64)
+    out = np.ones(n * n * p)
+    assert lib.rhf_response(n, p, w.num_pairs, _lib._ptr(w.h1start), _lib._ptr(w.h1row), _lib._ptr(w.h1col),
+                            _lib._ptr(h0), _lib._ptr(out)) == 0
+    resp, _ = ro.rhf_response(n, p, w.num_pairs, w.h1start, w.h1row, w.h1col, w.h0)
+    assert np.abs(out.reshape(p, n, n) - resp).max() <= TOL
+
+
+def test_degenerate_shapes():
+    """Empty fragments, a fragment-free plan, zero perturbations, and a single perturbation."""
+    w = wl.sweep(24)
+    # fragments with zero rows interleaved
+    rs = np.array([0, 4, 4, 8, 8, 8, 12], dtype=np.int32)
+    plan = _lib.Plan(w.norb, w.num_pairs, w.h1start, w.h1row, w.h1col, rs, None, w.row_idx[:12])
+    plan.set_h0(w.h0)
+    plan.compute()
+    jac, c, e = plan.jacobian(), plan.orbitals(), plan.eigenvalues()
+    ref = ro.jacobian_from_orbitals(c, e, w.num_pairs, w.h1start, w.h1row, w.h1col, rs, None, w.row_idx[:12])
+    assert jac.shape == (48, w.nterms) and np.abs(jac - ref).max() <= TOL
+    plan.close()
+    # no perturbations: nothing to compute, empty Jacobian
+    plan = _lib.Plan(w.norb, w.num_pairs, w.h1start[:1], w.h1row[:0], w.h1col[:0], w.row_start, None, w.row_idx)
+    plan.set_h0(w.h0)
+    plan.compute()
+    assert plan.jacobian().shape == (w.nresid, 0)
+    assert np.abs(plan.dblocks().reshape(-1, 16)[:, [0, 5, 10, 15]].sum() - 2 * w.num_pairs) < 1e-10   # trace of D
+    plan.close()
+    # one perturbation
+    plan = _lib.Plan(w.norb, w.num_pairs, w.h1start[:2], w.h1row[:1], w.h1col[:1], w.row_start, None, w.row_idx)
+    plan.set_h0(w.h0)
+    plan.compute()
+    ref = ro.jacobian_from_orbitals(plan.orbitals(), plan.eigenvalues(), w.num_pairs, w.h1start[:2], w.h1row[:1],
+                                    w.h1col[:1], w.row_start, None, w.row_idx)
+    assert np.abs(plan.jacobian() - ref).max() <= TOL
+    plan.close()
+
+
 def test_sn2_like_sampled_columns():
     w = wl.sn2_like()
     e, c = ro.eigh_sorted(w.h0)
