@@ -238,10 +238,14 @@ def _random_list_workload(seed, symmetric_mode):
     groups = range(n // m) if symmetric_mode else list(range(0, n // m, 2))
     for g in groups:
         sites = np.arange(m * g, m * g + m)
+        # a ring through the four sites: the group is one connected component
+        hr += [int(s) for s in sites]; hc += [int(s) for s in np.roll(sites, -1)]; hs.append(len(hr))
         for _ in range(int(rng.integers(1, 7))):
             k = int(rng.integers(1, 5))
-            r, c = rng.choice(sites, size=k), rng.choice(sites, size=k)
-            hr += list(map(int, r)); hc += list(map(int, c)); hs.append(len(hr))
+            chain = rng.choice(sites, size=k + 1)            # connected chain r0->r1->...: never split
+            if rng.random() < 0.3:
+                chain[1:] = chain[1]                         # duplicated / diagonal elements
+            hr += list(map(int, chain[:-1])); hc += list(map(int, chain[1:])); hs.append(len(hr))
     w.h1start, w.h1row, w.h1col = (np.array(hs, dtype=np.int32), np.array(hr, dtype=np.int32),
                                    np.array(hc, dtype=np.int32))
     return w
