@@ -40,6 +40,8 @@ struct qcdmet_plan {
     double *d_R = nullptr;
     double *d_C = nullptr, *d_e = nullptr;
     double *d_CoT = nullptr, *d_CvT = nullptr, *d_PO = nullptr, *d_PV = nullptr;
+    double *d_W = nullptr;              // [nv][ldo] denominators for the general kernel (built on first use)
+    bool w_valid = false;
     double *d_J = nullptr;          // where the Jacobian slice is written (own buffer or external)
     double *d_J_own = nullptr;
     size_t J_capacity = 0;          // capacity of d_J_own
@@ -108,6 +110,7 @@ JacView make_view(const qcdmet_plan *p)
     v.h1start = p->d_h1start; v.h1row = p->d_h1row; v.h1col = p->d_h1col;
     v.rowStart = p->d_rowStart; v.rowFrag = p->d_rowFrag; v.qoff = p->d_qoff;
     v.CoT = p->d_CoT; v.CvT = p->d_CvT; v.PO = p->d_PO; v.PV = p->d_PV; v.e = p->d_e;
+    v.W = p->d_W;
     v.J = p->d_J;
     return v;
 }
@@ -202,6 +205,7 @@ int build_panels(qcdmet_plan *p)
              "HOMO-LUMO gap %.3e is not positive: the RHF response is undefined", eg[1] - eg[0]);
     p->have_orbitals = true;
     p->have_jac = false;
+    p->w_valid = false;
     return QCDMET_OK;
 }
 
@@ -337,7 +341,7 @@ int qcdmet_plan_destroy(qcdmet_plan *p)
     cudaFree(p->d_h1start); cudaFree(p->d_h1row); cudaFree(p->d_h1col);
     cudaFree(p->d_rowStart); cudaFree(p->d_rowFrag); cudaFree(p->d_rowIdx); cudaFree(p->d_qoff);
     cudaFree(p->d_R); cudaFree(p->d_C); cudaFree(p->d_e);
-    cudaFree(p->d_CoT); cudaFree(p->d_CvT); cudaFree(p->d_PO); cudaFree(p->d_PV);
+    cudaFree(p->d_CoT); cudaFree(p->d_CvT); cudaFree(p->d_PO); cudaFree(p->d_PV); cudaFree(p->d_W);
     cudaFree(p->d_A); cudaFree(p->d_Awork); cudaFree(p->d_g); cudaFree(p->d_r); cudaFree(p->d_potrf);
     cudaFree(p->d_J_own); cudaFree(p->d_D); cudaFree(p->d_work); cudaFree(p->d_info);
     if (p->ev0) cudaEventDestroy(p->ev0);
@@ -454,6 +458,12 @@ int qcdmet_plan_compute(qcdmet_plan *p)
         p->symmetric_used = dmma_last_launch_symmetric(p->dmma);
         p->kernel_used = QCDMET_KERNEL_DMMA;
     } else {
+        if (!p->d_W) QC_TRY(dev_alloc(&p->d_W, (size_t)p->nv * p->ldo));
+        if (!p->w_valid) {
+            QC_TRY(launch_build_w(p->d_e, p->no, p->nv, p->ldo, p->d_W, p->stream));
+            p->w_valid = true;
+        }
+        v.W = p->d_W;
         QC_TRY(launch_jacobian_general(v, p->stream, &p->launches, &p->flops, p->ev0, p->ev1));
         p->flops = count_flops_general(p);
         p->kernel_used = QCDMET_KERNEL_GENERAL;

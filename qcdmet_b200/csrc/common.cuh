@@ -61,6 +61,7 @@ struct JacView {
     const int *rowFrag;        // [S] fragment of each row
     const long long *qoff;     // [F+1] residual offset of each fragment
     const double *CoT, *CvT, *PO, *PV, *e;
+    const double *W;           // [nv][ldo] energy denominators 1/(e_o - e_v) (general kernel)
     double *J;                 // [Q * ncols]
 };
 
@@ -71,6 +72,7 @@ int launch_gather_rows(const double *src, int ld, const int *rowIdx, int S, doub
                        cudaStream_t st);
 int launch_dblocks(const JacView &v, double *D, cudaStream_t st);
 int launch_one_rdm(const double *CoT, int ldo, int N, int no, double *D, cudaStream_t st);
+int launch_build_w(const double *e, int no, int nv, int ldo, double *W, cudaStream_t st);
 
 // kernels_general.cu
 // ev0/ev1 are recorded on `st` around the dominant kernel (first column chunk).

@@ -3,10 +3,11 @@
 // Correct for arbitrary CSR perturbations (nnz_p >= 1, translation-invariant lists included),
 // arbitrary fragment row lists and dense projector rows (fitImpBath).  Used for the shapes the
 // site-factorised DMMA kernel does not cover and as the on-device cross-check of that kernel at
-// sizes the CPU oracle cannot reach.  Plain FFMA-pipe FP64, shared-memory tiled.
+// sizes the CPU oracle cannot reach.  Plain FP64-FMA-pipe kernel (on B200 the DFMA and DMMA rates are the
+// same pipe: 33.7 vs 36.9 TFLOP/s measured), shared-memory tiled, 64 x 64 output tile, 4 x 4 per thread.
 //
 // Per column p (lib/rhf_response.cc:82-108 restricted to the fragment rows):
-//   Z_p[v,o] = (sum_{(r,c) in H1_p} Cv[r,v] Co[c,o]) / (e_o - e_v)
+//   Z_p[v,o] = (sum_{(r,c) in H1_p} Cv[r,v] Co[c,o]) * W[v,o],   W[v,o] = 1/(e_o - e_v) precomputed once
 //   Y_p[a,o] = sum_v PV[a,v] Z_p[v,o]
 //   G_p[a,b] = sum_o Y_p[a,o] PO[b,o]          for b in the fragment of row a
 //   J[(f;a,b),p] = 2 (G_p[a,b] + G_p[b,a])
@@ -15,19 +16,22 @@
 namespace qcdmet {
 
 namespace {
-constexpr int TA = 32;   // fragment rows per CTA
+constexpr int TA = 64;   // fragment rows per CTA
 constexpr int TO = 64;   // occupied orbitals per tile
 constexpr int TV = 32;   // virtual orbitals per chunk
-constexpr int NT = 256;  // threads per CTA
+constexpr int NT = 256;  // threads per CTA: 16 x 16, each a 4 x 4 register tile of Y
+constexpr int PVS_LD = TA + 2, ZS_LD = TO + 2, YS_LD = TO + 1;
+constexpr int GEN_SMEM = (TV * PVS_LD + TV * ZS_LD + TA * YS_LD) * 8 + (TA + 1) * 4;
 }
 
 __global__ void __launch_bounds__(NT)
 jac_general_kernel(JacView v, double *__restrict__ G)
 {
-    __shared__ double PVs[TV][TA + 1];   // PVs[vv][a]
-    __shared__ double Zs[TV][TO];        // Zs[vv][o]
-    __shared__ double Ys[TA][TO + 1];    // Ys[a][o]
-    __shared__ int pairOff[TA + 1];
+    extern __shared__ __align__(16) unsigned char gsm[];
+    double *PVs = reinterpret_cast<double *>(gsm);          // PVs[vv][a]
+    double *Zs = PVs + TV * PVS_LD;                          // Zs[vv][o]
+    double *Ys = Zs + TV * ZS_LD;                            // Ys[a][o]
+    int *pairOff = reinterpret_cast<int *>(Ys + TA * YS_LD);
 
     const int tid = threadIdx.x;
     const int a0 = blockIdx.x * TA;
@@ -48,27 +52,26 @@ jac_general_kernel(JacView v, double *__restrict__ G)
     __syncthreads();
     const int npairs = pairOff[TA];
 
-    const int ty = tid / 16, tx = tid % 16;    // Y micro-tile: rows {ty, ty+16}, cols {tx+16j}
+    const int ty = tid / 16, tx = tid % 16;    // Y register tile: rows 4 ty .. 4 ty + 3, cols 4 tx .. 4 tx + 3
     const int zo = tid % TO, zv0 = tid / TO;   // Z build: column zo, rows zv0 + 4j
 
     for (int o0 = 0; o0 < v.no; o0 += TO) {
-        double acc[2][4];
+        double acc[4][4];
 #pragma unroll
-        for (int i = 0; i < 2; ++i)
+        for (int i = 0; i < 4; ++i)
 #pragma unroll
             for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
 
         const int og = o0 + zo;
-        const double eo = (og < v.no) ? v.e[og] : 0.0;
 
         for (int v0 = 0; v0 < v.nv; v0 += TV) {
             // stage PV[a-tile][v-chunk]
             for (int t = tid; t < TA * TV; t += NT) {
                 int a = t / TV, vv = t % TV;
                 int ga = a0 + a, gv = v0 + vv;
-                PVs[vv][a] = (ga < v.S && gv < v.nv) ? v.PV[(size_t)ga * v.ldv + gv] : 0.0;
+                PVs[vv * PVS_LD + a] = (ga < v.S && gv < v.nv) ? v.PV[(size_t)ga * v.ldv + gv] : 0.0;
             }
-            // build Z tile
+            // build the Z tile from the CSR elements of the perturbation
 #pragma unroll
             for (int j = 0; j < TV / (NT / TO); ++j) {
                 int vv = zv0 + (NT / TO) * j;
@@ -79,28 +82,29 @@ jac_general_kernel(JacView v, double *__restrict__ G)
                     for (int el = eBeg; el < eEnd; ++el)
                         s += v.CvT[(size_t)v.h1row[el] * v.ldv + gv] *
                              v.CoT[(size_t)v.h1col[el] * v.ldo + og];
-                    z = s / (eo - v.e[v.no + gv]);
+                    z = s * v.W[(size_t)gv * v.ldo + og];
                 }
-                Zs[vv][zo] = z;
+                Zs[vv * ZS_LD + zo] = z;
             }
             __syncthreads();
 #pragma unroll 8
             for (int vv = 0; vv < TV; ++vv) {
-                double pa0 = PVs[vv][ty], pa1 = PVs[vv][ty + 16];
+                const double2 pa = *reinterpret_cast<const double2 *>(PVs + vv * PVS_LD + 4 * ty);
+                const double2 pb = *reinterpret_cast<const double2 *>(PVs + vv * PVS_LD + 4 * ty + 2);
+                const double2 za = *reinterpret_cast<const double2 *>(Zs + vv * ZS_LD + 4 * tx);
+                const double2 zb = *reinterpret_cast<const double2 *>(Zs + vv * ZS_LD + 4 * tx + 2);
+                const double pr[4] = {pa.x, pa.y, pb.x, pb.y}, zc[4] = {za.x, za.y, zb.x, zb.y};
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    double z = Zs[vv][tx + 16 * j];
-                    acc[0][j] += pa0 * z;
-                    acc[1][j] += pa1 * z;
-                }
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[i][j] += pr[i] * zc[j];
             }
             __syncthreads();
         }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            Ys[ty][tx + 16 * j] = acc[0][j];
-            Ys[ty + 16][tx + 16 * j] = acc[1][j];
-        }
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) Ys[(4 * ty + i) * YS_LD + 4 * tx + j] = acc[i][j];
         __syncthreads();
         // epilogue: contract with the occupied panel rows of the same fragment
         const int ow = min(TO, v.no - o0);
@@ -112,7 +116,7 @@ jac_general_kernel(JacView v, double *__restrict__ G)
             const int bl = t - pairOff[a];
             const double *pb = v.PO + (size_t)(rs + bl) * v.ldo + o0;
             double s = 0.0;
-            for (int oo = 0; oo < ow; ++oo) s += Ys[a][oo] * pb[oo];
+            for (int oo = 0; oo < ow; ++oo) s += Ys[a * YS_LD + oo] * pb[oo];
             double *dst = Gp + v.qoff[f] + (ga - rs) + (long long)rf * bl;
             if (o0 == 0) *dst = s; else *dst += s;
         }
@@ -147,6 +151,11 @@ int launch_jacobian_general(const JacView &v, cudaStream_t st, int *launches, do
     *flops = 0.0;
     if (ncols <= 0 || v.S == 0) return QCDMET_OK;
     const int atiles = (v.S + TA - 1) / TA;
+    static bool attr = false;
+    if (!attr) {
+        QC_CUDA(cudaFuncSetAttribute(jac_general_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEN_SMEM));
+        attr = true;
+    }
     // gridDim.y is limited to 65535: chunk the columns
     for (int c0 = 0; c0 < ncols; c0 += 32768) {
         const int nc = min(32768, ncols - c0);
@@ -155,7 +164,7 @@ int launch_jacobian_general(const JacView &v, cudaStream_t st, int *launches, do
         w.colEnd = w.colBegin + nc;
         double *G = v.J + (size_t)v.Q * c0;
         if (c0 == 0 && ev0) QC_CUDA(cudaEventRecord(ev0, st));
-        jac_general_kernel<<<dim3(atiles, nc), NT, 0, st>>>(w, G);
+        jac_general_kernel<<<dim3(atiles, nc), NT, GEN_SMEM, st>>>(w, G);
         QC_CUDA(cudaGetLastError());
         if (c0 == 0 && ev1) QC_CUDA(cudaEventRecord(ev1, st));
         const long long qb = (v.Q + 255) / 256;

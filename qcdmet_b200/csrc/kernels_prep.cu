@@ -87,6 +87,23 @@ int launch_dblocks(const JacView &v, double *D, cudaStream_t st)
     return QCDMET_OK;
 }
 
+// W[v][o] = 1 / (e_o - e_v)   (lib/rhf_response.cc:66-71 with the sign folded in), zero in the padding
+__global__ void build_w_kernel(const double *__restrict__ e, int no, int nv, int ldo, double *__restrict__ W)
+{
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)nv * ldo) return;
+    const int v = (int)(idx / ldo), o = (int)(idx % ldo);
+    W[idx] = (o < no) ? 1.0 / (e[o] - e[no + v]) : 0.0;
+}
+
+int launch_build_w(const double *e, int no, int nv, int ldo, double *W, cudaStream_t st)
+{
+    const size_t total = (size_t)nv * ldo;
+    build_w_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(e, no, nv, ldo, W);
+    QC_CUDA(cudaGetLastError());
+    return QCDMET_OK;
+}
+
 // Full 1-RDM D[i + N*j] = 2 sum_o CoT[i][o] CoT[j][o]   (compat: lib/rhf_response.cc:57-64)
 __global__ void one_rdm_kernel(const double *__restrict__ CoT, int ldo, int N, int no,
                                double *__restrict__ D)
