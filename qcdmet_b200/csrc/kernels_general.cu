@@ -151,11 +151,8 @@ int launch_jacobian_general(const JacView &v, cudaStream_t st, int *launches, do
     *flops = 0.0;
     if (ncols <= 0 || v.S == 0) return QCDMET_OK;
     const int atiles = (v.S + TA - 1) / TA;
-    static bool attr = false;
-    if (!attr) {
-        QC_CUDA(cudaFuncSetAttribute(jac_general_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEN_SMEM));
-        attr = true;
-    }
+    // per device (function attributes live in the context of the current device): set on every launch
+    QC_CUDA(cudaFuncSetAttribute(jac_general_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEN_SMEM));
     // gridDim.y is limited to 65535: chunk the columns
     for (int c0 = 0; c0 < ncols; c0 += 32768) {
         const int nc = min(32768, ncols - c0);
