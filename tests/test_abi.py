@@ -62,3 +62,14 @@ def test_no_cpu_fallback_without_device():
                           _lib._ptr(w.h1col), _lib._ptr(h0), _lib._ptr(out))
     assert rc == -2
     assert (out == 1.0).all() and np.array_equal(h0, w.h0.reshape(-1))   # nothing written
+
+
+def test_missing_library_fails_loudly():
+    """No silent fallback: a missing libqcdmet_b200.so is an OSError at load time."""
+    import subprocess
+    import sys
+    code = ("import os, sys; sys.path.insert(0, %r); os.environ['QCDMET_B200_LIB'] = '/nonexistent/libqcdmet_b200.so'; "
+            "from qcdmet_b200 import _lib\n"
+            "try:\n    _lib.load()\nexcept OSError as e:\n    print('OSError', 'no CPU fallback' in str(e))\n" % ROOT)
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+    assert out.stdout.strip() == "OSError True", out.stderr[-500:]

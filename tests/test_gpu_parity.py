@@ -339,6 +339,49 @@ def test_invariants_large():
     assert np.abs(sq - sq.T).max() < 1e-11
 
 
+def test_north_star_size_properties():
+    """The full target: Norb = 4000, 10^4 perturbations, Q = 16000 (1.28 GB Jacobian).  The oracle cannot
+    produce it in seconds, so: size-independent properties on the whole matrix, the second (general) kernel
+    on a slice of columns, and the oracle on two columns."""
+    w = wl.sweep(4000)
+    assert (w.nterms, w.nresid) == (10000, 16000)
+    plan = _lib.Plan(w.norb, w.num_pairs, w.h1start, w.h1row, w.h1col, w.row_start, w.rows, w.row_idx)
+    plan.set_h0(w.h0)
+    plan.compute()
+    jac = plan.jacobian()
+    assert plan.kernel_used == DMMA and plan.symmetric_used
+    c, e = plan.orbitals(), plan.eigenvalues()
+    blocks = jac.reshape(4, 4, 1000, 10000, order="F")
+    for lo in range(0, 10000, 2500):                 # exact block symmetry, chunked to bound host memory
+        b = blocks[:, :, :, lo:lo + 2500]
+        assert np.array_equal(b, b.transpose(1, 0, 2, 3))
+    tr = np.einsum("aafp->p", blocks)
+    assert np.abs(tr).max() < 1e-10                  # dD_p is traceless (fragments tile every site)
+    # Gram symmetry of the response function on a random sample of (row pair, column pair) entries
+    rng = np.random.default_rng(0)
+    pair_row = np.array([16 * f + r + 4 * cc for f in range(1000) for r in range(4) for cc in range(r, 4)])
+    scale = np.array([1.0 if r == cc else 0.5 for f in range(1000) for r in range(4) for cc in range(r, 4)])
+    i, j = rng.integers(0, 10000, 4000), rng.integers(0, 10000, 4000)
+    assert np.abs(jac[pair_row[i], j] * scale[j] - jac[pair_row[j], i] * scale[i]).max() < 1e-11
+    # sum rule: D stays idempotent, D dD + dD D = 2 dD  =>  for the diagonal blocks sum_b ... (checked on D itself)
+    d = plan.dblocks().reshape(4, 4, 1000, order="F")
+    assert abs(np.einsum("aaf->", d) - 2 * w.num_pairs) < 1e-9
+    # the independent general kernel on 24 columns spread over the matrix
+    plan.set_kernel(_lib.KERNEL_GENERAL)
+    for lo in (0, 4990, 9992):
+        plan.set_columns(lo, lo + 8)
+        plan.compute()
+        part = plan.jacobian()
+        assert np.abs(part - jac[:, lo:lo + 8]).max() <= TOL
+    plan.close()
+    # the oracle on two columns (a diagonal and a pair perturbation of a fragment in the middle)
+    s = w.h1start
+    for p in (5000, 5001):
+        ref = ro.jacobian_from_orbitals(c, e, w.num_pairs, s[p:p + 2] - s[p], w.h1row[s[p]:s[p + 1]],
+                                        w.h1col[s[p]:s[p + 1]], w.row_start, None, w.row_idx)
+        assert np.abs(ref[:, 0] - jac[:, p]).max() <= TOL
+
+
 def test_linearity_in_perturbation():
     """dD is linear in H1: a TI perturbation equals the sum of its per-cell perturbations."""
     l = 8
