@@ -8,17 +8,19 @@
 // M_r is shared by every perturbation that has an element in row r, so the dominant GEMM runs
 // once per *site* (N of them) instead of once per perturbation (P = N(m+1)/2): 2 S nv no flop per
 // site.  This replaces lib/rhf_response.cc:82-108 + src/dmet.py:496-520 for perturbation lists
-// whose connected components (perturbations sharing sites) have <= 4 sites and fragments of <= 4
-// rows -- the non-translation-invariant 2x2 / 4-site DMET shape of the north-star workload.
+// whose connected components (perturbations sharing sites) have <= 4 sites and fragments of <= 8
+// rows: DMET fits with impurities of <= 4 orbitals, impurity-only or impurity+bath rows.
+// Translation-invariant lists (one element per cell) are split into per-cell sub-perturbations
+// first and the sub-columns summed afterwards (dD is linear in H1).
 //
 // One CTA = (component g of <= 4 sites) x (a-tile of 32 fragment rows): a 128 x no output panel
-// M[(r,a), o], produced 128 columns at a time:
-//   * B operand: W, pre-tiled in HBM in DMMA fragment order, one 16 KB TMA bulk copy per stage
+// M[(r,a), o], produced BN = 128 / 96 / 64 columns at a time (Cfg<RF, NJ>, BN = 16 NJ):
+//   * B operand: W, pre-tiled in HBM in DMMA fragment order, one TMA bulk copy per stage (16 KB at BN=128)
 //   * A operand: (PV[a,:] * Cv[r,:]) built in registers from two TMA-staged panels (4 KB + 512 B)
-//   * 8 consumer warps (4 sites x 2 column halves), warp tile 32 x 64, 32 DMMA.8x8x4 per k4 step,
+//   * 8 consumer warps (4 sites x 2 column halves), warp tile 32 x BN/2, 4 NJ DMMA.8x8x4 per k4 step,
 //     accumulators in registers (FP64 has no tcgen05/TMEM path: tcgen05.mma has no f64 kind)
 //   * 1 producer warp, 4-stage mbarrier full/empty pipeline (cp.async.bulk -> UBLKCP)
-//   * epilogue per 128-column tile: accumulators x Co[c,o] x PO[b,o] on the FP64 pipe (operands
+//   * epilogue per column tile: accumulators x Co[c,o] x PO[b,o] on the FP64 pipe (operands
 //     TMA-prefetched by the producer, each warp runs its epilogue independently so the other warp of
 //     the SM sub-partition keeps the DMMA pipe busy), warp-shuffle reduction over the 4 lanes of a row,
 //     running sums in shared memory; after the last tile the CTA assembles G_p, symmetrises, and stores
@@ -27,6 +29,8 @@
 //     (impurity-only rows, the standard non-TI DMET fit) M_r[a,o] = M_a[r,o], so only block pairs
 //     (g, t) with tile(g) >= t are computed and each CTA also stores the mirrored patch
 //     J[rows of g, columns of the blocks in t] from the same N values: half the flops, exact.
+//   * multi-GPU: a rank executes a contiguous slice of the block-pair list and stores every J element
+//     into all ranks' buffers (CUDA-IPC-mapped peers, NVLink): the all-gather is fused into the kernel.
 #include "common.cuh"
 #include <algorithm>
 #include <cstdint>
