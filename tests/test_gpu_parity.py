@@ -382,6 +382,19 @@ def test_north_star_size_properties():
         assert np.abs(ref[:, 0] - jac[:, p]).max() <= TOL
 
 
+def test_bitwise_reproducible():
+    """No atomics, fixed summation order: repeated runs (and a fresh plan) give identical bits."""
+    for w in (wl.sweep(200), wl.hubbard24(True, l=8), wl.polyyne_like()):
+        e, c = ro.eigh_sorted(w.h0)
+        a, *_ = run_plan(w, _lib.KERNEL_AUTO, from_orbitals=(c, e))
+        plan = _lib.Plan(w.norb, w.num_pairs, w.h1start, w.h1row, w.h1col, w.row_start, w.rows, w.row_idx)
+        plan.set_orbitals(c, e)
+        for _ in range(3):
+            plan.compute()
+            assert np.array_equal(plan.jacobian(), a)
+        plan.close()
+
+
 def test_linearity_in_perturbation():
     """dD is linear in H1: a TI perturbation equals the sum of its per-cell perturbations."""
     l = 8
