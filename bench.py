@@ -305,6 +305,8 @@ def run_b200(args):
         # mode) is split evenly over the ranks.  Needs peer mapping; otherwise fall back to column shards +
         # NCCL all-gather.
         try:
+            if os.environ.get("QCDMET_BENCH_NO_FUSED"):
+                raise _lib.QcdmetError(0, "fused all-gather disabled by QCDMET_BENCH_NO_FUSED")
             plan.set_columns(0, P)
             handles = [None] * world
             dist.all_gather_object(handles, plan.export_jacobian())
