@@ -303,6 +303,38 @@ class dmet:
         self.time_func += time.time() - start_func
         return errors
 
+    # ------------------------------------------------------------------ src/dmet.py:441-475
+    def rdm_differences_bis(self, newumatflat):
+        """Masked (upper-triangle) impurity-block residual of the constrained-optimisation variant
+        (use_constrained_opt=True).  Host numpy as in the reference: this variant never calls the response."""
+        start_func = time.time()
+        newumatsquare_loc = self.flat2square(newumatflat)
+        OneRDM_loc = self.helper.construct1RDM_loc(self.doSCF, newumatsquare_loc)
+        pieces = []
+        jumpc = 0
+        for count in range(len(self.imp_size)):
+            m = int(self.imp_size[count])
+            idx = np.flatnonzero(self.impClust[count])
+            theerror = (OneRDM_loc[:, idx])[idx, :] - self.imp_1RDM[count][:m, :m]
+            mask_t = self.mask[jumpc:jumpc + m, jumpc:jumpc + m]
+            pieces.append(theerror[mask_t])          # boolean-mask order (row-major), as src/dmet.py:470
+            jumpc += m
+        self.time_func += time.time() - start_func
+        return np.concatenate(pieces)
+
+    # ------------------------------------------------------------------ src/dmet.py:365-379,390-393
+    def alt_costfunction(self, newumatflat):
+        newumatsquare_loc = self.flat2square(newumatflat)
+        OneRDM_loc = self.helper.construct1RDM_loc(self.doSCF, newumatsquare_loc)
+        errors_sq = self.flat2square(self.rdm_differences_bis(newumatflat))
+        base = self.ints.loc_oei() if self.minFunc == 'OEI' else self.ints.loc_rhf_fock()
+        e_fun = np.trace(np.dot(base, OneRDM_loc))
+        e_cstr = np.sum(newumatsquare_loc * errors_sq)
+        return -e_fun - e_cstr
+
+    def alt_costfunction_derivative(self, newumatflat):
+        return -self.rdm_differences_bis(newumatflat)
+
     # ------------------------------------------------------------------ src/dmet.py:477-525
     def rdm_differences_derivative(self, newumatflat):
         """(Q, P) Jacobian of rdm_differences.  One fused GPU call instead of the N x N x P
@@ -404,7 +436,11 @@ class dmet:
         """The umat solve of one DMET iteration (the SCmethod dispatch of doselfconsistent)."""
         from scipy import optimize
         start_cf = time.time()
-        if self.SCmethod == 'LSTSQ' and self.fit_on_gpu:
+        if self.altcostfunc and self.SCmethod == 'BFGS':        # src/dmet.py:627-629
+            result = optimize.minimize(self.alt_costfunction, self.square2flat(self.umat),
+                                       jac=self.alt_costfunction_derivative, options={'disp': False})
+            self.umat = self.flat2square(result.x)
+        elif self.SCmethod == 'LSTSQ' and self.fit_on_gpu:
             self.umat = self.flat2square(self.leastsq_gpu(self.square2flat(self.umat)))
         elif self.SCmethod == 'LSTSQ':
             result = optimize.leastsq(self.rdm_differences, self.square2flat(self.umat),

@@ -102,3 +102,26 @@ def test_dmma_schedule_host_logic():
     mixed = wl.make_workload("mx", 61, 27, [3, 1, 4, 2, 4, 4, 1, 3, 2, 4, 3, 3, 4])
     s = info(mixed)
     assert s["eligible"] and s["symmetric"] and s["components"] == 13 and s["row_tiles"] == 2
+
+
+def test_constrained_optimisation_variant():
+    """use_constrained_opt=True (src/dmet.py:365-379,390-393,441-475): host-only Lagrangian variant.  The
+    reference states its gradient -errors "gives correct verify_gradient results": check by finite differences."""
+    w = wl.make_workload("alt", 16, 6, [3, 4, 2])
+    d = dmet_mod.dmet(Ints(w.h0, 12), w.imp_clust, False, SCmethod='BFGS', fitImpBath=False, use_constrained_opt=True)
+    assert d.minFunc == 'FOCK_INIT' and d.helper.altcf
+    rng = np.random.default_rng(4)
+    d.imp_1RDM = [(lambda a: a + a.T)(rng.standard_normal((2 * m, 2 * m))) for m in (3, 4, 2)]
+    x = rng.standard_normal(d.helper.Nterms) * 0.05
+    r = d.rdm_differences_bis(x)
+    assert r.shape == x.shape
+    g = d.alt_costfunction_derivative(x)
+    assert np.array_equal(g, -r)
+    eps = 1e-6
+    for k in (0, 5, len(x) - 1):
+        dx = np.zeros_like(x)
+        dx[k] = eps
+        fd = (d.alt_costfunction(x + dx) - d.alt_costfunction(x - dx)) / (2 * eps)
+        # off-diagonal parameters enter umat twice (u_ij and u_ji): the reference's gradient is per parameter
+        scale = 1.0 if np.flatnonzero(d.mask.ravel())[k] % 17 == 0 else 2.0
+        assert abs(fd - scale * g[k]) < 1e-6 * max(1.0, abs(fd))
