@@ -160,6 +160,10 @@ int qcdmet_plan_get_full_response(qcdmet_plan *plan, double *rdm_deriv, double *
  * QCDMET_E_SOLVER if the damped matrix is not positive definite (raise lambda). */
 int qcdmet_plan_lm_step(qcdmet_plan *plan, const double *resid, double lambda, double *step, double *info);
 
+/* grad = 2 J^T resid from the device-resident Jacobian (the BFGS gradient of src/dmet.py:381-388);
+ * resid: Q doubles (host), grad: ncols doubles (host). */
+int qcdmet_plan_gradient(qcdmet_plan *plan, const double *resid, double *grad);
+
 /* Introspection (bench / tests). */
 long long qcdmet_plan_num_residuals(qcdmet_plan *plan);    /* Q                                  */
 int  qcdmet_plan_kernel_used(qcdmet_plan *plan);           /* QCDMET_KERNEL_GENERAL or _DMMA      */

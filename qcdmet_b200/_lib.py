@@ -59,6 +59,7 @@ SIGNATURES = {
     "qcdmet_plan_get_full_response": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "qcdmet_plan_lm_step": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_double, ctypes.c_void_p,
                                            ctypes.c_void_p]),
+    "qcdmet_plan_gradient": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "qcdmet_plan_num_residuals": (ctypes.c_longlong, [ctypes.c_void_p]),
     "qcdmet_plan_kernel_used": (ctypes.c_int, [ctypes.c_void_p]),
     "qcdmet_plan_launches": (ctypes.c_int, [ctypes.c_void_p]),
@@ -227,6 +228,14 @@ class Plan:
         info = np.zeros(2, dtype=np.float64)
         check(self.lib.qcdmet_plan_lm_step(self.handle, _ptr(resid), float(lam), _ptr(step), _ptr(info)))
         return step, float(info[0]), float(info[1])
+
+    def gradient(self, resid):
+        """2 J^T resid from the device-resident Jacobian."""
+        resid = as_f64(resid)
+        assert resid.size == self.nresid
+        grad = np.empty(self.col_end - self.col_begin, dtype=np.float64)
+        check(self.lib.qcdmet_plan_gradient(self.handle, _ptr(resid), _ptr(grad)))
+        return grad
 
     def dblocks(self):
         out = np.empty(self.nresid, dtype=np.float64)

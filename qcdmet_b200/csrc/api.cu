@@ -507,9 +507,9 @@ extern "C" int qcdmet_plan_lm_step(qcdmet_plan *p, const double *resid, double l
     if (!p->d_A) {
         QC_TRY(dev_alloc(&p->d_A, (size_t)p->P * p->P));
         QC_TRY(dev_alloc(&p->d_Awork, (size_t)p->P * p->P));
-        QC_TRY(dev_alloc(&p->d_g, (size_t)p->P));
-        QC_TRY(dev_alloc(&p->d_r, (size_t)Q));
     }
+    if (!p->d_g) QC_TRY(dev_alloc(&p->d_g, (size_t)p->P));
+    if (!p->d_r) QC_TRY(dev_alloc(&p->d_r, (size_t)Q));
     cublasSetStream(p->blas, p->stream);
     cusolverDnSetStream(p->solver, p->stream);
     const double one = 1.0, zero = 0.0;
@@ -561,6 +561,27 @@ extern "C" int qcdmet_plan_lm_step(qcdmet_plan *p, const double *resid, double l
         info[0] = fabs(gmax);
         info[1] = gdots;
     }
+    QC_CUDA(cudaStreamSynchronize(p->stream));
+    return QCDMET_OK;
+}
+
+// grad = 2 J^T resid on the device (the BFGS gradient of src/dmet.py:381-388 without shipping J to the host)
+extern "C" int qcdmet_plan_gradient(qcdmet_plan *p, const double *resid, double *grad)
+{
+    QC_CHECK(p != nullptr && resid != nullptr && grad != nullptr, QCDMET_E_ARG, "plan, resid or grad is NULL");
+    QC_CHECK(p->jac_in_memory, QCDMET_E_STATE, "no Jacobian computed yet");
+    DeviceGuard guard(p->device);
+    const int n = p->colEnd - p->colBegin;
+    const long long Q = p->Q;
+    QC_CHECK(n > 0 && Q > 0 && Q < (1LL << 31), QCDMET_E_ARG, "empty or oversized problem");
+    if (!p->d_g) QC_TRY(dev_alloc(&p->d_g, (size_t)p->P));
+    if (!p->d_r) QC_TRY(dev_alloc(&p->d_r, (size_t)Q));
+    cublasSetStream(p->blas, p->stream);
+    const double two = 2.0, zero = 0.0;
+    QC_CUDA(cudaMemcpyAsync(p->d_r, resid, sizeof(double) * (size_t)Q, cudaMemcpyHostToDevice, p->stream));
+    cublasStatus_t cs = cublasDgemv(p->blas, CUBLAS_OP_T, (int)Q, n, &two, p->d_J, (int)Q, p->d_r, 1, &zero, p->d_g, 1);
+    QC_CHECK(cs == CUBLAS_STATUS_SUCCESS, QCDMET_E_CUDA, "cublasDgemv failed: %d", (int)cs);
+    QC_CUDA(cudaMemcpyAsync(grad, p->d_g, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, p->stream));
     QC_CUDA(cudaStreamSynchronize(p->stream));
     return QCDMET_OK;
 }

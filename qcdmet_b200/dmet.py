@@ -352,9 +352,15 @@ class dmet:
         return np.linalg.norm(self.rdm_differences(newumatflat)) ** 2
 
     def costfunction_derivative(self, newumatflat):
+        """2 J^T r (src/dmet.py:381-388).  The Jacobian stays on the device; only the P-vector comes back."""
         errors = self.rdm_differences(newumatflat)
-        error_derivs = self.rdm_differences_derivative(newumatflat)
-        return 2.0 * np.dot(error_derivs.T, errors)
+        start_grad = time.time()
+        row_start, rows, row_idx = self._fragment_rows()
+        plan = self.helper.response_jacobian_device(self.flat2square(newumatflat), row_start, rows=rows,
+                                                    row_idx=row_idx, NOrotation=self.NOrotation)
+        thegradient = plan.gradient(errors)
+        self.time_grad += time.time() - start_grad
+        return thegradient
 
     # ------------------------------------------------------------------ src/dmet.py:527-539
     def verify_gradient(self, umatflat):

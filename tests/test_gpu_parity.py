@@ -487,6 +487,8 @@ def test_dmet_class_jacobian_and_gradient(case):
     assert np.abs(jac - ref).max() <= TOL
     diff, norm = d.verify_gradient(x)
     assert diff < 1e-4 * max(norm, 1.0)
+    g_dev = d.costfunction_derivative(x)                       # 2 J^T r on the device
+    assert np.abs(g_dev - 2.0 * jac.T @ d.rdm_differences(x)).max() <= 1e-11 * max(1.0, np.abs(g_dev).max())
     assert d.time_grad > 0.0
 
 
