@@ -154,9 +154,12 @@ class Plan:
         self.col_begin, self.col_end = 0, self.nterms
 
     def close(self):
-        if getattr(self, "handle", None) is not None and self.handle.value:
-            self.lib.qcdmet_plan_destroy(self.handle)
-            self.handle = ctypes.c_void_p()
+        try:
+            if getattr(self, "handle", None) is not None and self.handle.value:
+                self.lib.qcdmet_plan_destroy(self.handle)
+                self.handle = ctypes.c_void_p()
+        except (AttributeError, TypeError):      # interpreter shutdown: the library object is already gone
+            pass
 
     __del__ = close
 
