@@ -73,3 +73,36 @@ def test_missing_library_fails_loudly():
             "try:\n    _lib.load()\nexcept OSError as e:\n    print('OSError', 'no CPU fallback' in str(e))\n" % ROOT)
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
     assert out.stdout.strip() == "OSError True", out.stderr[-500:]
+
+
+def _build_c_example(tmp_path):
+    import subprocess
+    exe = str(tmp_path / "jacobian_c_abi")
+    cmd = ["gcc", "-O2", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+           os.path.join(ROOT, "examples", "jacobian_c_abi.c"), "-o", exe, "-L", os.path.join(ROOT, "qcdmet_b200"),
+           "-lqcdmet_b200", "-Wl,-rpath," + os.path.join(ROOT, "qcdmet_b200"), "-lm"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    return exe
+
+
+def test_header_is_plain_c_and_links(tmp_path):
+    """include/qcdmet_b200.h compiles as C (no C++/torch types) and the library links from a C program;
+    without a device the program reports the library's error instead of computing anything."""
+    import subprocess
+    exe = _build_c_example(tmp_path)
+    out = subprocess.run([exe, "16"], capture_output=True, text=True, timeout=120)
+    if _lib.load().qcdmet_device_count() == 0:
+        assert out.returncode == 1 and "no CPU fallback" in out.stderr
+    else:
+        assert out.returncode == 0, out.stdout + out.stderr
+
+
+@pytest.mark.gpu
+def test_c_program_computes_jacobian(tmp_path):
+    import subprocess
+    exe = _build_c_example(tmp_path)
+    for n in ("16", "200"):
+        out = subprocess.run([exe, n], capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, out.stdout + out.stderr
+        assert "block asymmetry 0.0e+00" in out.stdout
