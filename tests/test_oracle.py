@@ -43,6 +43,31 @@ def test_oracle_matches_compiled_reference(flavour):
 
 
 @pytest.mark.skipif(not ref_loader.available("mkl"), reason="oracle/_ref not built")
+def test_oracle_matches_compiled_reference_on_arbitrary_lists():
+    """lib/rhf_response.cc accepts any list of unit elements: unsymmetric single elements, duplicates,
+    long lists spanning the whole matrix.  The restatement must agree on all of them."""
+    rng = np.random.default_rng(7)
+    n, no = 26, 9
+    w = wl.make_workload("rnd", n, no, [4, 4, 4])
+    hs, hr, hc = [0], [], []
+    for _ in range(40):
+        k = int(rng.integers(1, 9))
+        hr += list(map(int, rng.integers(0, n, k)))
+        hc += list(map(int, rng.integers(0, n, k)))
+        hs.append(len(hr))
+    hs.append(len(hr))                                  # an empty perturbation at the end
+    hs, hr, hc = np.array(hs, np.int32), np.array(hr, np.int32), np.array(hc, np.int32)
+    resp_ref, d_ref = ref_loader.rhf_response(n, no, hs, hr, hc, w.h0, "mkl")
+    resp, d = ro.rhf_response(n, len(hs) - 1, no, hs, hr, hc, w.h0)
+    assert np.abs(resp - resp_ref).max() <= TOL and np.abs(d - d_ref).max() <= TOL
+    assert np.all(resp[-1] == 0.0) and np.all(resp_ref[-1] == 0.0)
+    e, c = ro.eigh_sorted(w.h0)
+    jac = ro.jacobian_from_orbitals(c, e, no, hs, hr, hc, w.row_start, None, w.row_idx)
+    imp_size = ro.make_imp_size(w.imp_clust, False)
+    assert np.abs(jac - ro.jacobian_from_response(resp_ref, w.imp_clust, imp_size, False)).max() <= TOL
+
+
+@pytest.mark.skipif(not ref_loader.available("mkl"), reason="oracle/_ref not built")
 def test_compiled_reference_nterms_zero():
     w = wl.sweep(16, nterms=0)
     resp, d = ref_loader.rhf_response(w.norb, w.num_pairs, w.h1start, w.h1row, w.h1col, w.h0)
