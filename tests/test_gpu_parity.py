@@ -272,6 +272,25 @@ def test_arbitrary_element_lists(seed, symmetric_mode):
     assert np.abs(out.reshape(p, n, n) - resp).max() <= TOL
 
 
+def test_lists_spanning_the_whole_matrix():
+    """Perturbations with up to 8 elements anywhere in the matrix (+ an empty one): only the general kernel
+    applies; Jacobian and compat full response against the oracle."""
+    rng = np.random.default_rng(7)
+    w = wl.make_workload("rnd", 50, 19, [4, 3, 5, 4, 2], fit_imp_bath=False)
+    hs, hr, hc = [0], [], []
+    for _ in range(60):
+        k = int(rng.integers(1, 9))
+        hr += list(map(int, rng.integers(0, w.norb, k)))
+        hc += list(map(int, rng.integers(0, w.norb, k)))
+        hs.append(len(hr))
+    hs.insert(30, hs[29])
+    w.h1start, w.h1row, w.h1col = np.array(hs, np.int32), np.array(hr, np.int32), np.array(hc, np.int32)
+    jac, c, e, d, used = run_plan(w, _lib.KERNEL_AUTO)
+    assert used == GENERAL
+    assert np.abs(jac - oracle_jac(w, c, e)).max() <= TOL
+    assert np.all(jac[:, 29] == 0.0)
+
+
 def test_degenerate_shapes():
     """Empty fragments, a fragment-free plan, zero perturbations, and a single perturbation."""
     w = wl.sweep(24)
