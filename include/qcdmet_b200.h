@@ -81,6 +81,10 @@ int qcdmet_jacobian(int Norb, int Nterms, int numPairs,
                     int colBegin, int colEnd,
                     double *J, double *D_blocks, double *eig_out);
 
+/* qcdmet_jacobian* keep the plan (device buffers, schedule, library handles) of their last call and reuse it
+ * when the perturbation list and fragment rows are unchanged; qcdmet_shutdown() releases it. */
+int qcdmet_shutdown(void);
+
 /* Test-only variant: orbitals given instead of H0 (no eigensolve), so that the kernels
  * can be compared against the oracle on bit-identical (C, e).
  * C: column-major Norb x Norb, eigenvector k in column k (LAPACK layout), e ascending. */

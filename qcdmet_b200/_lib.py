@@ -34,6 +34,7 @@ SIGNATURES = {
                                                      ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                                      ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
                                                      ctypes.c_void_p]),
+    "qcdmet_shutdown": (ctypes.c_int, []),
     "qcdmet_plan_create": (ctypes.c_int, [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, ctypes.c_int,
                                           ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
                                           ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,

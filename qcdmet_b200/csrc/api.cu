@@ -3,6 +3,8 @@
 #include <cstdarg>
 #include <algorithm>
 #include <numeric>
+#include <mutex>
+#include <cstdint>
 
 namespace qcdmet {
 
@@ -760,21 +762,70 @@ int qcdmet_plan_get_full_response(qcdmet_plan *p, double *rdm_deriv, double *one
     return QCDMET_OK;
 }
 
+// The stateless entry points keep the plan of the last call (lazily created per-process context,
+// SURVEY.md 8b "Ownership"): a Levenberg-Marquardt loop calls them many times with the same perturbation
+// list and fragment rows, and re-creating the device buffers (1.5 GB at N = 4000) and library handles on
+// every call would cost more than the kernels at small sizes.  Keyed on a hash of every index array (and
+// of R); released by qcdmet_shutdown().
+static std::mutex g_cache_mu;
+static qcdmet_plan *g_cached_plan = nullptr;
+static uint64_t g_cached_key = 0;
+
+static uint64_t fnv1a(uint64_t h, const void *data, size_t bytes)
+{
+    const unsigned char *p = (const unsigned char *)data;
+    for (size_t i = 0; i < bytes; ++i) { h ^= p[i]; h *= 1099511628211ULL; }
+    return h;
+}
+
 static int jacobian_impl(int Norb, int Nterms, int numPairs, const int *H1start, const int *H1row,
                          const int *H1col, const double *H0, const double *C, const double *e,
                          int Nfrag, const int *rowStart, const double *R, const int *rowIdx,
                          int colBegin, int colEnd, double *J, double *D_blocks, double *eig_out)
 {
-    qcdmet_plan *p = nullptr;
-    QC_TRY(qcdmet_plan_create(&p, -1, Norb, Nterms, numPairs, H1start, H1row, H1col, Nfrag, rowStart, R, rowIdx));
+    QC_TRY(validate_lists(Norb, Nterms, numPairs, H1start, H1row, H1col, Nfrag, rowStart, R, rowIdx));
+    int dev = -1;
+    if (cudaGetDevice(&dev) != cudaSuccess) dev = -1;
+    cudaGetLastError();
+    const int S = Nfrag > 0 ? rowStart[Nfrag] : 0;
+    const int head[6] = {Norb, Nterms, numPairs, Nfrag, dev, R ? 1 : 0};
+    uint64_t key = fnv1a(1469598103934665603ULL, head, sizeof(head));
+    key = fnv1a(key, H1start, sizeof(int) * (size_t)(Nterms + 1));
+    key = fnv1a(key, H1row, sizeof(int) * (size_t)H1start[Nterms]);
+    key = fnv1a(key, H1col, sizeof(int) * (size_t)H1start[Nterms]);
+    if (Nfrag > 0) key = fnv1a(key, rowStart, sizeof(int) * (size_t)(Nfrag + 1));
+    if (R) key = fnv1a(key, R, sizeof(double) * (size_t)S * Norb);
+    else if (S > 0) key = fnv1a(key, rowIdx, sizeof(int) * (size_t)S);
+
+    std::lock_guard<std::mutex> lock(g_cache_mu);
+    if (!g_cached_plan || g_cached_key != key) {
+        if (g_cached_plan) qcdmet_plan_destroy(g_cached_plan);
+        g_cached_plan = nullptr;
+        QC_TRY(qcdmet_plan_create(&g_cached_plan, -1, Norb, Nterms, numPairs, H1start, H1row, H1col, Nfrag,
+                                  rowStart, R, rowIdx));
+        g_cached_key = key;
+    }
+    qcdmet_plan *p = g_cached_plan;
     int rc = qcdmet_plan_set_columns(p, colBegin, colEnd);
     if (!rc) rc = H0 ? qcdmet_plan_set_h0(p, H0) : qcdmet_plan_set_orbitals(p, C, e);
     if (!rc && J) rc = qcdmet_plan_compute(p);
     if (!rc && J) rc = qcdmet_plan_get_jacobian(p, J);
     if (!rc && D_blocks) rc = qcdmet_plan_get_dblocks(p, D_blocks);
     if (!rc && eig_out) rc = qcdmet_plan_get_eigenvalues(p, eig_out);
-    qcdmet_plan_destroy(p);
+    if (rc) {                                   // do not keep a plan in an unknown state
+        qcdmet_plan_destroy(g_cached_plan);
+        g_cached_plan = nullptr;
+    }
     return rc;
+}
+
+int qcdmet_shutdown(void)
+{
+    std::lock_guard<std::mutex> lock(g_cache_mu);
+    if (g_cached_plan) qcdmet_plan_destroy(g_cached_plan);
+    g_cached_plan = nullptr;
+    g_cached_key = 0;
+    return QCDMET_OK;
 }
 
 int qcdmet_jacobian(int Norb, int Nterms, int numPairs, const int *H1start, const int *H1row,

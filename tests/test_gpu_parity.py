@@ -272,6 +272,47 @@ def test_arbitrary_element_lists(seed, symmetric_mode):
     assert np.abs(out.reshape(p, n, n) - resp).max() <= TOL
 
 
+def test_stateless_entry_points_and_plan_reuse():
+    """qcdmet_jacobian / qcdmet_jacobian_from_orbitals (host buffers in and out, the INTEGRATION.md binding):
+    repeated calls with the same lists reuse the cached plan, a new list replaces it."""
+    lib = _lib.load()
+
+    def call(w, h0=None, orbitals=None, cols=None):
+        lo, hi = cols if cols else (0, w.nterms)
+        jac = np.empty((w.nresid, hi - lo), dtype=np.float64, order="F")
+        dbl = np.empty(w.nresid)
+        common = (w.norb, w.nterms, w.num_pairs, _lib._ptr(w.h1start), _lib._ptr(w.h1row), _lib._ptr(w.h1col))
+        rows = (len(w.row_start) - 1, _lib._ptr(w.row_start), _lib._ptr(w.rows), _lib._ptr(w.row_idx))
+        if orbitals is None:
+            eig = np.empty(w.norb)
+            h0 = np.ascontiguousarray(h0)
+            rc = lib.qcdmet_jacobian(*common, _lib._ptr(h0), *rows, lo, hi, _lib._ptr(jac), _lib._ptr(dbl), _lib._ptr(eig))
+        else:
+            c = np.asfortranarray(orbitals[0])
+            ee = np.ascontiguousarray(orbitals[1])
+            rc = lib.qcdmet_jacobian_from_orbitals(*common, _lib._ptr(c), _lib._ptr(ee), *rows, lo, hi,
+                                                   _lib._ptr(jac), _lib._ptr(dbl))
+        assert rc == 0, lib.qcdmet_last_error()
+        return jac
+
+    w = wl.sweep(48)
+    e, c = ro.eigh_sorted(w.h0)
+    ref = oracle_jac(w, c, e)
+    assert np.abs(call(w, h0=w.h0) - ref).max() <= TOL
+    assert np.abs(call(w, orbitals=(c, e)) - ref).max() <= TOL                     # cached plan, other entry point
+    assert np.abs(call(w, orbitals=(c, e), cols=(13, 77)) - ref[:, 13:77]).max() <= TOL
+    h1 = w.h0 + 0.05 * np.diag(np.cos(np.arange(w.norb)))                          # same lists, new matrix
+    e1, c1 = ro.eigh_sorted(h1)
+    assert np.abs(call(w, h0=h1) - oracle_jac(w, c1, e1)).max() <= TOL
+    w2 = wl.hubbard24(True, fit_imp_bath=True, l=6)                                # different lists: new plan
+    e2, c2 = ro.eigh_sorted(w2.h0)
+    assert np.abs(call(w2, h0=w2.h0) - oracle_jac(w2, c2, e2)).max() <= TOL
+    assert np.abs(call(w, h0=w.h0) - ref).max() <= TOL
+    assert lib.qcdmet_shutdown() == 0
+    assert np.abs(call(w, h0=w.h0) - ref).max() <= TOL
+    assert lib.qcdmet_shutdown() == 0
+
+
 def test_lists_spanning_the_whole_matrix():
     """Perturbations with up to 8 elements anywhere in the matrix (+ an empty one): only the general kernel
     applies; Jacobian and compat full response against the oracle."""
