@@ -56,7 +56,7 @@ def parse():
                          "polyyne / sn2: the shapes of configs[2] / configs[3]")
     ap.add_argument("--norb", type=int, default=int(os.environ.get("QCDMET_BENCH_NORB", 4000)))
     ap.add_argument("--nterms", type=int, default=None, help="default 2.5*norb")
-    ap.add_argument("--kernel", default="auto", choices=["auto", "general", "dmma"])
+    ap.add_argument("--kernel", default="auto", choices=["auto", "general", "dmma", "factorised"])
     ap.add_argument("--cpu-sample-cols", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -297,7 +297,8 @@ def run_b200(args):
     log("orbitals ready")
     plan = _lib.Plan(w.norb, w.num_pairs, w.h1start, w.h1row, w.h1col, w.row_start, w.rows, w.row_idx,
                      device=local)
-    plan.set_kernel({"auto": _lib.KERNEL_AUTO, "general": _lib.KERNEL_GENERAL, "dmma": _lib.KERNEL_DMMA}[args.kernel])
+    plan.set_kernel({"auto": _lib.KERNEL_AUTO, "general": _lib.KERNEL_GENERAL, "dmma": _lib.KERNEL_DMMA,
+                     "factorised": _lib.KERNEL_FACTORISED}[args.kernel])
     plan.set_columns(lo, hi)
     plan.set_orbitals(c, e)
 
@@ -471,7 +472,7 @@ def run_b200(args):
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": desc,
-                       "kernel": {1: "general", 2: "dmma"}.get(kernel_used, str(kernel_used)),
+                       "kernel": {1: "general", 2: "dmma", 4: "factorised"}.get(kernel_used, str(kernel_used)),
                        "sharding": ("single GPU" if world == 1 else
                                     f"{world} ranks, block-pair work list split evenly, fused all-gather: each Jacobian element "
                                     "stored into every rank's buffer by NVLink peer stores, stream barrier (1-element NCCL all-reduce) "

@@ -39,10 +39,13 @@ extern "C" {
 #define QCDMET_E_GAP      -6   /* e[numPairs] - e[numPairs-1] <= 0: response diverges */
 
 /* Kernel selection for qcdmet_plan_set_kernel(). */
-#define QCDMET_KERNEL_AUTO     0   /* DMMA site-factorised kernel when eligible, else general */
+#define QCDMET_KERNEL_AUTO     0   /* fused DMMA kernel when eligible, else factorised, else general */
 #define QCDMET_KERNEL_GENERAL  1   /* plain FP64 general kernel (any CSR, any rows)           */
 #define QCDMET_KERNEL_DMMA     2   /* force the DMMA kernel (error if not eligible)           */
 #define QCDMET_KERNEL_DMMA_NOSYM 3 /* DMMA kernel without the symmetric (mirrored-patch) mode */
+#define QCDMET_KERNEL_FACTORISED 4 /* site panels M_r by the DMMA main loop into HBM + per-perturbation
+                                      contraction: any fragment sizes, <= 64 elements per perturbation,
+                                      panels must fit in device memory (error otherwise)                */
 
 /* ---------------------------------------------------------------------------------------
  * (1) Compat symbol.  Replaces lib/rhf_response.cc:32-119 one to one:
@@ -170,7 +173,7 @@ int qcdmet_plan_gradient(qcdmet_plan *plan, const double *resid, double *grad);
 
 /* Introspection (bench / tests). */
 long long qcdmet_plan_num_residuals(qcdmet_plan *plan);    /* Q                                  */
-int  qcdmet_plan_kernel_used(qcdmet_plan *plan);           /* QCDMET_KERNEL_GENERAL or _DMMA      */
+int  qcdmet_plan_kernel_used(qcdmet_plan *plan);           /* QCDMET_KERNEL_GENERAL, _DMMA or _FACTORISED */
 int  qcdmet_plan_launches(qcdmet_plan *plan);              /* kernels launched by the last compute */
 int  qcdmet_plan_symmetric_used(qcdmet_plan *plan);        /* 1 if the last compute used the mirrored-patch mode */
 double qcdmet_plan_flops(qcdmet_plan *plan);               /* FP64 flops executed by the last compute */
@@ -184,6 +187,12 @@ int  qcdmet_plan_kernel_time_ms(qcdmet_plan *plan, double *ms);
  *              full-range launch, column tiles }.  rowIdx == NULL means dense projector rows. */
 int qcdmet_schedule_info(int Norb, int Nterms, int numPairs, const int *H1start, const int *H1row,
                          const int *H1col, int Nfrag, const int *rowStart, const int *rowIdx, int *info);
+
+/* Host-only: the tile schedule of the factorised path's contraction kernel (csrc/kernels_contract.cu) for
+ * these fragment rows.  counts[3] = { tiles, row slots, items }; the arrays may be NULL (size query), else
+ * tileInfo[4 * tiles] = { slotBegin, nSlots, itemBegin, nItems } per tile, slotRow[slots] = fragment row of
+ * the slot or -1, items[] = u1 | u2 << 8 (pair of 4-row units of one fragment, u1 <= u2, tile-local). */
+int qcdmet_contract_schedule(int Nfrag, const int *rowStart, int *counts, int *tileInfo, int *slotRow, int *items);
 
 const char *qcdmet_last_error(void);
 const char *qcdmet_version(void);

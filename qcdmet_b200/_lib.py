@@ -15,7 +15,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("QCDMET_B200_LIB", os.path.join(_HERE, "libqcdmet_b200.so"))
 
-KERNEL_AUTO, KERNEL_GENERAL, KERNEL_DMMA, KERNEL_DMMA_NOSYM = 0, 1, 2, 3
+KERNEL_AUTO, KERNEL_GENERAL, KERNEL_DMMA, KERNEL_DMMA_NOSYM, KERNEL_FACTORISED = 0, 1, 2, 3, 4
 
 c_int_p = ctypes.POINTER(ctypes.c_int)
 c_double_p = ctypes.POINTER(ctypes.c_double)
@@ -69,6 +69,8 @@ SIGNATURES = {
     "qcdmet_plan_kernel_time_ms": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     "qcdmet_schedule_info": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
                                             ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "qcdmet_contract_schedule": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                                ctypes.c_void_p, ctypes.c_void_p]),
     "qcdmet_last_error": (ctypes.c_char_p, []),
     "qcdmet_version": (ctypes.c_char_p, []),
     "qcdmet_device_count": (ctypes.c_int, []),
@@ -131,6 +133,23 @@ def schedule_info(norb, num_pairs, h1start, h1row, h1col, row_start, row_idx=Non
     out = dict(zip(keys, (int(v) for v in info)))
     out["why"] = lib.qcdmet_last_error().decode() if not out["eligible"] else ""
     return out
+
+
+def contract_schedule(row_start):
+    """Host-only: tiles of the factorised path's contraction kernel -> list of (slot_rows, [(u1, u2), ...])."""
+    lib = load()
+    rs = as_i32(row_start)
+    counts = np.zeros(3, dtype=np.int32)
+    check(lib.qcdmet_contract_schedule(len(rs) - 1, _ptr(rs), _ptr(counts), None, None, None))
+    tile_info = np.zeros(4 * max(int(counts[0]), 1), dtype=np.int32)
+    slot_row = np.zeros(max(int(counts[1]), 1), dtype=np.int32)
+    items = np.zeros(max(int(counts[2]), 1), dtype=np.int32)
+    check(lib.qcdmet_contract_schedule(len(rs) - 1, _ptr(rs), _ptr(counts), _ptr(tile_info), _ptr(slot_row), _ptr(items)))
+    tiles = []
+    for t in range(int(counts[0])):
+        sb, ns, ib, ni = (int(x) for x in tile_info[4 * t:4 * t + 4])
+        tiles.append((slot_row[sb:sb + ns].copy(), [(int(i) & 0xFF, int(i) >> 8) for i in items[ib:ib + ni]]))
+    return tiles
 
 
 class Plan:

@@ -56,6 +56,10 @@ struct qcdmet_plan {
     cusolverDnHandle_t solver = nullptr;
     cublasHandle_t blas = nullptr;
     DmmaPlanData *dmma = nullptr;
+    // factorised path (site panels by the DMMA main loop + per-perturbation contraction): fragments > 8 rows
+    FactPlanData *fact = nullptr;
+    bool fact_tried = false, fact_ok = false, fact_orbitals_valid = false;
+    std::string fact_why;
     bool have_orbitals = false, have_jac = false;
     int launches = 0;
     double flops = 0.0;
@@ -208,6 +212,33 @@ int build_panels(qcdmet_plan *p)
     p->have_orbitals = true;
     p->have_jac = false;
     p->w_valid = false;
+    p->fact_orbitals_valid = false;
+    return QCDMET_OK;
+}
+
+// Build the factorised-path schedule and buffers on first use.  Not an error if the path does not apply
+// (too many elements per perturbation, panel array larger than half of the free device memory): the plan
+// then keeps the general kernel; fact_why says why.
+int ensure_fact(qcdmet_plan *p)
+{
+    if (p->fact_tried) return QCDMET_OK;
+    p->fact_tried = true;
+    p->fact_ok = false;
+    if (p->P == 0 || p->S == 0) { p->fact_why = "empty problem"; return QCDMET_OK; }
+    if (!fact_eligible(p->P, p->h1start.data(), &p->fact_why)) return QCDMET_OK;
+    size_t freeB = 0, totalB = 0;
+    QC_CUDA(cudaMemGetInfo(&freeB, &totalB));
+    const size_t need = fact_plan_bytes(p->N, p->no, p->P, p->S, p->h1start.data(), p->h1row.data());
+    if (need > freeB / 2) {
+        char buf[160];
+        snprintf(buf, sizeof(buf), "site panels need %.2f GB, more than half of the free device memory (%.2f GB)",
+                 need * 1e-9, freeB * 1e-9);
+        p->fact_why = buf;
+        return QCDMET_OK;
+    }
+    QC_TRY(fact_plan_build(&p->fact, p->N, p->no, p->P, p->F, p->rowStart.data(), p->ldo, p->h1start.data(),
+                           p->h1row.data()));
+    p->fact_ok = true;
     return QCDMET_OK;
 }
 
@@ -240,6 +271,22 @@ int qcdmet_schedule_info(int Norb, int Nterms, int numPairs, const int *H1start,
     std::string why;
     dmma_schedule_info(Norb, numPairs, Nterms, Nfrag, H1start, H1row, H1col, rowStart, rowIdx, info, &why);
     if (!info[0]) set_error("DMMA kernel not eligible: %s", why.c_str());
+    return QCDMET_OK;
+}
+
+int qcdmet_contract_schedule(int Nfrag, const int *rowStart, int *counts, int *tileInfo, int *slotRow, int *items)
+{
+    QC_CHECK(counts != nullptr, QCDMET_E_ARG, "counts is NULL");
+    QC_CHECK(Nfrag >= 0 && (Nfrag == 0 || (rowStart != nullptr && rowStart[0] == 0)), QCDMET_E_ARG,
+             "rowStart[0] must be 0");
+    for (int f = 0; f < Nfrag; ++f)
+        QC_CHECK(rowStart[f + 1] >= rowStart[f], QCDMET_E_ARG, "rowStart not monotone at %d", f);
+    ContractSchedule sc;
+    contract_schedule_build(Nfrag, rowStart, &sc);
+    counts[0] = sc.nTiles; counts[1] = (int)sc.slotRow.size(); counts[2] = (int)sc.items.size();
+    if (tileInfo) std::copy(sc.tileInfo.begin(), sc.tileInfo.end(), tileInfo);
+    if (slotRow) std::copy(sc.slotRow.begin(), sc.slotRow.end(), slotRow);
+    if (items) std::copy(sc.items.begin(), sc.items.end(), items);
     return QCDMET_OK;
 }
 
@@ -330,6 +377,8 @@ int qcdmet_plan_create(qcdmet_plan **out, int device, int Norb, int Nterms, int 
         rc = dmma_plan_build(&p->dmma, Norb, numPairs, Nterms, Nfrag, p->h1start.data(), p->h1row.data(),
                              p->h1col.data(), p->rowStart.data(), p->rowIdx.data());
         if (rc) return fail(rc);
+    } else if ((rc = ensure_fact(p))) {
+        return fail(rc);
     }
     *out = p;
     return QCDMET_OK;
@@ -351,6 +400,7 @@ int qcdmet_plan_destroy(qcdmet_plan *p)
     if (p->solver) cusolverDnDestroy(p->solver);
     if (p->blas) cublasDestroy(p->blas);
     if (p->dmma) dmma_plan_free(p->dmma);
+    if (p->fact) fact_plan_free(p->fact);
     cudaGetLastError();
     delete p;
     return QCDMET_OK;
@@ -371,10 +421,15 @@ int qcdmet_plan_set_columns(qcdmet_plan *p, int colBegin, int colEnd)
 int qcdmet_plan_set_kernel(qcdmet_plan *p, int kernel)
 {
     QC_CHECK(p != nullptr, QCDMET_E_ARG, "plan is NULL");
-    QC_CHECK(kernel >= QCDMET_KERNEL_AUTO && kernel <= QCDMET_KERNEL_DMMA_NOSYM, QCDMET_E_ARG,
+    QC_CHECK(kernel >= QCDMET_KERNEL_AUTO && kernel <= QCDMET_KERNEL_FACTORISED, QCDMET_E_ARG,
              "unknown kernel id %d", kernel);
     QC_CHECK((kernel != QCDMET_KERNEL_DMMA && kernel != QCDMET_KERNEL_DMMA_NOSYM) || p->dmma_ok, QCDMET_E_ARG,
              "DMMA kernel not eligible for this plan: %s", p->dmma_why.c_str());
+    if (kernel == QCDMET_KERNEL_FACTORISED) {
+        DeviceGuard guard(p->device);
+        QC_TRY(ensure_fact(p));
+        QC_CHECK(p->fact_ok, QCDMET_E_ARG, "factorised path not available for this plan: %s", p->fact_why.c_str());
+    }
     p->kernel_req = kernel;
     return QCDMET_OK;
 }
@@ -454,7 +509,18 @@ int qcdmet_plan_compute(qcdmet_plan *p)
         QC_CUDA(cudaEventCreate(&p->ev0));
         QC_CUDA(cudaEventCreate(&p->ev1));
     }
-    if (use_dmma) {
+    const bool use_fact = (p->kernel_req == QCDMET_KERNEL_FACTORISED) ||
+                          (p->kernel_req == QCDMET_KERNEL_AUTO && !p->dmma_ok && p->fact_ok);
+    if (use_fact) {
+        if (!p->fact_orbitals_valid) {
+            QC_TRY(fact_prepare_orbitals(p->fact, v, p->stream));
+            p->fact_orbitals_valid = true;
+        }
+        const long long nnzInRange = (long long)p->h1start[p->colEnd] - p->h1start[p->colBegin];
+        QC_TRY(launch_jacobian_factorised(p->fact, v, nnzInRange, p->stream, &p->launches, &p->flops, p->ev0, p->ev1));
+        p->kernel_used = QCDMET_KERNEL_FACTORISED;
+        p->symmetric_used = false;
+    } else if (use_dmma) {
         QC_TRY(launch_jacobian_dmma(p->dmma, v, p->stream, &p->launches, &p->flops, p->ev0, p->ev1,
                                     p->kernel_req != QCDMET_KERNEL_DMMA_NOSYM, p->peers_on ? &p->peers : nullptr));
         p->symmetric_used = dmma_last_launch_symmetric(p->dmma);
@@ -860,8 +926,7 @@ int rhf_response(const int Norb, const int Nterms, const int numPairs, int *H1st
     qcdmet_plan *p = nullptr;
     QC_TRY(qcdmet_plan_create(&p, -1, Norb, Nterms, numPairs, H1start, H1row, H1col, 1, rowStart.data(),
                               nullptr, rowIdx.data()));
-    int rc = qcdmet_plan_set_kernel(p, QCDMET_KERNEL_GENERAL);
-    if (!rc) rc = qcdmet_plan_set_h0(p, H0);
+    int rc = qcdmet_plan_set_h0(p, H0);
     if (!rc && Nterms > 0) rc = qcdmet_plan_compute(p);
     if (!rc) {
         if (Nterms > 0) rc = qcdmet_plan_get_full_response(p, rdm_deriv, H0);

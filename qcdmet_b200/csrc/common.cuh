@@ -102,4 +102,35 @@ bool dmma_last_launch_symmetric(const DmmaPlanData *d);
 void dmma_schedule_info(int N, int no, int P, int F, const int *h1start, const int *h1row, const int *h1col,
                         const int *rowStart, const int *rowIdx, int *info, std::string *why);
 
+// kernels_contract.cu: per-perturbation contraction of the site panels (factorised path)
+#define QCDMET_CONTRACT_MAX_NNZ 64      // elements per perturbation the contraction kernel stages
+struct ContractSchedule {               // host-built, see kernels_contract.cu
+    int nTiles = 0;
+    long long validSlots = 0;           // row slots that hold a fragment row (flop count)
+    std::vector<int> tileInfo;          // [nTiles][4] slotBegin, nSlots, itemBegin, nItems
+    std::vector<int> slotRow;           // fragment row of every slot, -1 = padding of a ragged unit
+    std::vector<unsigned short> items;  // unit pair of the tile: u1 | u2 << 8
+};
+struct ContractPlan {
+    ContractSchedule sched;
+    int *d_tileInfo = nullptr, *d_slotRow = nullptr;
+    unsigned short *d_items = nullptr;
+};
+void contract_schedule_build(int F, const int *rowStart, ContractSchedule *out);
+int contract_plan_build(ContractPlan **out, int F, const int *rowStart);
+void contract_plan_free(ContractPlan *c);
+int launch_contract_panels(const ContractPlan *c, const JacView &v, const double *M, const int *siteToU,
+                           long long nnzInRange, cudaStream_t st, int *launches, double *flops);
+
+// factorised path for large fragments (kernels_dmma.cu panel mode + kernels_contract.cu)
+struct FactPlanData;
+bool fact_eligible(int P, const int *h1start, std::string *why);
+size_t fact_plan_bytes(int N, int no, int P, int S, const int *h1start, const int *h1row);
+int fact_plan_build(FactPlanData **out, int N, int no, int P, int F, const int *rowStart, int ldo,
+                    const int *h1start, const int *h1row);
+void fact_plan_free(FactPlanData *f);
+int fact_prepare_orbitals(FactPlanData *f, const JacView &v, cudaStream_t st);
+int launch_jacobian_factorised(FactPlanData *f, const JacView &v, long long nnzInRange, cudaStream_t st,
+                               int *launches, double *flops, cudaEvent_t ev0, cudaEvent_t ev1);
+
 }  // namespace qcdmet

@@ -1,0 +1,260 @@
+// kernels_contract.cu -- per-perturbation contraction of the site panels M_r (factorised path for
+// fragments of more than 8 rows: polyyne- / sn2-like fits and the compat full response).
+//
+// kernels_dmma.cu (panel mode) leaves  M_r[a,o] = sum_v PV[a,v] Cv[r,v] W[v,o]  in HBM for every site r
+// that occurs as an element row.  Per column p (lib/rhf_response.cc:82-108 restricted to fragment blocks):
+//   Y_p[a,o]      = sum_{(r,c) in H1_p} M_r[a,o] Co[c,o]
+//   J[(f;a,b),p]  = 2 sum_o ( Y_p[a,o] PO[b,o] + PO[a,o] Y_p[b,o] )        a, b rows of fragment f
+// FP64 FMA pipe (same issue rate as DMMA on B200).  Work decomposition, built once per plan on the host:
+//   unit  = 4 consecutive rows of one fragment (last unit of a fragment may be ragged)
+//   item  = unordered pair of units (u1 <= u2) of the same fragment: a 4 x 4 register tile, one thread
+//   tile  = <= 32 units (128 row slots) and <= 256 items: whole small fragments packed together, or
+//           a pair of 16-unit slices of a large fragment.  One CTA per (tile, column).
+// Every (a,b) of every block has exactly one owner and J[a,b], J[b,a] are stored from the same register:
+// no atomics, blocks exactly symmetric, run-to-run bit-reproducible.
+#include "common.cuh"
+#include <algorithm>
+
+namespace qcdmet {
+
+namespace {
+constexpr int CU = 4;                  // rows per unit
+constexpr int CMAXU = 32;              // units per tile
+constexpr int CSLICE = 16;             // units per slice of a large fragment
+constexpr int CSLOTS = CU * CMAXU;     // row slots per tile
+constexpr int CNT = 256;               // threads per CTA = max items per tile
+constexpr int CTO = 32;                // occupied orbitals per staged chunk
+constexpr int CLD = CSLOTS + 2;        // smem row stride in doubles (even: 16 B aligned units)
+constexpr int CSMEM = 2 * CTO * CLD * 8 + CSLOTS * 4 + QCDMET_CONTRACT_MAX_NNZ * 16;
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+// host: schedule
+// ------------------------------------------------------------------------------------------
+void contract_schedule_build(int F, const int *rowStart, ContractSchedule *out)
+{
+    ContractSchedule &s = *out;
+    s.tileInfo.clear(); s.slotRow.clear(); s.items.clear();
+    s.nTiles = 0; s.validSlots = 0;
+    int units = 0, nitems = 0, slotBegin = 0, itemBegin = 0;
+    auto flush = [&]() {
+        if (units > 0) {
+            s.tileInfo.push_back(slotBegin); s.tileInfo.push_back(units * CU);
+            s.tileInfo.push_back(itemBegin); s.tileInfo.push_back(nitems);
+            ++s.nTiles;
+        }
+        units = 0; nitems = 0;
+        slotBegin = (int)s.slotRow.size(); itemBegin = (int)s.items.size();
+    };
+    auto push_units = [&](int rs, int rf, int u0, int nu) {
+        for (int u = u0; u < u0 + nu; ++u)
+            for (int i = 0; i < CU; ++i) {
+                const int al = u * CU + i;
+                s.slotRow.push_back(al < rf ? rs + al : -1);
+                if (al < rf) ++s.validSlots;
+            }
+    };
+    for (int f = 0; f < F; ++f) {
+        const int rs = rowStart[f], rf = rowStart[f + 1] - rs;
+        if (rf <= 0) continue;
+        const int nu = (rf + CU - 1) / CU;
+        const int pairs = nu * (nu + 1) / 2;
+        if (nu <= CMAXU && pairs <= CNT) {
+            // whole fragment in one tile, packed with its neighbours
+            if (units + nu > CMAXU || nitems + pairs > CNT) flush();
+            const int base = units;
+            push_units(rs, rf, 0, nu);
+            for (int u1 = 0; u1 < nu; ++u1)
+                for (int u2 = u1; u2 < nu; ++u2) s.items.push_back((unsigned short)((base + u1) | ((base + u2) << 8)));
+            units += nu; nitems += pairs;
+        } else {
+            // large fragment: one tile per pair of 16-unit slices (si <= sj)
+            flush();
+            const int ns = (nu + CSLICE - 1) / CSLICE;
+            for (int si = 0; si < ns; ++si)
+                for (int sj = si; sj < ns; ++sj) {
+                    const int ui0 = si * CSLICE, uin = std::min(CSLICE, nu - ui0);
+                    const int uj0 = sj * CSLICE, ujn = std::min(CSLICE, nu - uj0);
+                    push_units(rs, rf, ui0, uin);
+                    if (sj == si) {
+                        for (int u1 = 0; u1 < uin; ++u1)
+                            for (int u2 = u1; u2 < uin; ++u2) s.items.push_back((unsigned short)(u1 | (u2 << 8)));
+                        units = uin; nitems = uin * (uin + 1) / 2;
+                    } else {
+                        push_units(rs, rf, uj0, ujn);
+                        for (int u1 = 0; u1 < uin; ++u1)
+                            for (int u2 = 0; u2 < ujn; ++u2) s.items.push_back((unsigned short)(u1 | ((uin + u2) << 8)));
+                        units = uin + ujn; nitems = uin * ujn;
+                    }
+                    flush();
+                }
+        }
+    }
+    flush();
+}
+
+// ------------------------------------------------------------------------------------------
+// device
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(CNT, 2)
+contract_panels_kernel(const JacView v, const double *__restrict__ M, const int *__restrict__ siteToU,
+                       const int4 *__restrict__ tileInfo, const int *__restrict__ slotRowG,
+                       const unsigned short *__restrict__ itemsG)
+{
+    extern __shared__ __align__(16) unsigned char csm[];
+    double *Ys = reinterpret_cast<double *>(csm);                    // Ys[o][slot]  Y_p of the tile's rows
+    double *Ps = Ys + CTO * CLD;                                     // Ps[o][slot]  PO of the same rows
+    long long *elM = reinterpret_cast<long long *>(Ps + CTO * CLD);  // [nnz] offset of the panel M_r of element e
+    long long *elC = elM + QCDMET_CONTRACT_MAX_NNZ;                  // [nnz] offset of the row Co[c,:] of element e
+    int *srow = reinterpret_cast<int *>(elC + QCDMET_CONTRACT_MAX_NNZ);   // [CSLOTS] fragment row of the slot or -1
+
+    const int tid = threadIdx.x;
+    const int4 ti = tileInfo[blockIdx.x];            // slotBegin, nSlots, itemBegin, nItems
+    const int pl = blockIdx.y, p = v.colBegin + pl;
+    const int eBeg = v.h1start[p];
+    const int nnz = v.h1start[p + 1] - eBeg;         // <= QCDMET_CONTRACT_MAX_NNZ (checked at plan creation)
+
+    if (tid < CSLOTS) srow[tid] = tid < ti.y ? slotRowG[ti.x + tid] : -1;
+    if (tid < nnz) {
+        elM[tid] = (long long)siteToU[v.h1row[eBeg + tid]] * v.S * v.ldo;
+        elC[tid] = (long long)v.h1col[eBeg + tid] * v.ldo;
+    }
+    const bool active = tid < ti.w;
+    int u1 = 0, u2 = 0;
+    if (active) {
+        const unsigned it = itemsG[ti.z + tid];
+        u1 = it & 0xFF; u2 = it >> 8;
+    }
+    double acc[CU][CU];
+#pragma unroll
+    for (int i = 0; i < CU; ++i)
+#pragma unroll
+        for (int j = 0; j < CU; ++j) acc[i][j] = 0.0;
+    __syncthreads();
+
+    const int so = tid % CTO, sg = tid / CTO;        // staging: orbital lane, slot group
+    for (int o0 = 0; o0 < v.no; o0 += CTO) {
+        const int ow = min(CTO, v.no - o0);
+        if (so < ow) {
+            const int o = o0 + so;
+            for (int s = sg; s < ti.y; s += CNT / CTO) {
+                const int row = srow[s];
+                double y = 0.0, po = 0.0;
+                if (row >= 0) {
+                    const size_t ro = (size_t)row * v.ldo + o;
+                    for (int e = 0; e < nnz; ++e) y = fma(M[elM[e] + ro], v.CoT[elC[e] + o], y);
+                    po = v.PO[ro];
+                }
+                Ys[so * CLD + s] = y;
+                Ps[so * CLD + s] = po;
+            }
+        }
+        __syncthreads();
+        if (active) {
+            const double *y1 = Ys + u1 * CU, *y2 = Ys + u2 * CU, *q1 = Ps + u1 * CU, *q2 = Ps + u2 * CU;
+#pragma unroll 4
+            for (int oo = 0; oo < ow; ++oo) {
+                const int off = oo * CLD;
+                const double2 ya = *reinterpret_cast<const double2 *>(y1 + off), yb = *reinterpret_cast<const double2 *>(y1 + off + 2);
+                const double2 pa = *reinterpret_cast<const double2 *>(q1 + off), pb = *reinterpret_cast<const double2 *>(q1 + off + 2);
+                const double2 yc = *reinterpret_cast<const double2 *>(y2 + off), yd = *reinterpret_cast<const double2 *>(y2 + off + 2);
+                const double2 pc = *reinterpret_cast<const double2 *>(q2 + off), pd = *reinterpret_cast<const double2 *>(q2 + off + 2);
+                const double Y1[CU] = {ya.x, ya.y, yb.x, yb.y}, P1[CU] = {pa.x, pa.y, pb.x, pb.y};
+                const double Y2[CU] = {yc.x, yc.y, yd.x, yd.y}, P2[CU] = {pc.x, pc.y, pd.x, pd.y};
+#pragma unroll
+                for (int i = 0; i < CU; ++i)
+#pragma unroll
+                    for (int j = 0; j < CU; ++j) acc[i][j] = fma(Y1[i], P2[j], fma(P1[i], Y2[j], acc[i][j]));
+            }
+        }
+        __syncthreads();
+    }
+
+    if (!active) return;
+    // the first row of a unit always exists; both units belong to the same fragment
+    const int f = v.rowFrag[srow[u1 * CU]];
+    const int rs = v.rowStart[f], rf = v.rowStart[f + 1] - rs;
+    double *Jp = v.J + (size_t)v.Q * pl + v.qoff[f];
+#pragma unroll
+    for (int i = 0; i < CU; ++i) {
+        const int ra = srow[u1 * CU + i];
+        if (ra < 0) continue;
+        const long long al = ra - rs;
+#pragma unroll
+        for (int j = 0; j < CU; ++j) {
+            const int rb = srow[u2 * CU + j];
+            if (rb < 0 || (u1 == u2 && j < i)) continue;
+            const long long bl = rb - rs;
+            const double val = 2.0 * acc[i][j];
+            Jp[al + rf * bl] = val;
+            Jp[bl + rf * al] = val;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// host: plan, launch
+// ------------------------------------------------------------------------------------------
+int contract_plan_build(ContractPlan **out, int F, const int *rowStart)
+{
+    *out = nullptr;
+    ContractPlan *c = new ContractPlan();
+    contract_schedule_build(F, rowStart, &c->sched);
+    const ContractSchedule &s = c->sched;
+    const size_t nt = std::max<size_t>(s.tileInfo.size(), 4), nsl = std::max<size_t>(s.slotRow.size(), 1),
+                 ni = std::max<size_t>(s.items.size(), 1);
+    if (cudaMalloc((void **)&c->d_tileInfo, nt * sizeof(int)) != cudaSuccess ||
+        cudaMalloc((void **)&c->d_slotRow, nsl * sizeof(int)) != cudaSuccess ||
+        cudaMalloc((void **)&c->d_items, ni * sizeof(unsigned short)) != cudaSuccess) {
+        cudaGetLastError();
+        set_error("cudaMalloc of the contraction schedule failed");
+        contract_plan_free(c);
+        return QCDMET_E_ALLOC;
+    }
+    if (!s.tileInfo.empty())
+        QC_CUDA(cudaMemcpy(c->d_tileInfo, s.tileInfo.data(), s.tileInfo.size() * sizeof(int), cudaMemcpyHostToDevice));
+    if (!s.slotRow.empty())
+        QC_CUDA(cudaMemcpy(c->d_slotRow, s.slotRow.data(), s.slotRow.size() * sizeof(int), cudaMemcpyHostToDevice));
+    if (!s.items.empty())
+        QC_CUDA(cudaMemcpy(c->d_items, s.items.data(), s.items.size() * sizeof(unsigned short), cudaMemcpyHostToDevice));
+    *out = c;
+    return QCDMET_OK;
+}
+
+void contract_plan_free(ContractPlan *c)
+{
+    if (!c) return;
+    cudaFree(c->d_tileInfo); cudaFree(c->d_slotRow); cudaFree(c->d_items);
+    cudaGetLastError();
+    delete c;
+}
+
+int launch_contract_panels(const ContractPlan *c, const JacView &v, const double *M, const int *siteToU,
+                           long long nnzInRange, cudaStream_t st, int *launches, double *flops)
+{
+    *launches = 0;
+    *flops = 0.0;
+    const int ncols = v.colEnd - v.colBegin;
+    const ContractSchedule &s = c->sched;
+    if (ncols <= 0 || s.nTiles == 0) return QCDMET_OK;
+    // per device (function attributes live in the context of the current device): set on every launch
+    QC_CUDA(cudaFuncSetAttribute(contract_panels_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CSMEM));
+    // gridDim.y is limited to 65535: chunk the columns
+    for (int c0 = 0; c0 < ncols; c0 += 32768) {
+        const int nc = std::min(32768, ncols - c0);
+        JacView w = v;
+        w.colBegin = v.colBegin + c0;
+        w.colEnd = w.colBegin + nc;
+        w.J = v.J + (size_t)v.Q * c0;
+        contract_panels_kernel<<<dim3((unsigned)s.nTiles, (unsigned)nc), CNT, CSMEM, st>>>(
+            w, M, siteToU, reinterpret_cast<const int4 *>(c->d_tileInfo), c->d_slotRow, c->d_items);
+        QC_CUDA(cudaGetLastError());
+        *launches += 1;
+    }
+    // executed: 4 FMA-pairs per accumulator element and orbital; Y build 2 flop per element, slot and orbital
+    *flops = (double)ncols * (double)s.items.size() * (CU * CU * 4.0) * v.no +
+             2.0 * (double)nnzInRange * (double)s.validSlots * v.no;
+    return QCDMET_OK;
+}
+
+}  // namespace qcdmet

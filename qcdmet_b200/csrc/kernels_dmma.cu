@@ -107,6 +107,9 @@ struct DmmaArgs {
     const unsigned char *tilePartner;   // [nTiles][AT][RF] slot of the j-th row of the fragment, AT = none (RF of the variant)
     const unsigned char *tileSelf;      // [nTiles][AT]  a_loc | r_f << 4
     const long long *tileQ;             // [nTiles][AT]  qoff[f] + a_loc
+    // panel mode (large fragments): no epilogue, the M panels go to HBM as Mout[(4 comp + r)][row][ldm]
+    double *Mout;
+    int mRows, ldm;
     int nDest;                          // destinations of every Jacobian store (1, or the ranks of a node)
     double *J[QCDMET_MAX_PEERS];        // J[0..nDest): own buffer and peer-mapped buffers (NVLink P2P stores)
 };
@@ -269,7 +272,8 @@ __global__ void sum_subcolumns_kernel(const double *__restrict__ Jsub, const int
 // ------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------
-template <class C>
+// PANEL = true: no epilogue, the M panels go to HBM (factorised path for large fragments, end of this file)
+template <class C, bool PANEL = false>
 __global__ void __launch_bounds__(NTHREADS, 1) jac_dmma_kernel(const DmmaArgs g)
 {
     constexpr int RF = C::RF, NJ = C::NJ, BN = C::BN, PSTRIDE = C::PSTRIDE, NSTRIDE = C::NSTRIDE;
@@ -328,7 +332,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) jac_dmma_kernel(const DmmaArgs g)
             for (int ot = 0; ot < nOt; ++ot) {
                 const double *wsrc = g.Wt + (size_t)ot * nKc * W_STAGE;
                 for (int kc = 0; kc < nKc; ++kc, ++it) {
-                    if (kc == epiAt) {
+                    if (!PANEL && kc == epiAt) {
                         mbar_wait(epiEmpty, (ot & 1) ^ 1);          // every warp is done with tile ot-1's operands
                         mbar_expect_tx(epiFull, C::EPI_BYTES);
                         tma_bulk_g2s(smem_u32(POS), posrc + (size_t)ot * POS_DOUBLES, POS_DOUBLES * 8, epiFull);
@@ -389,6 +393,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) jac_dmma_kernel(const DmmaArgs g)
             if (lane == 0) mbar_arrive(smem_u32(&bars[STAGES + s]));
         }
 
+        if constexpr (PANEL) {
+            // ---- panel mode: store this tile of M_r[a, o] (fragments too large for the on-chip epilogue)
+            double *mbase = g.Mout + (size_t)(comp * RT + warp_m) * g.mRows * g.ldm;
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi) {
+                const int row = trow[mi * 8 + g4];
+                if (row < 0) continue;
+#pragma unroll
+                for (int nj = 0; nj < NJ; ++nj) {
+                    const int o = ot * BN + warp_n * (BN / 2) + nj * 8 + t4 * 2;
+                    if (o < g.ldm)
+                        *reinterpret_cast<double2 *>(mbase + (size_t)row * g.ldm + o) =
+                            make_double2(acc[mi][nj][0], acc[mi][nj][1]);
+                }
+            }
+            continue;
+        }
         // ---- epilogue for this column tile (per warp, no CTA-wide barrier)
         mbar_wait(epiFull, ot & 1);
 #pragma unroll
@@ -442,6 +463,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) jac_dmma_kernel(const DmmaArgs g)
         if (lane == 0) mbar_arrive(epiEmpty);
     }
 
+    if constexpr (PANEL) return;
     // ---- assemble G_p, symmetrise, store the CTA's patches of J
     consumer_sync();
     const double *Ns1 = Ns + 128 * NSTRIDE;
@@ -961,6 +983,7 @@ int launch_jacobian_dmma(DmmaPlanData *d, const JacView &v, cudaStream_t st, int
         a.compSites = d->d_compSites; a.compP = d->d_compP;
         a.compEnt = d->d_compEnt; a.tileRow = d->d_tileRow; a.tilePartner = d->d_tilePartner;
         a.tileSelf = d->d_tileSelf; a.tileQ = d->d_tileQ;
+        a.Mout = nullptr; a.mRows = 0; a.ldm = 0;
         a.nDest = z.nDest;
         for (int r = 0; r < QCDMET_MAX_PEERS; ++r) a.J[r] = z.J[r];
         if (ev0) QC_CUDA(cudaEventRecord(ev0, st));
@@ -1016,6 +1039,209 @@ void dmma_schedule_info(int N, int no, int P, int F, const int *h1start, const i
     info[8] = (int)std::min<long long>(pairs, 2147483647LL);
     info[9] = d.nOt;
     if (why) *why = sc.why;
+}
+
+// ------------------------------------------------------------------------------------------
+// Large fragments / large site groups (polyyne- and sn2-like shapes, the compat full response):
+// the same DMMA main loop produces the panels M_r[a, o] for every site r that occurs as an element
+// row and every fragment row a, stored to HBM (panel mode above); kernels_contract.cu then contracts,
+// per perturbation, Y_p[a,o] = sum_{(r,c) in p} M_r[a,o] Co[c,o] with the occupied rows of the same
+// fragment.  2 |sites| S nv no + P no (2 nnz_p S + 4 Q) flop instead of P (2 S nv no + ...).
+// ------------------------------------------------------------------------------------------
+struct FactPlanData {
+    DmmaPlanData sched;                 // components = chunks of 4 used sites, tiles = chunks of 32 rows
+    std::vector<int> siteToU;           // [N] index of the site in the panel array, -1 if it has no element row
+    int *d_siteToU = nullptr;
+    double *d_M = nullptr;              // [4 nComp][S][ldo]
+    size_t mDoubles = 0;
+    int numSites = 0;
+    ContractPlan *contract = nullptr;
+};
+
+namespace {
+int fact_pick_nj(int no)
+{
+    int best = 8;
+    long long bestPad = -1;
+    for (int nj : {8, 6, 4}) {
+        const long long bn = 16 * nj, pad = (no + bn - 1) / bn * bn;
+        if (bestPad < 0 || pad < bestPad) { bestPad = pad; best = nj; }
+    }
+    return best;
+}
+int fact_count_sites(int N, int P, const int *h1start, const int *h1row, std::vector<int> *siteToU)
+{
+    std::vector<char> used(N, 0);
+    for (int k = 0; k < h1start[P]; ++k) used[h1row[k]] = 1;
+    int n = 0;
+    if (siteToU) siteToU->assign(N, -1);
+    for (int i = 0; i < N; ++i)
+        if (used[i]) { if (siteToU) (*siteToU)[i] = n; ++n; }
+    return n;
+}
+}  // namespace
+
+bool fact_eligible(int P, const int *h1start, std::string *why)
+{
+    for (int p = 0; p < P; ++p)
+        if (h1start[p + 1] - h1start[p] > QCDMET_CONTRACT_MAX_NNZ) {
+            if (why) *why = "a perturbation has more than 64 elements";
+            return false;
+        }
+    return true;
+}
+
+// device memory the factorised path needs on top of the plan's own buffers
+size_t fact_plan_bytes(int N, int no, int P, int S, const int *h1start, const int *h1row)
+{
+    const int sites = fact_count_sites(N, P, h1start, h1row, nullptr);
+    const size_t nComp = (sites + RT - 1) / RT, nTiles = (S + AT - 1) / AT, nv = N - no;
+    const size_t nKc = (nv + KC - 1) / KC, bn = 16 * fact_pick_nj(no), nOt = (no + bn - 1) / bn;
+    const size_t ldo = round_up(no, 16);
+    return (nComp * RT * (size_t)S * ldo + nOt * nKc * KC * bn + nTiles * nKc * PV_STAGE + nComp * nKc * CV_STAGE) * 8;
+}
+
+int fact_plan_build(FactPlanData **out, int N, int no, int P, int F, const int *rowStart, int ldo,
+                    const int *h1start, const int *h1row)
+{
+    *out = nullptr;
+    const int S = F > 0 ? rowStart[F] : 0;
+    FactPlanData *f = new FactPlanData();
+    DmmaPlanData &d = f->sched;
+    d.N = N; d.no = no; d.nv = N - no; d.P = P; d.S = S;
+    f->numSites = fact_count_sites(N, P, h1start, h1row, &f->siteToU);
+    d.nComp = (f->numSites + RT - 1) / RT;
+    d.compSites.assign((size_t)d.nComp * RT, -1);
+    for (int i = 0; i < N; ++i)
+        if (f->siteToU[i] >= 0) d.compSites[f->siteToU[i]] = i;
+    d.compNumSites.assign(d.nComp, RT);
+    if (f->numSites % RT) d.compNumSites.back() = f->numSites % RT;
+    d.nTiles = (S + AT - 1) / AT;
+    d.tileRow.assign((size_t)d.nTiles * AT, -1);
+    for (int a = 0; a < S; ++a) d.tileRow[a] = a;
+    d.tileNumRows.assign(d.nTiles, AT);
+    if (S % AT) d.tileNumRows.back() = S % AT;
+    // tables the panel mode loads but never uses (kept at their legal size for Cfg<4, .>)
+    d.rf = 4;
+    d.compP.assign((size_t)d.nComp * MAXP, -1);
+    d.compEnt.assign((size_t)d.nComp * MAXP * MAXE, 0xFF);
+    d.tilePartner.assign((size_t)d.nTiles * AT * 4, (unsigned char)AT);
+    d.tileSelf.assign((size_t)d.nTiles * AT, 0);
+    d.tileQ.assign((size_t)d.nTiles * AT, 0);
+    d.nj = fact_pick_nj(no);
+    d.nKc = (d.nv + KC - 1) / KC;
+    d.nOt = (d.no + d.bn() - 1) / d.bn();
+    f->mDoubles = (size_t)d.nComp * RT * S * ldo;
+    int rc = QCDMET_OK;
+    if ((rc = upload(&d.d_compSites, d.compSites)) || (rc = upload(&d.d_compP, d.compP)) ||
+        (rc = upload(&d.d_compEnt, d.compEnt)) || (rc = upload(&d.d_tileRow, d.tileRow)) ||
+        (rc = upload(&d.d_tilePartner, d.tilePartner)) || (rc = upload(&d.d_tileSelf, d.tileSelf)) ||
+        (rc = upload(&d.d_tileQ, d.tileQ)) || (rc = upload(&f->d_siteToU, f->siteToU)) ||
+        (rc = contract_plan_build(&f->contract, F, rowStart))) {
+        fact_plan_free(f);
+        return rc;
+    }
+    d.work.clear();
+    for (int t = 0; t < d.nTiles; ++t)
+        for (int c = 0; c < d.nComp; ++c) d.work.push_back(make_int2(c, t));
+    const size_t one = 1;
+    if (cudaMalloc((void **)&d.d_work, std::max(d.work.size(), one) * sizeof(int2)) != cudaSuccess ||
+        cudaMalloc((void **)&d.d_Wt, std::max((size_t)d.nOt * d.nKc * d.wStage(), one) * 8) != cudaSuccess ||
+        cudaMalloc((void **)&d.d_PVt, std::max((size_t)d.nTiles * d.nKc * PV_STAGE, one) * 8) != cudaSuccess ||
+        cudaMalloc((void **)&d.d_CVt, std::max((size_t)d.nComp * d.nKc * CV_STAGE, one) * 8) != cudaSuccess ||
+        cudaMalloc((void **)&f->d_M, std::max(f->mDoubles, one) * 8) != cudaSuccess) {
+        cudaGetLastError();
+        set_error("cudaMalloc of the factorised-path buffers failed (%zu bytes for the panels M)", f->mDoubles * 8);
+        fact_plan_free(f);
+        return QCDMET_E_ALLOC;
+    }
+    if (!d.work.empty())
+        QC_CUDA(cudaMemcpy(d.d_work, d.work.data(), d.work.size() * sizeof(int2), cudaMemcpyHostToDevice));
+    *out = f;
+    return QCDMET_OK;
+}
+
+void fact_plan_free(FactPlanData *f)
+{
+    if (!f) return;
+    DmmaPlanData &d = f->sched;
+    cudaFree(d.d_compSites); cudaFree(d.d_compP); cudaFree(d.d_compEnt); cudaFree(d.d_tileRow);
+    cudaFree(d.d_tilePartner); cudaFree(d.d_tileSelf); cudaFree(d.d_tileQ); cudaFree(d.d_work);
+    cudaFree(d.d_Wt); cudaFree(d.d_PVt); cudaFree(d.d_CVt);
+    cudaFree(f->d_siteToU); cudaFree(f->d_M);
+    cudaGetLastError();
+    contract_plan_free(f->contract);
+    delete f;
+}
+
+// tiled operands of the panel kernel from the current orbitals
+int fact_prepare_orbitals(FactPlanData *f, const JacView &v, cudaStream_t st)
+{
+    DmmaPlanData *d = &f->sched;
+    const long long wt = (long long)d->nOt * d->nKc * d->wStage(), pvt = (long long)d->nTiles * d->nKc * PV_STAGE,
+                    cvt = (long long)d->nComp * d->nKc * CV_STAGE;
+    if (wt > 0) {
+        build_wt_kernel<<<(unsigned)((wt + 255) / 256), 256, 0, st>>>(v.e, v.no, v.nv, d->nKc, d->bn(), wt, d->d_Wt);
+        QC_CUDA(cudaGetLastError());
+    }
+    if (pvt > 0) {
+        build_pvt_kernel<<<(unsigned)((pvt + 255) / 256), 256, 0, st>>>(v.PV, v.ldv, v.nv, d->nKc, d->d_tileRow, pvt, d->d_PVt);
+        QC_CUDA(cudaGetLastError());
+    }
+    if (cvt > 0) {
+        build_cvt_kernel<<<(unsigned)((cvt + 255) / 256), 256, 0, st>>>(v.CvT, v.ldv, v.nv, d->nKc, d->d_compSites, cvt, d->d_CVt);
+        QC_CUDA(cudaGetLastError());
+    }
+    return QCDMET_OK;
+}
+
+// Panels M for all element-row sites (DMMA main loop, panel mode), then the per-perturbation contraction
+// for the columns of the view.  ev0/ev1 bracket both kernels.  The panels are recomputed by every call
+// (2 |sites| S nv no flop: a column-sharded rank repeats them, they are never served from a cache).
+int launch_jacobian_factorised(FactPlanData *f, const JacView &v, long long nnzInRange, cudaStream_t st,
+                               int *launches, double *flops, cudaEvent_t ev0, cudaEvent_t ev1)
+{
+    DmmaPlanData *d = &f->sched;
+    *launches = 0;
+    *flops = 0.0;
+    if (v.colEnd <= v.colBegin || v.S == 0) return QCDMET_OK;
+    if (ev0) QC_CUDA(cudaEventRecord(ev0, st));
+    if (!d->work.empty()) {
+        DmmaArgs a;
+        memset(&a, 0, sizeof(a));
+        a.nKc = d->nKc; a.nOt = d->nOt;
+        a.Wt = d->d_Wt; a.PVt = d->d_PVt; a.CVt = d->d_CVt;
+        a.work = d->d_work;
+        a.compSites = d->d_compSites; a.compP = d->d_compP; a.compEnt = d->d_compEnt;
+        a.tileRow = d->d_tileRow; a.tilePartner = d->d_tilePartner; a.tileSelf = d->d_tileSelf; a.tileQ = d->d_tileQ;
+        a.Mout = f->d_M; a.mRows = v.S; a.ldm = v.ldo;
+        a.nDest = 0;
+        const unsigned grid = (unsigned)d->work.size();
+        int rc = QCDMET_E_STATE;
+        // per device (function attributes live in the context of the current device): set on every launch
+#define QC_LAUNCH_PANEL(NJV)                                                                                  \
+        if (d->nj == NJV) {                                                                                   \
+            using K = Cfg<4, NJV>;                                                                            \
+            QC_CUDA(cudaFuncSetAttribute(jac_dmma_kernel<K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                         K::SMEM_BYTES));                                                     \
+            jac_dmma_kernel<K, true><<<grid, NTHREADS, K::SMEM_BYTES, st>>>(a);                               \
+            rc = QCDMET_OK;                                                                                   \
+        }
+        QC_LAUNCH_PANEL(8) QC_LAUNCH_PANEL(6) QC_LAUNCH_PANEL(4)
+#undef QC_LAUNCH_PANEL
+        QC_CHECK(rc == QCDMET_OK, QCDMET_E_STATE, "no panel kernel variant for nj=%d", d->nj);
+        QC_CUDA(cudaGetLastError());
+        *launches += 1;
+        // useful flops: main loop 2 nv no per (site, row) + one multiply per A element per column tile
+        *flops += (double)f->numSites * (double)v.S * (2.0 * d->nv * d->no + (double)d->nv * d->nOt);
+    }
+    int l2 = 0;
+    double f2 = 0.0;
+    QC_TRY(launch_contract_panels(f->contract, v, f->d_M, f->d_siteToU, nnzInRange, st, &l2, &f2));
+    if (ev1) QC_CUDA(cudaEventRecord(ev1, st));
+    *launches += l2;
+    *flops += f2;
+    return QCDMET_OK;
 }
 
 }  // namespace qcdmet

@@ -12,8 +12,21 @@ from util import GOLDEN, golden_ids, load_golden
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-10
-KERNELS = {"general": _lib.KERNEL_GENERAL, "auto": _lib.KERNEL_AUTO}
-GENERAL, DMMA = _lib.KERNEL_GENERAL, _lib.KERNEL_DMMA
+KERNELS = {"general": _lib.KERNEL_GENERAL, "auto": _lib.KERNEL_AUTO, "factorised": _lib.KERNEL_FACTORISED}
+GENERAL, DMMA, FACT = _lib.KERNEL_GENERAL, _lib.KERNEL_DMMA, _lib.KERNEL_FACTORISED
+
+
+def fact_applies(h1start, nrows):
+    """The factorised path stages <= 64 elements per perturbation and needs a non-empty problem."""
+    return len(h1start) > 1 and nrows > 0 and int(np.diff(h1start).max()) <= 64
+
+
+def expect_fact_refused(*plan_args):
+    plan = _lib.Plan(*plan_args)
+    with pytest.raises(_lib.QcdmetError) as ei:
+        plan.set_kernel(FACT)
+    assert ei.value.code == -1
+    plan.close()
 
 
 def run_plan(w, kernel, from_orbitals=None, cols=None):
@@ -43,8 +56,10 @@ def oracle_jac(w, c, e):
 def test_jacobian_matches_golden(path, kernel):
     """End to end from H0 (cuSOLVER syevd on the device) against the compiled reference's output."""
     g = load_golden(path)
-    plan = _lib.Plan(g["norb"], g["num_pairs"], g["h1start"], g["h1row"], g["h1col"], g["row_start"],
-                     g["rows"], g["row_idx"])
+    args = (g["norb"], g["num_pairs"], g["h1start"], g["h1row"], g["h1col"], g["row_start"], g["rows"], g["row_idx"])
+    if kernel == "factorised" and not fact_applies(g["h1start"], int(g["row_start"][-1])):
+        return expect_fact_refused(*args)
+    plan = _lib.Plan(*args)
     plan.set_kernel(KERNELS[kernel])
     plan.set_h0(g["h0"])
     plan.compute()
@@ -92,7 +107,10 @@ SHAPES = {
 @pytest.mark.parametrize("shape", list(SHAPES))
 def test_jacobian_matches_oracle_on_same_orbitals(shape, kernel):
     w = SHAPES[shape]()
+    if kernel == "factorised" and not fact_applies(w.h1start, w.nrows):
+        return expect_fact_refused(w.norb, w.num_pairs, w.h1start, w.h1row, w.h1col, w.row_start, w.rows, w.row_idx)
     jac, c, e, d, used = run_plan(w, KERNELS[kernel])
+    assert kernel == "auto" or used == KERNELS[kernel]
     ref = oracle_jac(w, c, e)
     assert jac.shape == (w.nresid, w.nterms)
     assert np.abs(jac - ref).max() <= TOL
@@ -121,40 +139,45 @@ DMMA_SHAPES = {
     "tiny_occupied_space": (lambda: wl.make_workload("to", 40, 2, [4] * 10), DMMA, True),
     "truncated_list": (lambda: wl.sweep(160, nterms=333), DMMA, False),      # fragments without perturbations
     "bath_rows_m2": (lambda: wl.make_workload("b2", 44, 20, [2, 2, 1, 2], fit_imp_bath=True), DMMA, False),
-    "frag5_general": (lambda: wl.make_workload("f5", 40, 17, [5, 4, 3]), GENERAL, False),
+    "frag5_factorised": (lambda: wl.make_workload("f5", 40, 17, [5, 4, 3]), FACT, False),
     "ti_split": (lambda: wl.hubbard24(True, l=8), DMMA, False),              # TI list split per cell, columns summed
     "ti_split_bath": (lambda: wl.hubbard24(True, fit_imp_bath=True, l=8), DMMA, False),
     "ti_m2_bath": (lambda: wl.make_workload("ti2", 24, 11, [2] * 12, trans_inv=True, fit_imp_bath=True), DMMA, False),
     "ti_m3": (lambda: wl.make_workload("ti3", 36, 16, [3] * 12, trans_inv=True), DMMA, False),
-    "ti_m5_general": (lambda: wl.make_workload("ti5", 40, 18, [5] * 8, trans_inv=True), GENERAL, False),
+    "ti_m5_factorised": (lambda: wl.make_workload("ti5", 40, 18, [5] * 8, trans_inv=True), FACT, False),
+    "ti_m5_many_elements_general": (lambda: wl.make_workload("ti5g", 200, 90, [5] * 40, trans_inv=True), GENERAL, False),
     "bath_rows_m4": (lambda: wl.make_workload("b4", 44, 20, [4, 4], fit_imp_bath=True), DMMA, False),   # 8-row fragments
     "bath_rows_mixed": (lambda: wl.make_workload("bm", 70, 31, [4, 3, 1, 4, 2, 4, 4, 3], fit_imp_bath=True), DMMA, False),
     "hubbard8x8_bath": (lambda: wl.hubbard24(False, fit_imp_bath=True, l=8), DMMA, False),
     "sweep192_tile96": (lambda: wl.sweep(192), DMMA, True),                  # no = 96: 96-column tiles
-    "frag9_general": (lambda: wl.make_workload("f9", 60, 25, [4, 4, 4, 4, 1], fit_imp_bath=False, nterms=None)
-                      if False else wl.make_workload("f9", 48, 21, [9, 4]), GENERAL, False),
+    "frag9_factorised": (lambda: wl.make_workload("f9", 48, 21, [9, 4]), FACT, False),
+    "bath_rows_m5_factorised": (lambda: wl.make_workload("b5", 44, 20, [5, 3], fit_imp_bath=True), FACT, False),
 }
 
 
 @pytest.mark.parametrize("shape", list(DMMA_SHAPES))
 def test_kernel_selection_and_dmma_parity(shape):
-    """AUTO picks the site-factorised DMMA kernel exactly where its schedule applies (<= 4 coupled
-    sites, <= 4 rows per fragment) and the general kernel elsewhere; both match the oracle."""
+    """AUTO picks the fused DMMA kernel exactly where its schedule applies (<= 4 coupled sites, <= 8 rows
+    per fragment), else the factorised path (site panels + contraction; <= 64 elements per perturbation),
+    else the general kernel; all match the oracle and each other."""
     factory, expect, expect_sym = DMMA_SHAPES[shape]
     w = factory()
     jac, c, e, d, used = run_plan(w, _lib.KERNEL_AUTO)
     assert used == expect
     assert run_plan.last_symmetric == expect_sym
     assert np.abs(jac - oracle_jac(w, c, e)).max() <= TOL
-    if expect == GENERAL:
-        assert np.abs(jac - oracle_jac(w, c, e)).max() <= TOL
+    gen, *_ = run_plan(w, _lib.KERNEL_GENERAL, from_orbitals=(c, e))
+    assert np.abs(jac - gen).max() <= TOL
+    if expect != DMMA:
         plan = _lib.Plan(w.norb, w.num_pairs, w.h1start, w.h1row, w.h1col, w.row_start, w.rows, w.row_idx)
         with pytest.raises(_lib.QcdmetError):
             plan.set_kernel(_lib.KERNEL_DMMA)
         plan.close()
+        if expect == GENERAL:
+            expect_fact_refused(w.norb, w.num_pairs, w.h1start, w.h1row, w.h1col, w.row_start, w.rows, w.row_idx)
     else:
-        gen, *_ = run_plan(w, _lib.KERNEL_GENERAL, from_orbitals=(c, e))
-        assert np.abs(jac - gen).max() <= TOL
+        fact, *_ = run_plan(w, FACT, from_orbitals=(c, e))
+        assert np.abs(jac - fact).max() <= TOL
         nosym, *_ = run_plan(w, _lib.KERNEL_DMMA_NOSYM, from_orbitals=(c, e))
         assert not run_plan.last_symmetric
         assert np.abs(jac - nosym).max() <= 1e-12
@@ -189,11 +212,11 @@ def test_from_given_orbitals_and_column_slices(kernel):
     for lo, hi in ((0, 1), (7, 133), (150, 300), (299, 300), (40, 40)):
         part, *_ = run_plan(w, KERNELS[kernel], from_orbitals=(c, e), cols=(lo, hi))
         assert part.shape == (w.nresid, hi - lo)
-        if kernel == "general" or hi == lo:
+        if kernel in ("general", "factorised") or hi == lo:
             assert np.array_equal(part, full[:, lo:hi])
         else:
             assert np.abs(part - full[:, lo:hi]).max() <= 1e-12
-    if kernel != "general":
+    if kernel == "auto":
         a, *_ = run_plan(w, _lib.KERNEL_DMMA_NOSYM, from_orbitals=(c, e))
         b, *_ = run_plan(w, _lib.KERNEL_DMMA_NOSYM, from_orbitals=(c, e), cols=(7, 133))
         assert np.array_equal(b, a[:, 7:133])
@@ -314,8 +337,8 @@ def test_stateless_entry_points_and_plan_reuse():
 
 
 def test_lists_spanning_the_whole_matrix():
-    """Perturbations with up to 8 elements anywhere in the matrix (+ an empty one): only the general kernel
-    applies; Jacobian and compat full response against the oracle."""
+    """Perturbations with up to 8 elements anywhere in the matrix (+ an empty one): the fused DMMA kernel does
+    not apply; factorised path and general kernel against the oracle."""
     rng = np.random.default_rng(7)
     w = wl.make_workload("rnd", 50, 19, [4, 3, 5, 4, 2], fit_imp_bath=False)
     hs, hr, hc = [0], [], []
@@ -327,9 +350,11 @@ def test_lists_spanning_the_whole_matrix():
     hs.insert(30, hs[29])
     w.h1start, w.h1row, w.h1col = np.array(hs, np.int32), np.array(hr, np.int32), np.array(hc, np.int32)
     jac, c, e, d, used = run_plan(w, _lib.KERNEL_AUTO)
-    assert used == GENERAL
+    assert used == FACT
     assert np.abs(jac - oracle_jac(w, c, e)).max() <= TOL
     assert np.all(jac[:, 29] == 0.0)
+    gen, *_ = run_plan(w, GENERAL, from_orbitals=(c, e))
+    assert np.abs(gen - oracle_jac(w, c, e)).max() <= TOL and np.all(gen[:, 29] == 0.0)
 
 
 def test_degenerate_shapes():
@@ -365,12 +390,79 @@ def test_sn2_like_sampled_columns():
     w = wl.sn2_like()
     e, c = ro.eigh_sorted(w.h0)
     cols = (2000, 2040)
-    part, *_ = run_plan(w, _lib.KERNEL_AUTO, from_orbitals=(c, e), cols=cols)
+    part, _, _, _, used = run_plan(w, _lib.KERNEL_AUTO, from_orbitals=(c, e), cols=cols)
+    assert used == FACT
     s = w.h1start
     ref = ro.jacobian_from_orbitals(c, e, w.num_pairs, s[cols[0]:cols[1] + 1] - s[cols[0]],
                                     w.h1row[s[cols[0]]:s[cols[1]]], w.h1col[s[cols[0]]:s[cols[1]]],
                                     w.row_start, w.rows, w.row_idx)
     assert np.abs(part - ref).max() <= TOL
+
+
+def _column_sample_oracle(w, c, e, cols):
+    s = w.h1start
+    out = []
+    for p in cols:
+        out.append(ro.jacobian_from_orbitals(c, e, w.num_pairs, s[p:p + 2] - s[p], w.h1row[s[p]:s[p + 1]],
+                                             w.h1col[s[p]:s[p + 1]], w.row_start, w.rows, w.row_idx)[:, 0])
+    return np.stack(out, axis=1)
+
+
+@pytest.mark.parametrize("shape", ["frag100_sliced", "frag89_90_bath", "ragged_units"])
+def test_factorised_large_fragments(shape):
+    """Fragments beyond one contraction tile (> 88 rows: pairs of 16-unit slices), ragged last units,
+    projector rows: factorised path against the oracle on sampled columns, against the general kernel
+    on all columns, exact block symmetry, column ranges bit-identical to the full run."""
+    w = {"frag100_sliced": lambda: wl.make_workload("big", 150, 60, [100, 30, 9]),
+         "frag89_90_bath": lambda: wl.make_workload("bb", 120, 50, [45, 3], fit_imp_bath=True),
+         "ragged_units": lambda: wl.make_workload("rg", 131, 57, [89, 1, 6, 2, 7, 13, 5]),
+         }[shape]()
+    e, c = ro.eigh_sorted(w.h0)
+    plan = _lib.Plan(w.norb, w.num_pairs, w.h1start, w.h1row, w.h1col, w.row_start, w.rows, w.row_idx)
+    plan.set_orbitals(c, e)
+    plan.compute()
+    jac = plan.jacobian()
+    assert plan.kernel_used == FACT and plan.launches == 2       # panel kernel + contraction
+    cols = np.unique(np.linspace(0, w.nterms - 1, 24).astype(int))
+    assert np.abs(jac[:, cols] - _column_sample_oracle(w, c, e, cols)).max() <= TOL
+    off = 0
+    for a, b in zip(w.row_start[:-1], w.row_start[1:]):
+        r = int(b - a)
+        blk = jac[off:off + r * r].reshape(r, r, -1, order="F")
+        assert np.array_equal(blk, blk.transpose(1, 0, 2))
+        off += r * r
+    lo, hi = w.nterms // 3, w.nterms // 3 + 17
+    plan.set_columns(lo, hi)
+    plan.compute()
+    assert plan.launches == 2
+    assert np.array_equal(plan.jacobian(), jac[:, lo:hi])
+    plan.set_columns(0, w.nterms)
+    plan.set_h0(w.h0 + 0.01 * np.eye(w.norb))
+    plan.compute()
+    assert plan.launches == 2
+    assert np.abs(plan.jacobian() - jac).max() <= 1e-9          # a constant shift does not change the response
+    plan.set_kernel(GENERAL)
+    plan.set_orbitals(c, e)
+    plan.compute()
+    assert plan.kernel_used == GENERAL
+    assert np.abs(plan.jacobian() - jac).max() <= TOL
+    plan.close()
+
+
+def test_compat_full_response_sliced():
+    """rhf_response at a size where the single all-sites fragment (N = 100: 25 units) is cut into slice pairs."""
+    w = wl.sweep(100, nterms=23)
+    lib = _lib.load()
+    n, p = w.norb, w.nterms
+    h0 = np.array(w.h0.reshape(n * n), dtype=np.float64)
+    out = np.ones(n * n * p)
+    assert lib.rhf_response(n, p, w.num_pairs, _lib._ptr(w.h1start), _lib._ptr(w.h1row), _lib._ptr(w.h1col),
+                            _lib._ptr(h0), _lib._ptr(out)) == 0, lib.qcdmet_last_error()
+    resp, one_rdm = ro.rhf_response(n, p, w.num_pairs, w.h1start, w.h1row, w.h1col, w.h0)
+    out = out.reshape(p, n, n)
+    assert np.abs(out - resp).max() <= TOL
+    assert np.array_equal(out, out.transpose(0, 2, 1))
+    assert np.abs(h0.reshape(n, n) - one_rdm).max() <= TOL
 
 
 def test_invariants_large():
