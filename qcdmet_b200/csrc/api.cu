@@ -226,6 +226,7 @@ int ensure_fact(qcdmet_plan *p)
     p->fact_ok = false;
     if (p->P == 0 || p->S == 0) { p->fact_why = "empty problem"; return QCDMET_OK; }
     if (!fact_eligible(p->P, p->h1start.data(), &p->fact_why)) return QCDMET_OK;
+    if ((long long)p->S * p->ldo >= (1LL << 31)) { p->fact_why = "fragment rows x occupied orbitals >= 2^31"; return QCDMET_OK; }
     size_t freeB = 0, totalB = 0;
     QC_CUDA(cudaMemGetInfo(&freeB, &totalB));
     const size_t need = fact_plan_bytes(p->N, p->no, p->P, p->S, p->h1start.data(), p->h1row.data());

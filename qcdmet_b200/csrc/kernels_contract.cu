@@ -24,8 +24,14 @@ constexpr int CSLICE = 16;             // units per slice of a large fragment
 constexpr int CSLOTS = CU * CMAXU;     // row slots per tile
 constexpr int CNT = 256;               // threads per CTA = max items per tile
 constexpr int CTO = 32;                // occupied orbitals per staged chunk
-constexpr int CLD = CSLOTS + 2;        // smem row stride in doubles (even: 16 B aligned units)
+// Shared-memory layout of a staged chunk: Ys[o][col(u) + i], col(u) = 4 u + 2 (u / 4).  The 16 B pad after
+// every 4 units makes the LDS.128 of 8 consecutive units hit 8 distinct 16 B bank groups, and the row
+// stride CLD = 2 (mod 16) doubles makes the staging stores (lanes = 8 orbital pairs x 4 rows) conflict-free.
+constexpr int CLD = CSLOTS + 2 * (CMAXU / 4) + 2;      // 146
+constexpr int CSTG = 4;                // staging tasks in flight per warp (loads issued before they are used)
 constexpr int CSMEM = 2 * CTO * CLD * 8 + CSLOTS * 4 + QCDMET_CONTRACT_MAX_NNZ * 16;
+__device__ __forceinline__ int unit_col(int u) { return CU * u + 2 * (u >> 2); }
+__device__ __forceinline__ double2 ld2(const double *p) { return *reinterpret_cast<const double2 *>(p); }
 }  // namespace
 
 // ------------------------------------------------------------------------------------------
@@ -97,7 +103,7 @@ void contract_schedule_build(int F, const int *rowStart, ContractSchedule *out)
 // device
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(CNT, 2)
-contract_panels_kernel(const JacView v, const double *__restrict__ M, const int *__restrict__ siteToU,
+contract_panels_kernel(const JacView v, const double *__restrict__ M, const int *__restrict__ elU,
                        const int4 *__restrict__ tileInfo, const int *__restrict__ slotRowG,
                        const unsigned short *__restrict__ itemsG)
 {
@@ -116,7 +122,7 @@ contract_panels_kernel(const JacView v, const double *__restrict__ M, const int 
 
     if (tid < CSLOTS) srow[tid] = tid < ti.y ? slotRowG[ti.x + tid] : -1;
     if (tid < nnz) {
-        elM[tid] = (long long)siteToU[v.h1row[eBeg + tid]] * v.S * v.ldo;
+        elM[tid] = (long long)elU[eBeg + tid] * v.S * v.ldo;      // elU[k] = panel index of the site h1row[k]
         elC[tid] = (long long)v.h1col[eBeg + tid] * v.ldo;
     }
     const bool active = tid < ti.w;
@@ -132,26 +138,55 @@ contract_panels_kernel(const JacView v, const double *__restrict__ M, const int 
         for (int j = 0; j < CU; ++j) acc[i][j] = 0.0;
     __syncthreads();
 
-    const int so = tid % CTO, sg = tid / CTO;        // staging: orbital lane, slot group
+    // staging: a task = (unit, 16-orbital half of the chunk); lane = (row of the unit, orbital pair), so a warp
+    // load is 4 rows x 128 contiguous bytes and a warp store is conflict-free; CSTG tasks are in flight
+    const int warp = tid >> 5, lane = tid & 31;
+    const int ls = lane & 3, lo = lane >> 2;
+    const int nUnits = ti.y / CU;
     for (int o0 = 0; o0 < v.no; o0 += CTO) {
         const int ow = min(CTO, v.no - o0);
-        if (so < ow) {
-            const int o = o0 + so;
-            for (int s = sg; s < ti.y; s += CNT / CTO) {
-                const int row = srow[s];
-                double y = 0.0, po = 0.0;
-                if (row >= 0) {
-                    const size_t ro = (size_t)row * v.ldo + o;
-                    for (int e = 0; e < nnz; ++e) y = fma(M[elM[e] + ro], v.CoT[elC[e] + o], y);
-                    po = v.PO[ro];
+        const int nh = (v.ldo - o0 > 16) ? 2 : 1;    // halves that exist (ldo is a multiple of 16, panels zero padded)
+        const int ntask = nUnits * nh;
+        for (int t0 = warp; t0 < ntask; t0 += (CNT / 32) * CSTG) {
+            double2 m0[CSTG], m1[CSTG], po[CSTG];
+            int dst[CSTG], oc[CSTG];
+            int src[CSTG];                           // offset of (row, orbital pair) in a panel (S ldo < 2^31); < 0: padding slot
+#pragma unroll
+            for (int k = 0; k < CSTG; ++k) {
+                const int t = t0 + (CNT / 32) * k;
+                const int u = nh == 2 ? (t >> 1) : t, h = nh == 2 ? (t & 1) : 0;
+                const int row = t < ntask ? srow[u * CU + ls] : -1;
+                oc[k] = 16 * h + 2 * lo;
+                dst[k] = t < ntask ? oc[k] * CLD + unit_col(u) + ls : -1;
+                src[k] = row >= 0 ? row * v.ldo + o0 + oc[k] : -1;
+                m0[k] = m1[k] = po[k] = make_double2(0.0, 0.0);
+                if (src[k] >= 0) {
+                    po[k] = ld2(v.PO + src[k]);
+                    if (nnz > 0) m0[k] = ld2(M + elM[0] + src[k]);
+                    if (nnz > 1) m1[k] = ld2(M + elM[1] + src[k]);
                 }
-                Ys[so * CLD + s] = y;
-                Ps[so * CLD + s] = po;
+            }
+#pragma unroll
+            for (int k = 0; k < CSTG; ++k) {
+                if (dst[k] < 0) continue;
+                double2 y = make_double2(0.0, 0.0);
+                if (src[k] >= 0) {
+                    const int o = o0 + oc[k];
+                    if (nnz > 0) { const double2 c = ld2(v.CoT + elC[0] + o); y.x = m0[k].x * c.x; y.y = m0[k].y * c.y; }
+                    if (nnz > 1) { const double2 c = ld2(v.CoT + elC[1] + o); y.x = fma(m1[k].x, c.x, y.x); y.y = fma(m1[k].y, c.y, y.y); }
+                    for (int e = 2; e < nnz; ++e) {
+                        const double2 m = ld2(M + elM[e] + src[k]), c = ld2(v.CoT + elC[e] + o);
+                        y.x = fma(m.x, c.x, y.x); y.y = fma(m.y, c.y, y.y);
+                    }
+                }
+                Ys[dst[k]] = y.x; Ys[dst[k] + CLD] = y.y;
+                Ps[dst[k]] = po[k].x; Ps[dst[k] + CLD] = po[k].y;
             }
         }
         __syncthreads();
         if (active) {
-            const double *y1 = Ys + u1 * CU, *y2 = Ys + u2 * CU, *q1 = Ps + u1 * CU, *q2 = Ps + u2 * CU;
+            const int c1 = unit_col(u1), c2 = unit_col(u2);
+            const double *y1 = Ys + c1, *y2 = Ys + c2, *q1 = Ps + c1, *q2 = Ps + c2;
 #pragma unroll 4
             for (int oo = 0; oo < ow; ++oo) {
                 const int off = oo * CLD;
@@ -229,7 +264,7 @@ void contract_plan_free(ContractPlan *c)
     delete c;
 }
 
-int launch_contract_panels(const ContractPlan *c, const JacView &v, const double *M, const int *siteToU,
+int launch_contract_panels(const ContractPlan *c, const JacView &v, const double *M, const int *elU,
                            long long nnzInRange, cudaStream_t st, int *launches, double *flops)
 {
     *launches = 0;
@@ -247,7 +282,7 @@ int launch_contract_panels(const ContractPlan *c, const JacView &v, const double
         w.colEnd = w.colBegin + nc;
         w.J = v.J + (size_t)v.Q * c0;
         contract_panels_kernel<<<dim3((unsigned)s.nTiles, (unsigned)nc), CNT, CSMEM, st>>>(
-            w, M, siteToU, reinterpret_cast<const int4 *>(c->d_tileInfo), c->d_slotRow, c->d_items);
+            w, M, elU, reinterpret_cast<const int4 *>(c->d_tileInfo), c->d_slotRow, c->d_items);
         QC_CUDA(cudaGetLastError());
         *launches += 1;
     }

@@ -1051,7 +1051,8 @@ void dmma_schedule_info(int N, int no, int P, int F, const int *h1start, const i
 struct FactPlanData {
     DmmaPlanData sched;                 // components = chunks of 4 used sites, tiles = chunks of 32 rows
     std::vector<int> siteToU;           // [N] index of the site in the panel array, -1 if it has no element row
-    int *d_siteToU = nullptr;
+    std::vector<int> elU;               // [nnz] panel index of the row site of every element
+    int *d_elU = nullptr;
     double *d_M = nullptr;              // [4 nComp][S][ldo]
     size_t mDoubles = 0;
     int numSites = 0;
@@ -1114,6 +1115,8 @@ int fact_plan_build(FactPlanData **out, int N, int no, int P, int F, const int *
     d.compSites.assign((size_t)d.nComp * RT, -1);
     for (int i = 0; i < N; ++i)
         if (f->siteToU[i] >= 0) d.compSites[f->siteToU[i]] = i;
+    f->elU.resize(h1start[P]);
+    for (int k = 0; k < h1start[P]; ++k) f->elU[k] = f->siteToU[h1row[k]];
     d.compNumSites.assign(d.nComp, RT);
     if (f->numSites % RT) d.compNumSites.back() = f->numSites % RT;
     d.nTiles = (S + AT - 1) / AT;
@@ -1136,7 +1139,7 @@ int fact_plan_build(FactPlanData **out, int N, int no, int P, int F, const int *
     if ((rc = upload(&d.d_compSites, d.compSites)) || (rc = upload(&d.d_compP, d.compP)) ||
         (rc = upload(&d.d_compEnt, d.compEnt)) || (rc = upload(&d.d_tileRow, d.tileRow)) ||
         (rc = upload(&d.d_tilePartner, d.tilePartner)) || (rc = upload(&d.d_tileSelf, d.tileSelf)) ||
-        (rc = upload(&d.d_tileQ, d.tileQ)) || (rc = upload(&f->d_siteToU, f->siteToU)) ||
+        (rc = upload(&d.d_tileQ, d.tileQ)) || (rc = upload(&f->d_elU, f->elU)) ||
         (rc = contract_plan_build(&f->contract, F, rowStart))) {
         fact_plan_free(f);
         return rc;
@@ -1168,7 +1171,7 @@ void fact_plan_free(FactPlanData *f)
     cudaFree(d.d_compSites); cudaFree(d.d_compP); cudaFree(d.d_compEnt); cudaFree(d.d_tileRow);
     cudaFree(d.d_tilePartner); cudaFree(d.d_tileSelf); cudaFree(d.d_tileQ); cudaFree(d.d_work);
     cudaFree(d.d_Wt); cudaFree(d.d_PVt); cudaFree(d.d_CVt);
-    cudaFree(f->d_siteToU); cudaFree(f->d_M);
+    cudaFree(f->d_elU); cudaFree(f->d_M);
     cudaGetLastError();
     contract_plan_free(f->contract);
     delete f;
@@ -1237,7 +1240,7 @@ int launch_jacobian_factorised(FactPlanData *f, const JacView &v, long long nnzI
     }
     int l2 = 0;
     double f2 = 0.0;
-    QC_TRY(launch_contract_panels(f->contract, v, f->d_M, f->d_siteToU, nnzInRange, st, &l2, &f2));
+    QC_TRY(launch_contract_panels(f->contract, v, f->d_M, f->d_elU, nnzInRange, st, &l2, &f2));
     if (ev1) QC_CUDA(cudaEventRecord(ev1, st));
     *launches += l2;
     *flops += f2;
