@@ -23,13 +23,16 @@ constexpr int CMAXU = 32;              // units per tile
 constexpr int CSLICE = 16;             // units per slice of a large fragment
 constexpr int CSLOTS = CU * CMAXU;     // row slots per tile
 constexpr int CNT = 256;               // threads per CTA = max items per tile
-constexpr int CTO = 32;                // occupied orbitals per staged chunk
+constexpr int CTO = 16;                // occupied orbitals per staged chunk
+constexpr int CCB = 8;                 // columns per CTA (consecutive, pipelined through the same two buffers)
+constexpr int CTASK = CMAXU / (CNT / 32);   // staging tasks (units) per warp and chunk: 4
+constexpr int CMAXE = QCDMET_CONTRACT_MAX_NNZ;
 // Shared-memory layout of a staged chunk: Ys[o][col(u) + i], col(u) = 4 u + 2 (u / 4).  The 16 B pad after
 // every 4 units makes the LDS.128 of 8 consecutive units hit 8 distinct 16 B bank groups, and the row
 // stride CLD = 2 (mod 16) doubles makes the staging stores (lanes = 8 orbital pairs x 4 rows) conflict-free.
 constexpr int CLD = CSLOTS + 2 * (CMAXU / 4) + 2;      // 146
-constexpr int CSTG = 4;                // staging tasks in flight per warp (loads issued before they are used)
-constexpr int CSMEM = 2 * CTO * CLD * 8 + CSLOTS * 4 + QCDMET_CONTRACT_MAX_NNZ * 16;
+constexpr int CBUF = CTO * CLD;                        // doubles per staged array
+constexpr int CSMEM = 4 * CBUF * 8 + CCB * CMAXE * 16 + CCB * 4 + CSLOTS * 4;
 __device__ __forceinline__ int unit_col(int u) { return CU * u + 2 * (u >> 2); }
 __device__ __forceinline__ double2 ld2(const double *p) { return *reinterpret_cast<const double2 *>(p); }
 }  // namespace
@@ -102,28 +105,38 @@ void contract_schedule_build(int F, const int *rowStart, ContractSchedule *out)
 // ------------------------------------------------------------------------------------------
 // device
 // ------------------------------------------------------------------------------------------
+// One CTA = (tile, batch of CCB consecutive columns).  The (column, 16-orbital chunk) pairs of the batch run
+// through two shared-memory buffers: the global loads of pair it+1 are issued into registers before the
+// FMA loop of pair it and committed to the other buffer after it (one barrier per pair), so the L2 latency
+// of the panels hides behind the arithmetic and only the first chunk of a CTA is exposed.
 __global__ void __launch_bounds__(CNT, 2)
 contract_panels_kernel(const JacView v, const double *__restrict__ M, const int *__restrict__ elU,
                        const int4 *__restrict__ tileInfo, const int *__restrict__ slotRowG,
                        const unsigned short *__restrict__ itemsG)
 {
     extern __shared__ __align__(16) unsigned char csm[];
-    double *Ys = reinterpret_cast<double *>(csm);                    // Ys[o][slot]  Y_p of the tile's rows
-    double *Ps = Ys + CTO * CLD;                                     // Ps[o][slot]  PO of the same rows
-    long long *elM = reinterpret_cast<long long *>(Ps + CTO * CLD);  // [nnz] offset of the panel M_r of element e
-    long long *elC = elM + QCDMET_CONTRACT_MAX_NNZ;                  // [nnz] offset of the row Co[c,:] of element e
-    int *srow = reinterpret_cast<int *>(elC + QCDMET_CONTRACT_MAX_NNZ);   // [CSLOTS] fragment row of the slot or -1
+    double *Ys = reinterpret_cast<double *>(csm);                    // Ys[buf][o][col]  Y_p of the tile's rows
+    double *Ps = Ys + 2 * CBUF;                                      // Ps[buf][o][col]  PO of the same rows
+    long long *elM = reinterpret_cast<long long *>(Ps + 2 * CBUF);   // [CCB][CMAXE] offset of the panel M_r of element e
+    long long *elC = elM + CCB * CMAXE;                              // [CCB][CMAXE] offset of the row Co[c,:] of element e
+    int *nnzs = reinterpret_cast<int *>(elC + CCB * CMAXE);          // [CCB] elements of the column
+    int *srow = nnzs + CCB;                                          // [CSLOTS] fragment row of the slot or -1
 
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int4 ti = tileInfo[blockIdx.x];            // slotBegin, nSlots, itemBegin, nItems
-    const int pl = blockIdx.y, p = v.colBegin + pl;
-    const int eBeg = v.h1start[p];
-    const int nnz = v.h1start[p + 1] - eBeg;         // <= QCDMET_CONTRACT_MAX_NNZ (checked at plan creation)
+    const int pl0 = blockIdx.y * CCB;                // first local column of the batch
+    const int ncb = min(CCB, v.colEnd - v.colBegin - pl0);
 
     if (tid < CSLOTS) srow[tid] = tid < ti.y ? slotRowG[ti.x + tid] : -1;
-    if (tid < nnz) {
-        elM[tid] = (long long)elU[eBeg + tid] * v.S * v.ldo;      // elU[k] = panel index of the site h1row[k]
-        elC[tid] = (long long)v.h1col[eBeg + tid] * v.ldo;
+    for (int i = tid; i < ncb * CMAXE; i += CNT) {
+        const int cb = i / CMAXE, e = i % CMAXE;
+        const int p = v.colBegin + pl0 + cb;
+        const int eb = v.h1start[p], n = v.h1start[p + 1] - eb;   // n <= CMAXE (checked at plan creation)
+        if (e == 0) nnzs[cb] = n;
+        if (e < n) {
+            elM[i] = (long long)elU[eb + e] * v.S * v.ldo;        // elU[k] = panel index of the site h1row[k]
+            elC[i] = (long long)v.h1col[eb + e] * v.ldo;
+        }
     }
     const bool active = tid < ti.w;
     int u1 = 0, u2 = 0;
@@ -138,62 +151,84 @@ contract_panels_kernel(const JacView v, const double *__restrict__ M, const int 
         for (int j = 0; j < CU; ++j) acc[i][j] = 0.0;
     __syncthreads();
 
-    // staging: a task = (unit, 16-orbital half of the chunk); lane = (row of the unit, orbital pair), so a warp
-    // load is 4 rows x 128 contiguous bytes and a warp store is conflict-free; CSTG tasks are in flight
-    const int warp = tid >> 5, lane = tid & 31;
+    // staging geometry of this thread (the same for every chunk): task k = unit warp + 8 k; lane = (row of the
+    // unit, orbital pair): a warp load is 4 rows x 128 contiguous bytes, a warp store is conflict-free
     const int ls = lane & 3, lo = lane >> 2;
     const int nUnits = ti.y / CU;
-    for (int o0 = 0; o0 < v.no; o0 += CTO) {
-        const int ow = min(CTO, v.no - o0);
-        const int nh = (v.ldo - o0 > 16) ? 2 : 1;    // halves that exist (ldo is a multiple of 16, panels zero padded)
-        const int ntask = nUnits * nh;
-        for (int t0 = warp; t0 < ntask; t0 += (CNT / 32) * CSTG) {
-            double2 m0[CSTG], m1[CSTG], po[CSTG];
-            int dst[CSTG], oc[CSTG];
-            int src[CSTG];                           // offset of (row, orbital pair) in a panel (S ldo < 2^31); < 0: padding slot
+    int src[CTASK], dst[CTASK];          // offset of (row, orbital pair) in a panel, < 0: padding slot; smem offset, < 0: no unit
 #pragma unroll
-            for (int k = 0; k < CSTG; ++k) {
-                const int t = t0 + (CNT / 32) * k;
-                const int u = nh == 2 ? (t >> 1) : t, h = nh == 2 ? (t & 1) : 0;
-                const int row = t < ntask ? srow[u * CU + ls] : -1;
-                oc[k] = 16 * h + 2 * lo;
-                dst[k] = t < ntask ? oc[k] * CLD + unit_col(u) + ls : -1;
-                src[k] = row >= 0 ? row * v.ldo + o0 + oc[k] : -1;
-                m0[k] = m1[k] = po[k] = make_double2(0.0, 0.0);
-                if (src[k] >= 0) {
-                    po[k] = ld2(v.PO + src[k]);
-                    if (nnz > 0) m0[k] = ld2(M + elM[0] + src[k]);
-                    if (nnz > 1) m1[k] = ld2(M + elM[1] + src[k]);
-                }
-            }
+    for (int k = 0; k < CTASK; ++k) {
+        const int u = warp + (CNT / 32) * k;
+        const int row = u < nUnits ? srow[u * CU + ls] : -1;
+        src[k] = row >= 0 ? row * v.ldo + 2 * lo : -1;           // S ldo < 2^31 (checked at plan creation)
+        dst[k] = u < nUnits ? 2 * lo * CLD + unit_col(u) + ls : -1;
+    }
+    const int c1 = unit_col(u1), c2 = unit_col(u2);
+    // the first row of a unit always exists; both units of an item belong to the same fragment
+    int f = 0, rs = 0, rf = 0;
+    if (active) {
+        f = v.rowFrag[srow[u1 * CU]];
+        rs = v.rowStart[f];
+        rf = v.rowStart[f + 1] - rs;
+    }
+
+    const int nChunks = (v.no + CTO - 1) / CTO;      // every chunk lies inside the zero-padded ldo (multiple of 16)
+    const int nIt = ncb * nChunks;
+    double2 m0[CTASK], m1[CTASK], po[CTASK];
+
+    auto issue = [&](int cb, int o0) {               // global loads of one (column, chunk) pair -> registers
+        const int nnz = nnzs[cb];
+        const long long e0 = nnz > 0 ? elM[cb * CMAXE] : 0, e1 = nnz > 1 ? elM[cb * CMAXE + 1] : 0;
 #pragma unroll
-            for (int k = 0; k < CSTG; ++k) {
-                if (dst[k] < 0) continue;
-                double2 y = make_double2(0.0, 0.0);
-                if (src[k] >= 0) {
-                    const int o = o0 + oc[k];
-                    if (nnz > 0) { const double2 c = ld2(v.CoT + elC[0] + o); y.x = m0[k].x * c.x; y.y = m0[k].y * c.y; }
-                    if (nnz > 1) { const double2 c = ld2(v.CoT + elC[1] + o); y.x = fma(m1[k].x, c.x, y.x); y.y = fma(m1[k].y, c.y, y.y); }
-                    for (int e = 2; e < nnz; ++e) {
-                        const double2 m = ld2(M + elM[e] + src[k]), c = ld2(v.CoT + elC[e] + o);
-                        y.x = fma(m.x, c.x, y.x); y.y = fma(m.y, c.y, y.y);
-                    }
-                }
-                Ys[dst[k]] = y.x; Ys[dst[k] + CLD] = y.y;
-                Ps[dst[k]] = po[k].x; Ps[dst[k] + CLD] = po[k].y;
+        for (int k = 0; k < CTASK; ++k) {
+            m0[k] = m1[k] = po[k] = make_double2(0.0, 0.0);
+            if (src[k] >= 0) {
+                po[k] = ld2(v.PO + src[k] + o0);
+                if (nnz > 0) m0[k] = ld2(M + e0 + src[k] + o0);
+                if (nnz > 1) m1[k] = ld2(M + e1 + src[k] + o0);
             }
         }
-        __syncthreads();
+    };
+    auto commit = [&](int cb, int o0, int buf) {     // registers -> Y, PO chunk in shared memory
+        const int nnz = nnzs[cb];
+        const long long *eM = elM + cb * CMAXE, *eC = elC + cb * CMAXE;
+        double *ys = Ys + buf * CBUF, *ps = Ps + buf * CBUF;
+        const int o = o0 + 2 * lo;
+#pragma unroll
+        for (int k = 0; k < CTASK; ++k) {
+            if (dst[k] < 0) continue;
+            double2 y = make_double2(0.0, 0.0);
+            if (src[k] >= 0) {
+                if (nnz > 0) { const double2 c = ld2(v.CoT + eC[0] + o); y.x = m0[k].x * c.x; y.y = m0[k].y * c.y; }
+                if (nnz > 1) { const double2 c = ld2(v.CoT + eC[1] + o); y.x = fma(m1[k].x, c.x, y.x); y.y = fma(m1[k].y, c.y, y.y); }
+                for (int e = 2; e < nnz; ++e) {      // longer lists (translation-invariant, arbitrary CSR): not prefetched
+                    const double2 m = ld2(M + eM[e] + src[k] + o0), c = ld2(v.CoT + eC[e] + o);
+                    y.x = fma(m.x, c.x, y.x); y.y = fma(m.y, c.y, y.y);
+                }
+            }
+            ys[dst[k]] = y.x; ys[dst[k] + CLD] = y.y;
+            ps[dst[k]] = po[k].x; ps[dst[k] + CLD] = po[k].y;
+        }
+    };
+
+    issue(0, 0);
+    commit(0, 0, 0);
+    __syncthreads();
+    int cb = 0, ch = 0;                              // the pair being computed
+    for (int it = 0; it < nIt; ++it) {
+        const int buf = it & 1;
+        int cbn = cb, chn = ch + 1;                  // the pair being fetched
+        if (chn == nChunks) { chn = 0; ++cbn; }
+        if (it + 1 < nIt) issue(cbn, chn * CTO);
         if (active) {
-            const int c1 = unit_col(u1), c2 = unit_col(u2);
-            const double *y1 = Ys + c1, *y2 = Ys + c2, *q1 = Ps + c1, *q2 = Ps + c2;
+            const int ow = min(CTO, v.no - ch * CTO);
+            const double *y1 = Ys + buf * CBUF + c1, *y2 = Ys + buf * CBUF + c2;
+            const double *q1 = Ps + buf * CBUF + c1, *q2 = Ps + buf * CBUF + c2;
 #pragma unroll 4
             for (int oo = 0; oo < ow; ++oo) {
                 const int off = oo * CLD;
-                const double2 ya = *reinterpret_cast<const double2 *>(y1 + off), yb = *reinterpret_cast<const double2 *>(y1 + off + 2);
-                const double2 pa = *reinterpret_cast<const double2 *>(q1 + off), pb = *reinterpret_cast<const double2 *>(q1 + off + 2);
-                const double2 yc = *reinterpret_cast<const double2 *>(y2 + off), yd = *reinterpret_cast<const double2 *>(y2 + off + 2);
-                const double2 pc = *reinterpret_cast<const double2 *>(q2 + off), pd = *reinterpret_cast<const double2 *>(q2 + off + 2);
+                const double2 ya = ld2(y1 + off), yb = ld2(y1 + off + 2), pa = ld2(q1 + off), pb = ld2(q1 + off + 2);
+                const double2 yc = ld2(y2 + off), yd = ld2(y2 + off + 2), pc = ld2(q2 + off), pd = ld2(q2 + off + 2);
                 const double Y1[CU] = {ya.x, ya.y, yb.x, yb.y}, P1[CU] = {pa.x, pa.y, pb.x, pb.y};
                 const double Y2[CU] = {yc.x, yc.y, yd.x, yd.y}, P2[CU] = {pc.x, pc.y, pd.x, pd.y};
 #pragma unroll
@@ -201,29 +236,29 @@ contract_panels_kernel(const JacView v, const double *__restrict__ M, const int 
 #pragma unroll
                     for (int j = 0; j < CU; ++j) acc[i][j] = fma(Y1[i], P2[j], fma(P1[i], Y2[j], acc[i][j]));
             }
+            if (ch == nChunks - 1) {
+                // column done: J[a,b] and J[b,a] from the same register, then restart the sums
+                double *Jp = v.J + (size_t)v.Q * (pl0 + cb) + v.qoff[f];
+#pragma unroll
+                for (int i = 0; i < CU; ++i) {
+                    const int ra = srow[u1 * CU + i];
+#pragma unroll
+                    for (int j = 0; j < CU; ++j) {
+                        const int rb = srow[u2 * CU + j];
+                        if (ra >= 0 && rb >= 0 && !(u1 == u2 && j < i)) {
+                            const long long al = ra - rs, bl = rb - rs;
+                            const double val = 2.0 * acc[i][j];
+                            Jp[al + rf * bl] = val;
+                            Jp[bl + rf * al] = val;
+                        }
+                        acc[i][j] = 0.0;
+                    }
+                }
+            }
         }
+        if (it + 1 < nIt) commit(cbn, chn * CTO, buf ^ 1);
         __syncthreads();
-    }
-
-    if (!active) return;
-    // the first row of a unit always exists; both units belong to the same fragment
-    const int f = v.rowFrag[srow[u1 * CU]];
-    const int rs = v.rowStart[f], rf = v.rowStart[f + 1] - rs;
-    double *Jp = v.J + (size_t)v.Q * pl + v.qoff[f];
-#pragma unroll
-    for (int i = 0; i < CU; ++i) {
-        const int ra = srow[u1 * CU + i];
-        if (ra < 0) continue;
-        const long long al = ra - rs;
-#pragma unroll
-        for (int j = 0; j < CU; ++j) {
-            const int rb = srow[u2 * CU + j];
-            if (rb < 0 || (u1 == u2 && j < i)) continue;
-            const long long bl = rb - rs;
-            const double val = 2.0 * acc[i][j];
-            Jp[al + rf * bl] = val;
-            Jp[bl + rf * al] = val;
-        }
+        cb = cbn; ch = chn;
     }
 }
 
@@ -274,14 +309,15 @@ int launch_contract_panels(const ContractPlan *c, const JacView &v, const double
     if (ncols <= 0 || s.nTiles == 0) return QCDMET_OK;
     // per device (function attributes live in the context of the current device): set on every launch
     QC_CUDA(cudaFuncSetAttribute(contract_panels_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CSMEM));
-    // gridDim.y is limited to 65535: chunk the columns
-    for (int c0 = 0; c0 < ncols; c0 += 32768) {
-        const int nc = std::min(32768, ncols - c0);
+    // gridDim.y is limited to 65535 batches of CCB columns: chunk the columns
+    const int chunk = 65535 * CCB;
+    for (int c0 = 0; c0 < ncols; c0 += chunk) {
+        const int nc = std::min(chunk, ncols - c0);
         JacView w = v;
         w.colBegin = v.colBegin + c0;
         w.colEnd = w.colBegin + nc;
         w.J = v.J + (size_t)v.Q * c0;
-        contract_panels_kernel<<<dim3((unsigned)s.nTiles, (unsigned)nc), CNT, CSMEM, st>>>(
+        contract_panels_kernel<<<dim3((unsigned)s.nTiles, (unsigned)((nc + CCB - 1) / CCB)), CNT, CSMEM, st>>>(
             w, M, elU, reinterpret_cast<const int4 *>(c->d_tileInfo), c->d_slotRow, c->d_items);
         QC_CUDA(cudaGetLastError());
         *launches += 1;
