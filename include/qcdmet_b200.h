@@ -189,10 +189,11 @@ int qcdmet_schedule_info(int Norb, int Nterms, int numPairs, const int *H1start,
                          const int *H1col, int Nfrag, const int *rowStart, const int *rowIdx, int *info);
 
 /* Host-only: the tile schedule of the factorised path's contraction kernel (csrc/kernels_contract.cu) for
- * these fragment rows.  counts[3] = { tiles, row slots, items }; the arrays may be NULL (size query), else
- * tileInfo[4 * tiles] = { slotBegin, nSlots, itemBegin, nItems } per tile, slotRow[slots] = fragment row of
- * the slot or -1, items[] = u1 | u2 << 8 (pair of 4-row units of one fragment, u1 <= u2, tile-local). */
-int qcdmet_contract_schedule(int Nfrag, const int *rowStart, int *counts, int *tileInfo, int *slotRow, int *items);
+ * these fragment rows.  counts[3] = { tiles, row slots, strip-table entries (24 per tile) }; the arrays may be
+ * NULL (size query), else tileInfo[4 * tiles] = { slotBegin, nSlots, first strip-table entry, nStrips } per
+ * tile, slotRow[slots] = fragment row of the slot or -1, strips[tile][warp 0..7][0..2] = b1 | b2 << 8 | n2 << 16
+ * (8-row blocks of one fragment, tile-local: block b1 against blocks b2 .. b2 + n2 - 1, b2 >= b1) or -1. */
+int qcdmet_contract_schedule(int Nfrag, const int *rowStart, int *counts, int *tileInfo, int *slotRow, int *strips);
 
 const char *qcdmet_last_error(void);
 const char *qcdmet_version(void);

@@ -136,19 +136,26 @@ def schedule_info(norb, num_pairs, h1start, h1row, h1col, row_start, row_idx=Non
 
 
 def contract_schedule(row_start):
-    """Host-only: tiles of the factorised path's contraction kernel -> list of (slot_rows, [(u1, u2), ...])."""
+    """Host-only: tiles of the factorised path's contraction kernel ->
+    list of (slot_rows, strips[8 warps][<= 3] of (b1, b2, n2))."""
     lib = load()
     rs = as_i32(row_start)
     counts = np.zeros(3, dtype=np.int32)
     check(lib.qcdmet_contract_schedule(len(rs) - 1, _ptr(rs), _ptr(counts), None, None, None))
     tile_info = np.zeros(4 * max(int(counts[0]), 1), dtype=np.int32)
     slot_row = np.zeros(max(int(counts[1]), 1), dtype=np.int32)
-    items = np.zeros(max(int(counts[2]), 1), dtype=np.int32)
-    check(lib.qcdmet_contract_schedule(len(rs) - 1, _ptr(rs), _ptr(counts), _ptr(tile_info), _ptr(slot_row), _ptr(items)))
+    strips = np.zeros(max(int(counts[2]), 1), dtype=np.int32)
+    check(lib.qcdmet_contract_schedule(len(rs) - 1, _ptr(rs), _ptr(counts), _ptr(tile_info), _ptr(slot_row), _ptr(strips)))
+    assert int(counts[2]) == 24 * int(counts[0])
     tiles = []
     for t in range(int(counts[0])):
-        sb, ns, ib, ni = (int(x) for x in tile_info[4 * t:4 * t + 4])
-        tiles.append((slot_row[sb:sb + ns].copy(), [(int(i) & 0xFF, int(i) >> 8) for i in items[ib:ib + ni]]))
+        sb, ns, tb, nstr = (int(x) for x in tile_info[4 * t:4 * t + 4])
+        per_warp = []
+        for w in range(8):
+            ent = [int(x) for x in strips[tb + 3 * w:tb + 3 * w + 3] if x >= 0]
+            per_warp.append([(x & 0xFF, (x >> 8) & 0xFF, x >> 16) for x in ent])
+        assert sum(len(p) for p in per_warp) == nstr
+        tiles.append((slot_row[sb:sb + ns].copy(), per_warp))
     return tiles
 
 

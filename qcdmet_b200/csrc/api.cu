@@ -275,7 +275,7 @@ int qcdmet_schedule_info(int Norb, int Nterms, int numPairs, const int *H1start,
     return QCDMET_OK;
 }
 
-int qcdmet_contract_schedule(int Nfrag, const int *rowStart, int *counts, int *tileInfo, int *slotRow, int *items)
+int qcdmet_contract_schedule(int Nfrag, const int *rowStart, int *counts, int *tileInfo, int *slotRow, int *strips)
 {
     QC_CHECK(counts != nullptr, QCDMET_E_ARG, "counts is NULL");
     QC_CHECK(Nfrag >= 0 && (Nfrag == 0 || (rowStart != nullptr && rowStart[0] == 0)), QCDMET_E_ARG,
@@ -284,10 +284,10 @@ int qcdmet_contract_schedule(int Nfrag, const int *rowStart, int *counts, int *t
         QC_CHECK(rowStart[f + 1] >= rowStart[f], QCDMET_E_ARG, "rowStart not monotone at %d", f);
     ContractSchedule sc;
     contract_schedule_build(Nfrag, rowStart, &sc);
-    counts[0] = sc.nTiles; counts[1] = (int)sc.slotRow.size(); counts[2] = (int)sc.items.size();
+    counts[0] = sc.nTiles; counts[1] = (int)sc.slotRow.size(); counts[2] = (int)sc.strips.size();
     if (tileInfo) std::copy(sc.tileInfo.begin(), sc.tileInfo.end(), tileInfo);
     if (slotRow) std::copy(sc.slotRow.begin(), sc.slotRow.end(), slotRow);
-    if (items) std::copy(sc.items.begin(), sc.items.end(), items);
+    if (strips) std::copy(sc.strips.begin(), sc.strips.end(), strips);
     return QCDMET_OK;
 }
 

@@ -104,17 +104,18 @@ void dmma_schedule_info(int N, int no, int P, int F, const int *h1start, const i
 
 // kernels_contract.cu: per-perturbation contraction of the site panels (factorised path)
 #define QCDMET_CONTRACT_MAX_NNZ 64      // elements per perturbation the contraction kernel stages
+#define QCDMET_CONTRACT_STRIPS_PER_WARP 3
 struct ContractSchedule {               // host-built, see kernels_contract.cu
     int nTiles = 0;
     long long validSlots = 0;           // row slots that hold a fragment row (flop count)
-    std::vector<int> tileInfo;          // [nTiles][4] slotBegin, nSlots, itemBegin, nItems
-    std::vector<int> slotRow;           // fragment row of every slot, -1 = padding of a ragged unit
-    std::vector<unsigned short> items;  // unit pair of the tile: u1 | u2 << 8
+    long long blockPairs = 0;           // 8 x 8 block pairs over all tiles (flop count)
+    std::vector<int> tileInfo;          // [nTiles][4] slotBegin, nSlots, first entry in strips, nStrips
+    std::vector<int> slotRow;           // fragment row of every slot, -1 = padding of a ragged block
+    std::vector<int> strips;            // [nTiles][8 warps][3] b1 | b2 << 8 | n2 << 16 (tile-local blocks), -1 = none
 };
 struct ContractPlan {
     ContractSchedule sched;
-    int *d_tileInfo = nullptr, *d_slotRow = nullptr;
-    unsigned short *d_items = nullptr;
+    int *d_tileInfo = nullptr, *d_slotRow = nullptr, *d_strips = nullptr;
 };
 void contract_schedule_build(int F, const int *rowStart, ContractSchedule *out);
 int contract_plan_build(ContractPlan **out, int F, const int *rowStart);

@@ -5,11 +5,13 @@
 // that occurs as an element row.  Per column p (lib/rhf_response.cc:82-108 restricted to fragment blocks):
 //   Y_p[a,o]      = sum_{(r,c) in H1_p} M_r[a,o] Co[c,o]
 //   J[(f;a,b),p]  = 2 sum_o ( Y_p[a,o] PO[b,o] + PO[a,o] Y_p[b,o] )        a, b rows of fragment f
-// FP64 FMA pipe (same issue rate as DMMA on B200).  Work decomposition, built once per plan on the host:
-//   unit  = 4 consecutive rows of one fragment (last unit of a fragment may be ragged)
-//   item  = unordered pair of units (u1 <= u2) of the same fragment: a 4 x 4 register tile, one thread
-//   tile  = <= 32 units (128 row slots) and <= 256 items: whole small fragments packed together, or
-//           a pair of 16-unit slices of a large fragment.  One CTA per (tile, column).
+// a symmetric rank-2k update per fragment, on the FP64 tensor pipe (DMMA.8x8x4).  Work decomposition,
+// built once per plan on the host:
+//   block = 8 consecutive rows of one fragment (the last block of a fragment may be ragged)
+//   strip = (block b1; up to 4 consecutive blocks b2 >= b1 of the same fragment): the A fragments of b1 are
+//           loaded once per k-step and serve all pairs of the strip; 2 DMMA per pair and k-step
+//   tile  = <= 16 blocks (128 row slots) and <= 24 strips, at most 3 per warp: whole fragments packed
+//           together, or a pair of 8-block slices of a large fragment.  One CTA = (tile, 8 consecutive columns).
 // Every (a,b) of every block has exactly one owner and J[a,b], J[b,a] are stored from the same register:
 // no atomics, blocks exactly symmetric, run-to-run bit-reproducible.
 #include "common.cuh"
@@ -18,23 +20,30 @@
 namespace qcdmet {
 
 namespace {
-constexpr int CU = 4;                  // rows per unit
-constexpr int CMAXU = 32;              // units per tile
-constexpr int CSLICE = 16;             // units per slice of a large fragment
-constexpr int CSLOTS = CU * CMAXU;     // row slots per tile
-constexpr int CNT = 256;               // threads per CTA = max items per tile
-constexpr int CTO = 16;                // occupied orbitals per staged chunk
-constexpr int CCB = 8;                 // columns per CTA (consecutive, pipelined through the same two buffers)
-constexpr int CTASK = CMAXU / (CNT / 32);   // staging tasks (units) per warp and chunk: 4
+constexpr int CB8 = 8;                 // rows per block
+constexpr int CMAXB = 16;              // blocks per tile
+constexpr int CSLICE = 8;              // blocks per slice of a large fragment
+constexpr int CSLOTS = CB8 * CMAXB;    // row slots per tile
+constexpr int CNT = 256;               // threads per CTA
+constexpr int CWARPS = CNT / 32;
+constexpr int CMAXS = QCDMET_CONTRACT_STRIPS_PER_WARP;
+constexpr int CMAXN2 = 4;              // block pairs per strip
+constexpr int CTO = 32;                // occupied orbitals per staged chunk
+// Shared-memory layout of a staged chunk: Ys[slot][o], row stride CLD = 4 (mod 16) doubles: the 8 rows x 4
+// orbitals of a DMMA operand fragment (LDS.64, half-warp = 4 rows x 4 orbitals) and the staging stores
+// (STS.128, quarter-warp = 4 rows x 2 orbital pairs) both touch every bank once.
+constexpr int CLD = CTO + 4;           // 36
+constexpr int CBUF = CSLOTS * CLD;     // doubles per staged array
+constexpr int CCB = 8;                 // columns per CTA
+constexpr int CSTG = 3;                // staging tasks in flight per warp (loads issued before they are used)
 constexpr int CMAXE = QCDMET_CONTRACT_MAX_NNZ;
-// Shared-memory layout of a staged chunk: Ys[o][col(u) + i], col(u) = 4 u + 2 (u / 4).  The 16 B pad after
-// every 4 units makes the LDS.128 of 8 consecutive units hit 8 distinct 16 B bank groups, and the row
-// stride CLD = 2 (mod 16) doubles makes the staging stores (lanes = 8 orbital pairs x 4 rows) conflict-free.
-constexpr int CLD = CSLOTS + 2 * (CMAXU / 4) + 2;      // 146
-constexpr int CBUF = CTO * CLD;                        // doubles per staged array
-constexpr int CSMEM = 4 * CBUF * 8 + CCB * CMAXE * 16 + CCB * 4 + CSLOTS * 4;
-__device__ __forceinline__ int unit_col(int u) { return CU * u + 2 * (u >> 2); }
+constexpr int CSMEM = 2 * CBUF * 8 + CCB * CMAXE * 16 + CCB * 4 + CSLOTS * 4;
 __device__ __forceinline__ double2 ld2(const double *p) { return *reinterpret_cast<const double2 *>(p); }
+__device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double b)
+{
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+        : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
 }  // namespace
 
 // ------------------------------------------------------------------------------------------
@@ -43,57 +52,78 @@ __device__ __forceinline__ double2 ld2(const double *p) { return *reinterpret_ca
 void contract_schedule_build(int F, const int *rowStart, ContractSchedule *out)
 {
     ContractSchedule &s = *out;
-    s.tileInfo.clear(); s.slotRow.clear(); s.items.clear();
-    s.nTiles = 0; s.validSlots = 0;
-    int units = 0, nitems = 0, slotBegin = 0, itemBegin = 0;
+    s.tileInfo.clear(); s.slotRow.clear(); s.strips.clear();
+    s.nTiles = 0; s.validSlots = 0; s.blockPairs = 0;
+    struct Strip { int b1, b2, n2; };
+    std::vector<Strip> cur;            // strips of the tile under construction (tile-local block indices)
+    int blocks = 0, slotBegin = 0;
     auto flush = [&]() {
-        if (units > 0) {
-            s.tileInfo.push_back(slotBegin); s.tileInfo.push_back(units * CU);
-            s.tileInfo.push_back(itemBegin); s.tileInfo.push_back(nitems);
+        if (blocks > 0) {
+            // longest strips first, each to the least loaded warp that still has a free slot
+            std::vector<int> order(cur.size());
+            for (size_t i = 0; i < order.size(); ++i) order[i] = (int)i;
+            std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cur[a].n2 > cur[b].n2; });
+            int load[CWARPS] = {0}, cnt[CWARPS] = {0};
+            std::vector<int> tab(CWARPS * CMAXS, -1);
+            for (int i : order) {
+                int best = -1;
+                for (int w = 0; w < CWARPS; ++w)
+                    if (cnt[w] < CMAXS && (best < 0 || load[w] < load[best])) best = w;
+                tab[best * CMAXS + cnt[best]++] = cur[i].b1 | (cur[i].b2 << 8) | (cur[i].n2 << 16);
+                load[best] += cur[i].n2;
+                s.blockPairs += cur[i].n2;
+            }
+            s.tileInfo.push_back(slotBegin); s.tileInfo.push_back(blocks * CB8);
+            s.tileInfo.push_back((int)s.strips.size()); s.tileInfo.push_back((int)cur.size());
+            s.strips.insert(s.strips.end(), tab.begin(), tab.end());
             ++s.nTiles;
         }
-        units = 0; nitems = 0;
-        slotBegin = (int)s.slotRow.size(); itemBegin = (int)s.items.size();
+        cur.clear();
+        blocks = 0;
+        slotBegin = (int)s.slotRow.size();
     };
-    auto push_units = [&](int rs, int rf, int u0, int nu) {
-        for (int u = u0; u < u0 + nu; ++u)
-            for (int i = 0; i < CU; ++i) {
-                const int al = u * CU + i;
+    auto push_blocks = [&](int rs, int rf, int b0, int nb) {
+        for (int b = b0; b < b0 + nb; ++b)
+            for (int i = 0; i < CB8; ++i) {
+                const int al = b * CB8 + i;
                 s.slotRow.push_back(al < rf ? rs + al : -1);
                 if (al < rf) ++s.validSlots;
             }
     };
+    // strips covering the pairs (a0 + x, c0 + y), x < na, y < nc (y >= x only when diag)
+    auto add_strips = [&](int a0, int na, int c0, int nc, bool diag, std::vector<Strip> *dst) {
+        for (int x = 0; x < na; ++x)
+            for (int y = diag ? x : 0; y < nc; y += CMAXN2)
+                dst->push_back({a0 + x, c0 + y, std::min(CMAXN2, nc - y)});
+    };
     for (int f = 0; f < F; ++f) {
         const int rs = rowStart[f], rf = rowStart[f + 1] - rs;
         if (rf <= 0) continue;
-        const int nu = (rf + CU - 1) / CU;
-        const int pairs = nu * (nu + 1) / 2;
-        if (nu <= CMAXU && pairs <= CNT) {
+        const int nb = (rf + CB8 - 1) / CB8;
+        std::vector<Strip> mine;
+        if (nb <= CMAXB) add_strips(0, nb, 0, nb, true, &mine);
+        if (nb <= CMAXB && (int)mine.size() <= CWARPS * CMAXS) {
             // whole fragment in one tile, packed with its neighbours
-            if (units + nu > CMAXU || nitems + pairs > CNT) flush();
-            const int base = units;
-            push_units(rs, rf, 0, nu);
-            for (int u1 = 0; u1 < nu; ++u1)
-                for (int u2 = u1; u2 < nu; ++u2) s.items.push_back((unsigned short)((base + u1) | ((base + u2) << 8)));
-            units += nu; nitems += pairs;
+            if (blocks + nb > CMAXB || cur.size() + mine.size() > (size_t)(CWARPS * CMAXS)) flush();
+            for (const Strip &st : mine) cur.push_back({st.b1 + blocks, st.b2 + blocks, st.n2});
+            push_blocks(rs, rf, 0, nb);
+            blocks += nb;
         } else {
-            // large fragment: one tile per pair of 16-unit slices (si <= sj)
+            // large fragment: one tile per pair of 8-block slices (si <= sj)
             flush();
-            const int ns = (nu + CSLICE - 1) / CSLICE;
+            const int ns = (nb + CSLICE - 1) / CSLICE;
             for (int si = 0; si < ns; ++si)
                 for (int sj = si; sj < ns; ++sj) {
-                    const int ui0 = si * CSLICE, uin = std::min(CSLICE, nu - ui0);
-                    const int uj0 = sj * CSLICE, ujn = std::min(CSLICE, nu - uj0);
-                    push_units(rs, rf, ui0, uin);
+                    const int bi0 = si * CSLICE, bin = std::min(CSLICE, nb - bi0);
+                    const int bj0 = sj * CSLICE, bjn = std::min(CSLICE, nb - bj0);
+                    push_blocks(rs, rf, bi0, bin);
                     if (sj == si) {
-                        for (int u1 = 0; u1 < uin; ++u1)
-                            for (int u2 = u1; u2 < uin; ++u2) s.items.push_back((unsigned short)(u1 | (u2 << 8)));
-                        units = uin; nitems = uin * (uin + 1) / 2;
+                        add_strips(0, bin, 0, bin, true, &cur);
+                        blocks = bin;
                     } else {
-                        push_units(rs, rf, uj0, ujn);
-                        for (int u1 = 0; u1 < uin; ++u1)
-                            for (int u2 = 0; u2 < ujn; ++u2) s.items.push_back((unsigned short)(u1 | ((uin + u2) << 8)));
-                        units = uin + ujn; nitems = uin * ujn;
+                        push_blocks(rs, rf, bj0, bjn);
+                        add_strips(0, bin, bin, bjn, false, &cur);
+                        blocks = bin + bjn;
                     }
                     flush();
                 }
@@ -105,25 +135,21 @@ void contract_schedule_build(int F, const int *rowStart, ContractSchedule *out)
 // ------------------------------------------------------------------------------------------
 // device
 // ------------------------------------------------------------------------------------------
-// One CTA = (tile, batch of CCB consecutive columns).  The (column, 16-orbital chunk) pairs of the batch run
-// through two shared-memory buffers: the global loads of pair it+1 are issued into registers before the
-// FMA loop of pair it and committed to the other buffer after it (one barrier per pair), so the L2 latency
-// of the panels hides behind the arithmetic and only the first chunk of a CTA is exposed.
 __global__ void __launch_bounds__(CNT, 2)
 contract_panels_kernel(const JacView v, const double *__restrict__ M, const int *__restrict__ elU,
                        const int4 *__restrict__ tileInfo, const int *__restrict__ slotRowG,
-                       const unsigned short *__restrict__ itemsG)
+                       const int *__restrict__ stripsG)
 {
     extern __shared__ __align__(16) unsigned char csm[];
-    double *Ys = reinterpret_cast<double *>(csm);                    // Ys[buf][o][col]  Y_p of the tile's rows
-    double *Ps = Ys + 2 * CBUF;                                      // Ps[buf][o][col]  PO of the same rows
-    long long *elM = reinterpret_cast<long long *>(Ps + 2 * CBUF);   // [CCB][CMAXE] offset of the panel M_r of element e
+    double *Ys = reinterpret_cast<double *>(csm);                    // Ys[slot][o]  Y_p of the tile's rows
+    double *Ps = Ys + CBUF;                                          // Ps[slot][o]  PO of the same rows
+    long long *elM = reinterpret_cast<long long *>(Ps + CBUF);       // [CCB][CMAXE] offset of the panel M_r of element e
     long long *elC = elM + CCB * CMAXE;                              // [CCB][CMAXE] offset of the row Co[c,:] of element e
     int *nnzs = reinterpret_cast<int *>(elC + CCB * CMAXE);          // [CCB] elements of the column
     int *srow = nnzs + CCB;                                          // [CSLOTS] fragment row of the slot or -1
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int4 ti = tileInfo[blockIdx.x];            // slotBegin, nSlots, itemBegin, nItems
+    const int4 ti = tileInfo[blockIdx.x];            // slotBegin, nSlots, first strip-table entry, nStrips
     const int pl0 = blockIdx.y * CCB;                // first local column of the batch
     const int ncb = min(CCB, v.colEnd - v.colBegin - pl0);
 
@@ -138,127 +164,129 @@ contract_panels_kernel(const JacView v, const double *__restrict__ M, const int 
             elC[i] = (long long)v.h1col[eb + e] * v.ldo;
         }
     }
-    const bool active = tid < ti.w;
-    int u1 = 0, u2 = 0;
-    if (active) {
-        const unsigned it = itemsG[ti.z + tid];
-        u1 = it & 0xFF; u2 = it >> 8;
+    // this warp's strips
+    int sb1[CMAXS], sb2[CMAXS], sn2[CMAXS];
+#pragma unroll
+    for (int s = 0; s < CMAXS; ++s) {
+        const int w = stripsG[ti.z + warp * CMAXS + s];
+        sb1[s] = w < 0 ? 0 : (w & 0xFF);
+        sb2[s] = w < 0 ? 0 : ((w >> 8) & 0xFF);
+        sn2[s] = w < 0 ? 0 : (w >> 16);
     }
-    double acc[CU][CU];
+    double acc[CMAXS][CMAXN2][2];
 #pragma unroll
-    for (int i = 0; i < CU; ++i)
+    for (int s = 0; s < CMAXS; ++s)
 #pragma unroll
-        for (int j = 0; j < CU; ++j) acc[i][j] = 0.0;
+        for (int j = 0; j < CMAXN2; ++j) acc[s][j][0] = acc[s][j][1] = 0.0;
     __syncthreads();
 
-    // staging geometry of this thread (the same for every chunk): task k = unit warp + 8 k; lane = (row of the
-    // unit, orbital pair): a warp load is 4 rows x 128 contiguous bytes, a warp store is conflict-free
+    const int g4 = lane >> 2, t4 = lane & 3;         // DMMA fragment coordinates: row / column, k index
+    // staging: task = (4 consecutive slots, 16-orbital half of the chunk); lane = (slot of the group, orbital
+    // pair): a warp load is 4 rows x 128 contiguous bytes, a warp store is conflict-free
     const int ls = lane & 3, lo = lane >> 2;
-    const int nUnits = ti.y / CU;
-    int src[CTASK], dst[CTASK];          // offset of (row, orbital pair) in a panel, < 0: padding slot; smem offset, < 0: no unit
-#pragma unroll
-    for (int k = 0; k < CTASK; ++k) {
-        const int u = warp + (CNT / 32) * k;
-        const int row = u < nUnits ? srow[u * CU + ls] : -1;
-        src[k] = row >= 0 ? row * v.ldo + 2 * lo : -1;           // S ldo < 2^31 (checked at plan creation)
-        dst[k] = u < nUnits ? 2 * lo * CLD + unit_col(u) + ls : -1;
-    }
-    const int c1 = unit_col(u1), c2 = unit_col(u2);
-    // the first row of a unit always exists; both units of an item belong to the same fragment
-    int f = 0, rs = 0, rf = 0;
-    if (active) {
-        f = v.rowFrag[srow[u1 * CU]];
-        rs = v.rowStart[f];
-        rf = v.rowStart[f + 1] - rs;
-    }
+    const int nGroups = ti.y / 4;
 
-    const int nChunks = (v.no + CTO - 1) / CTO;      // every chunk lies inside the zero-padded ldo (multiple of 16)
-    const int nIt = ncb * nChunks;
-    double2 m0[CTASK], m1[CTASK], po[CTASK];
-
-    auto issue = [&](int cb, int o0) {               // global loads of one (column, chunk) pair -> registers
-        const int nnz = nnzs[cb];
-        const long long e0 = nnz > 0 ? elM[cb * CMAXE] : 0, e1 = nnz > 1 ? elM[cb * CMAXE + 1] : 0;
-#pragma unroll
-        for (int k = 0; k < CTASK; ++k) {
-            m0[k] = m1[k] = po[k] = make_double2(0.0, 0.0);
-            if (src[k] >= 0) {
-                po[k] = ld2(v.PO + src[k] + o0);
-                if (nnz > 0) m0[k] = ld2(M + e0 + src[k] + o0);
-                if (nnz > 1) m1[k] = ld2(M + e1 + src[k] + o0);
-            }
-        }
-    };
-    auto commit = [&](int cb, int o0, int buf) {     // registers -> Y, PO chunk in shared memory
+    for (int cb = 0; cb < ncb; ++cb) {
         const int nnz = nnzs[cb];
         const long long *eM = elM + cb * CMAXE, *eC = elC + cb * CMAXE;
-        double *ys = Ys + buf * CBUF, *ps = Ps + buf * CBUF;
-        const int o = o0 + 2 * lo;
+        for (int o0 = 0; o0 < v.no; o0 += CTO) {
+            const int nh = (v.ldo - o0 > 16) ? 2 : 1;    // halves that exist (ldo is a multiple of 16, panels zero padded)
+            const int ntask = nGroups * nh;
+            for (int t0 = warp; t0 < ntask; t0 += CWARPS * CSTG) {
+                double2 m0[CSTG], m1[CSTG], po[CSTG];
+                int dst[CSTG], src[CSTG];                // smem offset (< 0: no task); panel offset (< 0: padding slot)
 #pragma unroll
-        for (int k = 0; k < CTASK; ++k) {
-            if (dst[k] < 0) continue;
-            double2 y = make_double2(0.0, 0.0);
-            if (src[k] >= 0) {
-                if (nnz > 0) { const double2 c = ld2(v.CoT + eC[0] + o); y.x = m0[k].x * c.x; y.y = m0[k].y * c.y; }
-                if (nnz > 1) { const double2 c = ld2(v.CoT + eC[1] + o); y.x = fma(m1[k].x, c.x, y.x); y.y = fma(m1[k].y, c.y, y.y); }
-                for (int e = 2; e < nnz; ++e) {      // longer lists (translation-invariant, arbitrary CSR): not prefetched
-                    const double2 m = ld2(M + eM[e] + src[k] + o0), c = ld2(v.CoT + eC[e] + o);
-                    y.x = fma(m.x, c.x, y.x); y.y = fma(m.y, c.y, y.y);
+                for (int k = 0; k < CSTG; ++k) {
+                    const int t = t0 + CWARPS * k;
+                    const int grp = nh == 2 ? (t >> 1) : t, h = nh == 2 ? (t & 1) : 0;
+                    const int slot = grp * 4 + ls;
+                    const int row = t < ntask ? srow[slot] : -1;
+                    dst[k] = t < ntask ? slot * CLD + 16 * h + 2 * lo : -1;
+                    src[k] = row >= 0 ? row * v.ldo + o0 + 16 * h + 2 * lo : -1;   // S ldo < 2^31 (checked at plan creation)
+                    m0[k] = m1[k] = po[k] = make_double2(0.0, 0.0);
+                    if (src[k] >= 0) {
+                        po[k] = ld2(v.PO + src[k]);
+                        if (nnz > 0) m0[k] = ld2(M + eM[0] + src[k]);
+                        if (nnz > 1) m1[k] = ld2(M + eM[1] + src[k]);
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < CSTG; ++k) {
+                    if (dst[k] < 0) continue;
+                    double2 y = make_double2(0.0, 0.0);
+                    if (src[k] >= 0) {
+                        const int t = t0 + CWARPS * k;
+                        const int o = o0 + (nh == 2 ? 16 * (t & 1) : 0) + 2 * lo;
+                        if (nnz > 0) { const double2 c = ld2(v.CoT + eC[0] + o); y.x = m0[k].x * c.x; y.y = m0[k].y * c.y; }
+                        if (nnz > 1) { const double2 c = ld2(v.CoT + eC[1] + o); y.x = fma(m1[k].x, c.x, y.x); y.y = fma(m1[k].y, c.y, y.y); }
+                        for (int e = 2; e < nnz; ++e) {      // longer lists (translation-invariant, arbitrary CSR)
+                            const double2 m = ld2(M + eM[e] + src[k]), c = ld2(v.CoT + eC[e] + o);
+                            y.x = fma(m.x, c.x, y.x); y.y = fma(m.y, c.y, y.y);
+                        }
+                    }
+                    *reinterpret_cast<double2 *>(Ys + dst[k]) = y;
+                    *reinterpret_cast<double2 *>(Ps + dst[k]) = po[k];
                 }
             }
-            ys[dst[k]] = y.x; ys[dst[k] + CLD] = y.y;
-            ps[dst[k]] = po[k].x; ps[dst[k] + CLD] = po[k].y;
-        }
-    };
-
-    issue(0, 0);
-    commit(0, 0, 0);
-    __syncthreads();
-    int cb = 0, ch = 0;                              // the pair being computed
-    for (int it = 0; it < nIt; ++it) {
-        const int buf = it & 1;
-        int cbn = cb, chn = ch + 1;                  // the pair being fetched
-        if (chn == nChunks) { chn = 0; ++cbn; }
-        if (it + 1 < nIt) issue(cbn, chn * CTO);
-        if (active) {
-            const int ow = min(CTO, v.no - ch * CTO);
-            const double *y1 = Ys + buf * CBUF + c1, *y2 = Ys + buf * CBUF + c2;
-            const double *q1 = Ps + buf * CBUF + c1, *q2 = Ps + buf * CBUF + c2;
-#pragma unroll 4
-            for (int oo = 0; oo < ow; ++oo) {
-                const int off = oo * CLD;
-                const double2 ya = ld2(y1 + off), yb = ld2(y1 + off + 2), pa = ld2(q1 + off), pb = ld2(q1 + off + 2);
-                const double2 yc = ld2(y2 + off), yd = ld2(y2 + off + 2), pc = ld2(q2 + off), pd = ld2(q2 + off + 2);
-                const double Y1[CU] = {ya.x, ya.y, yb.x, yb.y}, P1[CU] = {pa.x, pa.y, pb.x, pb.y};
-                const double Y2[CU] = {yc.x, yc.y, yd.x, yd.y}, P2[CU] = {pc.x, pc.y, pd.x, pd.y};
+            __syncthreads();
+            // k-steps of 4 orbitals; the orbitals of the last step beyond no are zero in the panels
+            const int nk = (min(CTO, v.no - o0) + 3) / 4;
 #pragma unroll
-                for (int i = 0; i < CU; ++i)
+            for (int s = 0; s < CMAXS; ++s) {
+                if (sn2[s] == 0) continue;               // warp-uniform
+                const double *ya = Ys + (sb1[s] * CB8 + g4) * CLD + t4, *pa = Ps + (sb1[s] * CB8 + g4) * CLD + t4;
+                const double *yb = Ys + (sb2[s] * CB8 + g4) * CLD + t4, *pb = Ps + (sb2[s] * CB8 + g4) * CLD + t4;
+                for (int kk = 0; kk < nk; ++kk) {
+                    const double aY = ya[4 * kk], aP = pa[4 * kk];
+                    double bP[CMAXN2], bY[CMAXN2];
 #pragma unroll
-                    for (int j = 0; j < CU; ++j) acc[i][j] = fma(Y1[i], P2[j], fma(P1[i], Y2[j], acc[i][j]));
+                    for (int j = 0; j < CMAXN2; ++j) {
+                        bP[j] = bY[j] = 0.0;
+                        if (j < sn2[s]) {                // warp-uniform
+                            bP[j] = pb[j * CB8 * CLD + 4 * kk];
+                            bY[j] = yb[j * CB8 * CLD + 4 * kk];
+                        }
+                    }
+                    // the two products of a pair go to the same accumulator: issue them n2 DMMAs apart
+#pragma unroll
+                    for (int j = 0; j < CMAXN2; ++j)
+                        if (j < sn2[s]) dmma884(acc[s][j][0], acc[s][j][1], aY, bP[j]);      // Y[b1] PO[b2]^T
+#pragma unroll
+                    for (int j = 0; j < CMAXN2; ++j)
+                        if (j < sn2[s]) dmma884(acc[s][j][0], acc[s][j][1], aP, bY[j]);      // PO[b1] Y[b2]^T
+                }
             }
-            if (ch == nChunks - 1) {
-                // column done: J[a,b] and J[b,a] from the same register, then restart the sums
-                double *Jp = v.J + (size_t)v.Q * (pl0 + cb) + v.qoff[f];
+            __syncthreads();
+        }
+        // column done: J[a,b] and J[b,a] from the same register, then restart the sums.  Accumulator layout of
+        // DMMA.8x8x4: the lane holds D[g4][2 t4] and D[g4][2 t4 + 1].
+        double *Jc = v.J + (size_t)v.Q * (pl0 + cb);
 #pragma unroll
-                for (int i = 0; i < CU; ++i) {
-                    const int ra = srow[u1 * CU + i];
+        for (int s = 0; s < CMAXS; ++s) {
+            if (sn2[s] == 0) continue;
+            // fragment of the strip's rows (the first row of a block always exists)
+            const int f = v.rowFrag[srow[sb1[s] * CB8]];
+            const int rs = v.rowStart[f], rf = v.rowStart[f + 1] - rs;
+            const int ra = srow[sb1[s] * CB8 + g4];
+            double *Jp = Jc + v.qoff[f];
 #pragma unroll
-                    for (int j = 0; j < CU; ++j) {
-                        const int rb = srow[u2 * CU + j];
-                        if (ra >= 0 && rb >= 0 && !(u1 == u2 && j < i)) {
+            for (int j = 0; j < CMAXN2; ++j) {
+                if (j < sn2[s]) {
+                    const bool diag = (sb2[s] + j == sb1[s]);
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int rb = srow[(sb2[s] + j) * CB8 + 2 * t4 + e];
+                        if (ra >= 0 && rb >= 0 && !(diag && 2 * t4 + e < g4)) {
                             const long long al = ra - rs, bl = rb - rs;
-                            const double val = 2.0 * acc[i][j];
+                            const double val = 2.0 * acc[s][j][e];
                             Jp[al + rf * bl] = val;
                             Jp[bl + rf * al] = val;
                         }
-                        acc[i][j] = 0.0;
                     }
                 }
+                acc[s][j][0] = acc[s][j][1] = 0.0;
             }
         }
-        if (it + 1 < nIt) commit(cbn, chn * CTO, buf ^ 1);
-        __syncthreads();
-        cb = cbn; ch = chn;
     }
 }
 
@@ -272,10 +300,10 @@ int contract_plan_build(ContractPlan **out, int F, const int *rowStart)
     contract_schedule_build(F, rowStart, &c->sched);
     const ContractSchedule &s = c->sched;
     const size_t nt = std::max<size_t>(s.tileInfo.size(), 4), nsl = std::max<size_t>(s.slotRow.size(), 1),
-                 ni = std::max<size_t>(s.items.size(), 1);
+                 ni = std::max<size_t>(s.strips.size(), 1);
     if (cudaMalloc((void **)&c->d_tileInfo, nt * sizeof(int)) != cudaSuccess ||
         cudaMalloc((void **)&c->d_slotRow, nsl * sizeof(int)) != cudaSuccess ||
-        cudaMalloc((void **)&c->d_items, ni * sizeof(unsigned short)) != cudaSuccess) {
+        cudaMalloc((void **)&c->d_strips, ni * sizeof(int)) != cudaSuccess) {
         cudaGetLastError();
         set_error("cudaMalloc of the contraction schedule failed");
         contract_plan_free(c);
@@ -285,8 +313,8 @@ int contract_plan_build(ContractPlan **out, int F, const int *rowStart)
         QC_CUDA(cudaMemcpy(c->d_tileInfo, s.tileInfo.data(), s.tileInfo.size() * sizeof(int), cudaMemcpyHostToDevice));
     if (!s.slotRow.empty())
         QC_CUDA(cudaMemcpy(c->d_slotRow, s.slotRow.data(), s.slotRow.size() * sizeof(int), cudaMemcpyHostToDevice));
-    if (!s.items.empty())
-        QC_CUDA(cudaMemcpy(c->d_items, s.items.data(), s.items.size() * sizeof(unsigned short), cudaMemcpyHostToDevice));
+    if (!s.strips.empty())
+        QC_CUDA(cudaMemcpy(c->d_strips, s.strips.data(), s.strips.size() * sizeof(int), cudaMemcpyHostToDevice));
     *out = c;
     return QCDMET_OK;
 }
@@ -294,7 +322,7 @@ int contract_plan_build(ContractPlan **out, int F, const int *rowStart)
 void contract_plan_free(ContractPlan *c)
 {
     if (!c) return;
-    cudaFree(c->d_tileInfo); cudaFree(c->d_slotRow); cudaFree(c->d_items);
+    cudaFree(c->d_tileInfo); cudaFree(c->d_slotRow); cudaFree(c->d_strips);
     cudaGetLastError();
     delete c;
 }
@@ -318,12 +346,13 @@ int launch_contract_panels(const ContractPlan *c, const JacView &v, const double
         w.colEnd = w.colBegin + nc;
         w.J = v.J + (size_t)v.Q * c0;
         contract_panels_kernel<<<dim3((unsigned)s.nTiles, (unsigned)((nc + CCB - 1) / CCB)), CNT, CSMEM, st>>>(
-            w, M, elU, reinterpret_cast<const int4 *>(c->d_tileInfo), c->d_slotRow, c->d_items);
+            w, M, elU, reinterpret_cast<const int4 *>(c->d_tileInfo), c->d_slotRow, c->d_strips);
         QC_CUDA(cudaGetLastError());
         *launches += 1;
     }
-    // executed: 4 FMA-pairs per accumulator element and orbital; Y build 2 flop per element, slot and orbital
-    *flops = (double)ncols * (double)s.items.size() * (CU * CU * 4.0) * v.no +
+    // executed: 2 DMMA.8x8x4 (2 x 512 flop) per block pair and k-step of 4 orbitals (padding of ragged
+    // blocks and of no to a multiple of 4 included); Y build 2 flop per element, slot and orbital
+    *flops = (double)ncols * (double)s.blockPairs * 1024.0 * ((v.no + 3) / 4) +
              2.0 * (double)nnzInRange * (double)s.validSlots * v.no;
     return QCDMET_OK;
 }

@@ -408,14 +408,14 @@ def _column_sample_oracle(w, c, e, cols):
     return np.stack(out, axis=1)
 
 
-@pytest.mark.parametrize("shape", ["frag100_sliced", "frag89_90_bath", "ragged_units"])
+@pytest.mark.parametrize("shape", ["frag100_sliced", "frag102_bath_sliced", "frag89_whole_ragged"])
 def test_factorised_large_fragments(shape):
-    """Fragments beyond one contraction tile (> 88 rows: pairs of 16-unit slices), ragged last units,
+    """Fragments beyond one contraction tile (> 96 rows: pairs of 8-block slices), ragged last blocks,
     projector rows: factorised path against the oracle on sampled columns, against the general kernel
     on all columns, exact block symmetry, column ranges bit-identical to the full run."""
     w = {"frag100_sliced": lambda: wl.make_workload("big", 150, 60, [100, 30, 9]),
-         "frag89_90_bath": lambda: wl.make_workload("bb", 120, 50, [45, 3], fit_imp_bath=True),
-         "ragged_units": lambda: wl.make_workload("rg", 131, 57, [89, 1, 6, 2, 7, 13, 5]),
+         "frag102_bath_sliced": lambda: wl.make_workload("bb", 130, 55, [51, 3], fit_imp_bath=True),
+         "frag89_whole_ragged": lambda: wl.make_workload("rg", 131, 57, [89, 1, 6, 2, 7, 13, 5]),
          }[shape]()
     e, c = ro.eigh_sorted(w.h0)
     plan = _lib.Plan(w.norb, w.num_pairs, w.h1start, w.h1row, w.h1col, w.row_start, w.rows, w.row_idx)
@@ -450,7 +450,7 @@ def test_factorised_large_fragments(shape):
 
 
 def test_compat_full_response_sliced():
-    """rhf_response at a size where the single all-sites fragment (N = 100: 25 units) is cut into slice pairs."""
+    """rhf_response at a size where the single all-sites fragment (N = 100: 13 blocks) is cut into slice pairs."""
     w = wl.sweep(100, nterms=23)
     lib = _lib.load()
     n, p = w.norb, w.nterms

@@ -128,45 +128,52 @@ def test_constrained_optimisation_variant():
 
 
 def _emulate_contraction(tiles, row_start, y, po):
-    """numpy emulation of csrc/kernels_contract.cu for one column: every item (unit pair of a tile) forms
-    acc[i][j] = sum_o Y[a_i,o] PO[b_j,o] + PO[a_i,o] Y[b_j,o] and stores 2 acc at (a,b) and (b,a)."""
+    """numpy emulation of csrc/kernels_contract.cu for one column, lane by lane: every strip (block b1 against
+    blocks b2 .. b2+n2-1) of every warp forms D = Y[b1] PO[b2]^T + PO[b1] Y[b2]^T per 8 x 8 block pair; lane
+    (g, t) of the DMMA accumulator holds D[g][2t], D[g][2t+1] and stores 2 D at (a,b) and (b,a)."""
     row_start = np.asarray(row_start)
     qoff = np.concatenate([[0], np.cumsum(np.diff(row_start).astype(np.int64) ** 2)])
     row_frag = np.repeat(np.arange(len(row_start) - 1), np.diff(row_start))
     jcol = np.full(qoff[-1], np.nan)
     writes = np.zeros(qoff[-1], dtype=np.int64)
-    for slot_row, items in tiles:
-        assert len(slot_row) <= 128 and len(slot_row) % 4 == 0 and 0 < len(items) <= 256
-        for u1, u2 in items:
-            assert u1 <= u2 < len(slot_row) // 4
-            f = row_frag[slot_row[4 * u1]]
-            assert slot_row[4 * u1] >= 0 and slot_row[4 * u2] >= 0 and row_frag[slot_row[4 * u2]] == f
-            rs, rf = row_start[f], row_start[f + 1] - row_start[f]
-            for i in range(4):
-                ra = slot_row[4 * u1 + i]
-                if ra < 0:
-                    continue
-                for j in range(4):
-                    rb = slot_row[4 * u2 + j]
-                    if rb < 0 or (u1 == u2 and j < i):
-                        continue
-                    val = 2.0 * (y[ra] @ po[rb] + po[ra] @ y[rb])
-                    al, bl = ra - rs, rb - rs
-                    for q in {qoff[f] + al + rf * bl, qoff[f] + bl + rf * al}:
-                        jcol[q] = val
-                        writes[q] += 1
+    for slot_row, per_warp in tiles:
+        nslots = len(slot_row)
+        assert nslots <= 128 and nslots % 8 == 0 and len(per_warp) == 8
+        ys = np.where(slot_row[:, None] >= 0, y[np.maximum(slot_row, 0)], 0.0)     # staged chunk, padding slots zero
+        ps = np.where(slot_row[:, None] >= 0, po[np.maximum(slot_row, 0)], 0.0)
+        for strips in per_warp:
+            assert len(strips) <= 3
+            for b1, b2, n2 in strips:
+                assert 1 <= n2 <= 4 and b1 <= b2 and 8 * (b2 + n2) <= nslots
+                f = row_frag[slot_row[8 * b1]]
+                rs, rf = row_start[f], row_start[f + 1] - row_start[f]
+                for j in range(n2):
+                    bb = b2 + j
+                    assert slot_row[8 * bb] >= 0 and row_frag[slot_row[8 * bb]] == f
+                    d = ys[8 * b1:8 * b1 + 8] @ ps[8 * bb:8 * bb + 8].T + ps[8 * b1:8 * b1 + 8] @ ys[8 * bb:8 * bb + 8].T
+                    for lane in range(32):
+                        g, t = lane >> 2, lane & 3
+                        ra = slot_row[8 * b1 + g]
+                        for e in range(2):
+                            rb = slot_row[8 * bb + 2 * t + e]
+                            if ra < 0 or rb < 0 or (bb == b1 and 2 * t + e < g):
+                                continue
+                            al, bl = ra - rs, rb - rs
+                            for q in {qoff[f] + al + rf * bl, qoff[f] + bl + rf * al}:
+                                jcol[q] = 2.0 * d[g, 2 * t + e]
+                                writes[q] += 1
     return jcol, writes
 
 
 def test_contraction_schedule_covers_every_block_element_once():
     """The host-built tile schedule of the factorised path (qcdmet_contract_schedule): every element of every
     fragment block has exactly one owner, tiles respect the kernel's limits, and the emulated contraction
-    equals 2 (G + G^T) block by block -- small packed fragments, ragged units, fragments sliced into
-    16-unit pairs (> 88 rows), empty fragments."""
+    equals 2 (G + G^T) block by block -- small packed fragments, ragged blocks, fragments sliced into
+    8-block pairs (> 96 rows), empty fragments."""
     from qcdmet_b200 import _lib
     rng = np.random.default_rng(3)
-    cases = [[14] * 12, [52] + [24] * 10 + [29], [1, 2, 3, 4, 5, 6, 7, 8, 9], [0, 5, 0, 0, 13, 0], [89], [88, 90],
-             [200, 3, 131], [576], [4] * 70, [], [0, 0]]
+    cases = [[14] * 12, [52] + [24] * 10 + [29], [1, 2, 3, 4, 5, 6, 7, 8, 9], [0, 5, 0, 0, 13, 0], [96], [97], [88, 90, 104],
+             [200, 3, 131], [576], [4] * 70, [9] * 40, [], [0, 0]]
     for sizes in cases:
         row_start = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
         tiles = _lib.contract_schedule(row_start)
@@ -182,6 +189,9 @@ def test_contraction_schedule_covers_every_block_element_once():
             g = y[a:b] @ po[a:b].T
             ref.append((2.0 * (g + g.T)).reshape(-1, order="F"))
         assert np.allclose(jcol, np.concatenate(ref), rtol=0, atol=1e-12)
-    # packing: the 12 x 14-row polyyne fragments need 2 tiles, the sn2 table 3
+    # packing: the 12 x 14-row polyyne fragments (2 blocks, 2 strips each) need 2 tiles, the sn2 table 3
     assert len(_lib.contract_schedule(np.arange(0, 14 * 13, 14))) == 2
     assert len(_lib.contract_schedule(np.concatenate([[0], np.cumsum([52] + [24] * 10 + [29])]))) == 3
+    # a whole fragment stays in one tile up to 12 blocks (96 rows); beyond that it is cut into slice pairs
+    assert len(_lib.contract_schedule(np.array([0, 96]))) == 1
+    assert len(_lib.contract_schedule(np.array([0, 97]))) == 3
