@@ -121,7 +121,7 @@ void contract_schedule_build(int F, const int *rowStart, ContractSchedule *out);
 int contract_plan_build(ContractPlan **out, int F, const int *rowStart);
 void contract_plan_free(ContractPlan *c);
 int launch_contract_panels(const ContractPlan *c, const JacView &v, const double *M, const int *elU,
-                           long long nnzInRange, cudaStream_t st, int *launches, double *flops);
+                           long long nnzInRange, bool nnzAtMost2, cudaStream_t st, int *launches, double *flops);
 
 // factorised path for large fragments (kernels_dmma.cu panel mode + kernels_contract.cu)
 struct FactPlanData;

@@ -35,7 +35,7 @@ constexpr int CTO = 32;                // occupied orbitals per staged chunk
 constexpr int CLD = CTO + 4;           // 36
 constexpr int CBUF = CSLOTS * CLD;     // doubles per staged array
 constexpr int CCB = 8;                 // columns per CTA
-constexpr int CSTG = 3;                // staging tasks in flight per warp (loads issued before they are used)
+constexpr int CSTG = 4;                // staging tasks in flight per thread (loads issued before they are used)
 constexpr int CMAXE = QCDMET_CONTRACT_MAX_NNZ;
 constexpr int CSMEM = 2 * CBUF * 8 + CCB * CMAXE * 16 + CCB * 4 + CSLOTS * 4;
 __device__ __forceinline__ double2 ld2(const double *p) { return *reinterpret_cast<const double2 *>(p); }
@@ -135,6 +135,34 @@ void contract_schedule_build(int F, const int *rowStart, ContractSchedule *out)
 // ------------------------------------------------------------------------------------------
 // device
 // ------------------------------------------------------------------------------------------
+namespace {
+// One strip over the k-steps of a staged chunk: block b1 against N2 consecutive blocks b2.
+// D[b1,b2] += Y[b1] PO[b2]^T + PO[b1] Y[b2]^T; the two products of a pair are issued N2 DMMAs apart.
+template <int N2>
+__device__ __forceinline__ void strip_steps(double (&acc)[CMAXN2][2], const double *__restrict__ ya,
+                                            const double *__restrict__ pa, const double *__restrict__ yb,
+                                            const double *__restrict__ pb, int nk)
+{
+#pragma unroll 2
+    for (int kk = 0; kk < nk; ++kk) {
+        const double aY = ya[4 * kk], aP = pa[4 * kk];
+        double bP[N2], bY[N2];
+#pragma unroll
+        for (int j = 0; j < N2; ++j) {
+            bP[j] = pb[j * CB8 * CLD + 4 * kk];
+            bY[j] = yb[j * CB8 * CLD + 4 * kk];
+        }
+#pragma unroll
+        for (int j = 0; j < N2; ++j) dmma884(acc[j][0], acc[j][1], aY, bP[j]);
+#pragma unroll
+        for (int j = 0; j < N2; ++j) dmma884(acc[j][0], acc[j][1], aP, bY[j]);
+    }
+}
+}  // namespace
+
+// NNZ2: every perturbation of the plan has at most 2 elements (all DMET lists of src/dmet.py:118-159 outside
+// the translation-invariant case): both panel loads of a task are prefetched, no element loop.
+template <bool NNZ2>
 __global__ void __launch_bounds__(CNT, 2)
 contract_panels_kernel(const JacView v, const double *__restrict__ M, const int *__restrict__ elU,
                        const int4 *__restrict__ tileInfo, const int *__restrict__ slotRowG,
@@ -164,15 +192,12 @@ contract_panels_kernel(const JacView v, const double *__restrict__ M, const int 
             elC[i] = (long long)v.h1col[eb + e] * v.ldo;
         }
     }
-    // this warp's strips
-    int sb1[CMAXS], sb2[CMAXS], sn2[CMAXS];
+    // padding slots of ragged blocks stay zero for the whole CTA: staging never touches them
+    for (int i = tid; i < CBUF; i += CNT) *reinterpret_cast<double2 *>(Ys + 2 * i) = make_double2(0.0, 0.0);
+    // this warp's strips: b1 | b2 << 8 | n2 << 16, -1 = none
+    int sw[CMAXS];
 #pragma unroll
-    for (int s = 0; s < CMAXS; ++s) {
-        const int w = stripsG[ti.z + warp * CMAXS + s];
-        sb1[s] = w < 0 ? 0 : (w & 0xFF);
-        sb2[s] = w < 0 ? 0 : ((w >> 8) & 0xFF);
-        sn2[s] = w < 0 ? 0 : (w >> 16);
-    }
+    for (int s = 0; s < CMAXS; ++s) sw[s] = stripsG[ti.z + warp * CMAXS + s];
     double acc[CMAXS][CMAXN2][2];
 #pragma unroll
     for (int s = 0; s < CMAXS; ++s)
@@ -181,51 +206,66 @@ contract_panels_kernel(const JacView v, const double *__restrict__ M, const int 
     __syncthreads();
 
     const int g4 = lane >> 2, t4 = lane & 3;         // DMMA fragment coordinates: row / column, k index
-    // staging: task = (4 consecutive slots, 16-orbital half of the chunk); lane = (slot of the group, orbital
-    // pair): a warp load is 4 rows x 128 contiguous bytes, a warp store is conflict-free
+    constexpr int STG = NNZ2 ? CSTG : 2;             // staging tasks in flight per thread (register budget)
+    static_assert(8 % STG == 0, "the 8 tasks of a thread are staged in equal batches");
+    // Staging geometry, fixed for the CTA.  A task = (4 consecutive slots, 16-orbital half of the chunk);
+    // lane = (slot of the group, orbital pair): a warp load is 4 rows x 128 contiguous bytes, a warp store
+    // (STS.128) is conflict-free.  Warp w serves half w & 1 of the groups (w >> 1) + 4 i, i < 8.
     const int ls = lane & 3, lo = lane >> 2;
-    const int nGroups = ti.y / 4;
+    const int half = warp & 1;
+    const int colo = 16 * half + 2 * lo;             // orbital of this lane inside the chunk
+    const int dst0 = (4 * (warp >> 1) + ls) * CLD + colo;
+    int roff[8];                                     // row * ldo + colo of task i; < 0: padding slot or no task
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int slot = 4 * ((warp >> 1) + 4 * i) + ls;
+        const int row = slot < ti.y ? srow[slot] : -1;
+        roff[i] = row >= 0 ? row * v.ldo + colo : -1;            // S ldo < 2^31 (checked at plan creation)
+    }
+    int offA[CMAXS], offB[CMAXS];                    // operand fragments of the strips in a staged array
+#pragma unroll
+    for (int s = 0; s < CMAXS; ++s) {
+        offA[s] = ((sw[s] & 0xFF) * CB8 + g4) * CLD + t4;
+        offB[s] = (((sw[s] >> 8) & 0xFF) * CB8 + g4) * CLD + t4;
+    }
 
     for (int cb = 0; cb < ncb; ++cb) {
         const int nnz = nnzs[cb];
         const long long *eM = elM + cb * CMAXE, *eC = elC + cb * CMAXE;
+        const double *pM0 = M + (nnz > 0 ? eM[0] : 0), *pM1 = M + (nnz > 1 ? eM[1] : 0);
+        const double *pC0 = v.CoT + (nnz > 0 ? eC[0] : 0), *pC1 = v.CoT + (nnz > 1 ? eC[1] : 0);
         for (int o0 = 0; o0 < v.no; o0 += CTO) {
-            const int nh = (v.ldo - o0 > 16) ? 2 : 1;    // halves that exist (ldo is a multiple of 16, panels zero padded)
-            const int ntask = nGroups * nh;
-            for (int t0 = warp; t0 < ntask; t0 += CWARPS * CSTG) {
-                double2 m0[CSTG], m1[CSTG], po[CSTG];
-                int dst[CSTG], src[CSTG];                // smem offset (< 0: no task); panel offset (< 0: padding slot)
+            if (o0 + 16 * half < v.ldo) {            // this warp's half exists (ldo is a multiple of 16; panels zero padded)
+                double2 c0 = make_double2(0.0, 0.0), c1 = make_double2(0.0, 0.0);
+                if (nnz > 0) c0 = ld2(pC0 + o0 + colo);
+                if (nnz > 1) c1 = ld2(pC1 + o0 + colo);
 #pragma unroll
-                for (int k = 0; k < CSTG; ++k) {
-                    const int t = t0 + CWARPS * k;
-                    const int grp = nh == 2 ? (t >> 1) : t, h = nh == 2 ? (t & 1) : 0;
-                    const int slot = grp * 4 + ls;
-                    const int row = t < ntask ? srow[slot] : -1;
-                    dst[k] = t < ntask ? slot * CLD + 16 * h + 2 * lo : -1;
-                    src[k] = row >= 0 ? row * v.ldo + o0 + 16 * h + 2 * lo : -1;   // S ldo < 2^31 (checked at plan creation)
-                    m0[k] = m1[k] = po[k] = make_double2(0.0, 0.0);
-                    if (src[k] >= 0) {
-                        po[k] = ld2(v.PO + src[k]);
-                        if (nnz > 0) m0[k] = ld2(M + eM[0] + src[k]);
-                        if (nnz > 1) m1[k] = ld2(M + eM[1] + src[k]);
-                    }
-                }
+                for (int i0 = 0; i0 < 8; i0 += STG) {
+                    double2 m0[STG], m1[STG], po[STG];
 #pragma unroll
-                for (int k = 0; k < CSTG; ++k) {
-                    if (dst[k] < 0) continue;
-                    double2 y = make_double2(0.0, 0.0);
-                    if (src[k] >= 0) {
-                        const int t = t0 + CWARPS * k;
-                        const int o = o0 + (nh == 2 ? 16 * (t & 1) : 0) + 2 * lo;
-                        if (nnz > 0) { const double2 c = ld2(v.CoT + eC[0] + o); y.x = m0[k].x * c.x; y.y = m0[k].y * c.y; }
-                        if (nnz > 1) { const double2 c = ld2(v.CoT + eC[1] + o); y.x = fma(m1[k].x, c.x, y.x); y.y = fma(m1[k].y, c.y, y.y); }
-                        for (int e = 2; e < nnz; ++e) {      // longer lists (translation-invariant, arbitrary CSR)
-                            const double2 m = ld2(M + eM[e] + src[k]), c = ld2(v.CoT + eC[e] + o);
-                            y.x = fma(m.x, c.x, y.x); y.y = fma(m.y, c.y, y.y);
+                    for (int k = 0; k < STG; ++k) {
+                        m0[k] = m1[k] = po[k] = make_double2(0.0, 0.0);
+                        if (roff[i0 + k] >= 0) {
+                            po[k] = ld2(v.PO + roff[i0 + k] + o0);
+                            if (nnz > 0) m0[k] = ld2(pM0 + roff[i0 + k] + o0);
+                            if (nnz > 1) m1[k] = ld2(pM1 + roff[i0 + k] + o0);
                         }
                     }
-                    *reinterpret_cast<double2 *>(Ys + dst[k]) = y;
-                    *reinterpret_cast<double2 *>(Ps + dst[k]) = po[k];
+#pragma unroll
+                    for (int k = 0; k < STG; ++k) {
+                        if (roff[i0 + k] < 0) continue;
+                        double2 y;
+                        y.x = fma(m1[k].x, c1.x, m0[k].x * c0.x);
+                        y.y = fma(m1[k].y, c1.y, m0[k].y * c0.y);
+                        if constexpr (!NNZ2) {
+                            for (int e = 2; e < nnz; ++e) {      // longer lists (translation-invariant, arbitrary CSR)
+                                const double2 m = ld2(M + eM[e] + roff[i0 + k] + o0), c = ld2(v.CoT + eC[e] + o0 + colo);
+                                y.x = fma(m.x, c.x, y.x); y.y = fma(m.y, c.y, y.y);
+                            }
+                        }
+                        *reinterpret_cast<double2 *>(Ys + dst0 + (i0 + k) * 16 * CLD) = y;
+                        *reinterpret_cast<double2 *>(Ps + dst0 + (i0 + k) * 16 * CLD) = po[k];
+                    }
                 }
             }
             __syncthreads();
@@ -233,27 +273,13 @@ contract_panels_kernel(const JacView v, const double *__restrict__ M, const int 
             const int nk = (min(CTO, v.no - o0) + 3) / 4;
 #pragma unroll
             for (int s = 0; s < CMAXS; ++s) {
-                if (sn2[s] == 0) continue;               // warp-uniform
-                const double *ya = Ys + (sb1[s] * CB8 + g4) * CLD + t4, *pa = Ps + (sb1[s] * CB8 + g4) * CLD + t4;
-                const double *yb = Ys + (sb2[s] * CB8 + g4) * CLD + t4, *pb = Ps + (sb2[s] * CB8 + g4) * CLD + t4;
-                for (int kk = 0; kk < nk; ++kk) {
-                    const double aY = ya[4 * kk], aP = pa[4 * kk];
-                    double bP[CMAXN2], bY[CMAXN2];
-#pragma unroll
-                    for (int j = 0; j < CMAXN2; ++j) {
-                        bP[j] = bY[j] = 0.0;
-                        if (j < sn2[s]) {                // warp-uniform
-                            bP[j] = pb[j * CB8 * CLD + 4 * kk];
-                            bY[j] = yb[j * CB8 * CLD + 4 * kk];
-                        }
-                    }
-                    // the two products of a pair go to the same accumulator: issue them n2 DMMAs apart
-#pragma unroll
-                    for (int j = 0; j < CMAXN2; ++j)
-                        if (j < sn2[s]) dmma884(acc[s][j][0], acc[s][j][1], aY, bP[j]);      // Y[b1] PO[b2]^T
-#pragma unroll
-                    for (int j = 0; j < CMAXN2; ++j)
-                        if (j < sn2[s]) dmma884(acc[s][j][0], acc[s][j][1], aP, bY[j]);      // PO[b1] Y[b2]^T
+                if (sw[s] < 0) continue;                 // warp-uniform
+                const double *ya = Ys + offA[s], *pa = Ps + offA[s], *yb = Ys + offB[s], *pb = Ps + offB[s];
+                switch (sw[s] >> 16) {                   // warp-uniform
+                case 4: strip_steps<4>(acc[s], ya, pa, yb, pb, nk); break;
+                case 3: strip_steps<3>(acc[s], ya, pa, yb, pb, nk); break;
+                case 2: strip_steps<2>(acc[s], ya, pa, yb, pb, nk); break;
+                default: strip_steps<1>(acc[s], ya, pa, yb, pb, nk); break;
                 }
             }
             __syncthreads();
@@ -263,19 +289,20 @@ contract_panels_kernel(const JacView v, const double *__restrict__ M, const int 
         double *Jc = v.J + (size_t)v.Q * (pl0 + cb);
 #pragma unroll
         for (int s = 0; s < CMAXS; ++s) {
-            if (sn2[s] == 0) continue;
+            if (sw[s] < 0) continue;
+            const int b1 = sw[s] & 0xFF, b2 = (sw[s] >> 8) & 0xFF, n2 = sw[s] >> 16;
             // fragment of the strip's rows (the first row of a block always exists)
-            const int f = v.rowFrag[srow[sb1[s] * CB8]];
+            const int f = v.rowFrag[srow[b1 * CB8]];
             const int rs = v.rowStart[f], rf = v.rowStart[f + 1] - rs;
-            const int ra = srow[sb1[s] * CB8 + g4];
+            const int ra = srow[b1 * CB8 + g4];
             double *Jp = Jc + v.qoff[f];
 #pragma unroll
             for (int j = 0; j < CMAXN2; ++j) {
-                if (j < sn2[s]) {
-                    const bool diag = (sb2[s] + j == sb1[s]);
+                if (j < n2) {
+                    const bool diag = (b2 + j == b1);
 #pragma unroll
                     for (int e = 0; e < 2; ++e) {
-                        const int rb = srow[(sb2[s] + j) * CB8 + 2 * t4 + e];
+                        const int rb = srow[(b2 + j) * CB8 + 2 * t4 + e];
                         if (ra >= 0 && rb >= 0 && !(diag && 2 * t4 + e < g4)) {
                             const long long al = ra - rs, bl = rb - rs;
                             const double val = 2.0 * acc[s][j][e];
@@ -328,7 +355,7 @@ void contract_plan_free(ContractPlan *c)
 }
 
 int launch_contract_panels(const ContractPlan *c, const JacView &v, const double *M, const int *elU,
-                           long long nnzInRange, cudaStream_t st, int *launches, double *flops)
+                           long long nnzInRange, bool nnzAtMost2, cudaStream_t st, int *launches, double *flops)
 {
     *launches = 0;
     *flops = 0.0;
@@ -336,7 +363,8 @@ int launch_contract_panels(const ContractPlan *c, const JacView &v, const double
     const ContractSchedule &s = c->sched;
     if (ncols <= 0 || s.nTiles == 0) return QCDMET_OK;
     // per device (function attributes live in the context of the current device): set on every launch
-    QC_CUDA(cudaFuncSetAttribute(contract_panels_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CSMEM));
+    QC_CUDA(cudaFuncSetAttribute(contract_panels_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CSMEM));
+    QC_CUDA(cudaFuncSetAttribute(contract_panels_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CSMEM));
     // gridDim.y is limited to 65535 batches of CCB columns: chunk the columns
     const int chunk = 65535 * CCB;
     for (int c0 = 0; c0 < ncols; c0 += chunk) {
@@ -345,8 +373,13 @@ int launch_contract_panels(const ContractPlan *c, const JacView &v, const double
         w.colBegin = v.colBegin + c0;
         w.colEnd = w.colBegin + nc;
         w.J = v.J + (size_t)v.Q * c0;
-        contract_panels_kernel<<<dim3((unsigned)s.nTiles, (unsigned)((nc + CCB - 1) / CCB)), CNT, CSMEM, st>>>(
-            w, M, elU, reinterpret_cast<const int4 *>(c->d_tileInfo), c->d_slotRow, c->d_strips);
+        const dim3 grid((unsigned)s.nTiles, (unsigned)((nc + CCB - 1) / CCB));
+        if (nnzAtMost2)
+            contract_panels_kernel<true><<<grid, CNT, CSMEM, st>>>(
+                w, M, elU, reinterpret_cast<const int4 *>(c->d_tileInfo), c->d_slotRow, c->d_strips);
+        else
+            contract_panels_kernel<false><<<grid, CNT, CSMEM, st>>>(
+                w, M, elU, reinterpret_cast<const int4 *>(c->d_tileInfo), c->d_slotRow, c->d_strips);
         QC_CUDA(cudaGetLastError());
         *launches += 1;
     }

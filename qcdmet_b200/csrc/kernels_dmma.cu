@@ -890,8 +890,8 @@ int launch_jacobian_dmma(DmmaPlanData *d, const JacView &v, cudaStream_t st, int
     const int shareRank = peers ? peers->rank : 0, shareN = peers ? peers->nranks : 1;
     if (d->launchBegin != v.colBegin || d->launchEnd != v.colEnd || d->launchSym != wantSym ||
         d->launchRank != shareRank || d->launchRanks != shareN) {
-        // work list: (component, tile) pairs, tile-major so that co-resident CTAs share a PVt panel.
-        // Symmetric mode (full column range): only pairs with tile(component) >= tile.
+        // work list: (component, tile) pairs; symmetric mode (full column range): only pairs with
+        // tile(component) >= tile.
         const bool sym = wantSym;
         std::vector<char> hit(d->nComp, 0);
         for (int c = 0; c < d->nComp; ++c)
@@ -899,12 +899,18 @@ int launch_jacobian_dmma(DmmaPlanData *d, const JacView &v, cudaStream_t st, int
                 const int p = d->compP[(size_t)c * MAXP + k];
                 hit[c] = (p >= cb && p < ce);
             }
+        // Order: blocks of L2BLK components, tile-major inside a block.  Co-resident CTAs share one PVt/POt
+        // panel (tile) and the CVt/COt rows of one component block stay L2-resident (128 x 128 KB at
+        // N = 4000) next to the Wt panel while every tile passes over them, so each operand panel comes
+        // from DRAM about once per component block instead of once per tile.
+        constexpr int L2BLK = 128;
         std::vector<int2> all;
-        for (int t = 0; t < d->nTiles; ++t)
-            for (int c = 0; c < d->nComp; ++c) {
-                if (!hit[c] || (sym && d->compTile[c] < t)) continue;
-                all.push_back(make_int2(c, t));
-            }
+        for (int c0 = 0; c0 < d->nComp; c0 += L2BLK)
+            for (int t = 0; t < d->nTiles; ++t)
+                for (int c = c0; c < std::min(c0 + L2BLK, d->nComp); ++c) {
+                    if (!hit[c] || (sym && d->compTile[c] < t)) continue;
+                    all.push_back(make_int2(c, t));
+                }
         // this rank's share: a contiguous slice of the (equal-cost) block-pair list
         const size_t wb = all.size() * (size_t)shareRank / shareN, we = all.size() * (size_t)(shareRank + 1) / shareN;
         d->work.assign(all.begin() + wb, all.begin() + we);
@@ -1056,6 +1062,7 @@ struct FactPlanData {
     double *d_M = nullptr;              // [4 nComp][S][ldo]
     size_t mDoubles = 0;
     int numSites = 0;
+    int maxNnz = 0;                     // longest perturbation of the plan
     ContractPlan *contract = nullptr;
 };
 
@@ -1115,6 +1122,7 @@ int fact_plan_build(FactPlanData **out, int N, int no, int P, int F, const int *
     d.compSites.assign((size_t)d.nComp * RT, -1);
     for (int i = 0; i < N; ++i)
         if (f->siteToU[i] >= 0) d.compSites[f->siteToU[i]] = i;
+    for (int p = 0; p < P; ++p) f->maxNnz = std::max(f->maxNnz, h1start[p + 1] - h1start[p]);
     f->elU.resize(h1start[P]);
     for (int k = 0; k < h1start[P]; ++k) f->elU[k] = f->siteToU[h1row[k]];
     d.compNumSites.assign(d.nComp, RT);
@@ -1240,7 +1248,7 @@ int launch_jacobian_factorised(FactPlanData *f, const JacView &v, long long nnzI
     }
     int l2 = 0;
     double f2 = 0.0;
-    QC_TRY(launch_contract_panels(f->contract, v, f->d_M, f->d_elU, nnzInRange, st, &l2, &f2));
+    QC_TRY(launch_contract_panels(f->contract, v, f->d_M, f->d_elU, nnzInRange, f->maxNnz <= 2, st, &l2, &f2));
     if (ev1) QC_CUDA(cudaEventRecord(ev1, st));
     *launches += l2;
     *flops += f2;

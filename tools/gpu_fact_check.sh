@@ -1,6 +1,7 @@
 #!/usr/bin/env bash
-# gpurun round-trip for the factorised path: GPU tests, bench of the large-fragment shapes, ncu of the
-# contraction and panel kernels.  Every stage has its own timeout.
+# gpurun round-trip: GPU tests, bench of the large-fragment shapes and of the north-star shape, ncu of the
+# contraction kernel and (optionally, NCU4000=1) of the main DMMA kernel at N = 4000.  Every stage has its
+# own timeout.
 set -u
 mkdir -p gpurun_out
 timeout 500 python -m pytest tests -m gpu -q --tb=short > gpurun_out/pytest_gpu_fact.log 2>&1
@@ -9,9 +10,13 @@ for wl in sn2 polyyne; do
   timeout 200 python bench.py --workload $wl --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_fact_$wl.json 2> gpurun_out/bench_fact_$wl.err
   echo "bench $wl rc=$?"; cat gpurun_out/bench_fact_$wl.json; tail -3 gpurun_out/bench_fact_$wl.err
 done
-timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/launches_fact_sn2.csv \
-  python bench.py --workload sn2 --steps 2 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/ncu_list_fact.log 2>&1
-echo "ncu list rc=$?"
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:contract_panels -s 3 -c 1 -f -o gpurun_out/prof_contract_sn2 \
   python bench.py --workload sn2 --steps 2 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/ncu_full_fact.log 2>&1
-echo "ncu full rc=$?"
+echo "ncu contract rc=$?"
+if [ "${NCU4000:-0}" = "1" ]; then
+  timeout 400 python bench.py --norb 4000 --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_l2order_N4000.json 2> gpurun_out/bench_l2order_N4000.err
+  echo "bench N=4000 rc=$?"; cat gpurun_out/bench_l2order_N4000.json; tail -3 gpurun_out/bench_l2order_N4000.err
+  timeout 500 ncu --set full --clock-control none -k regex:jac_dmma -c 1 -f -o gpurun_out/prof_dmma_v4_N4000 \
+    python bench.py --norb 4000 --steps 1 --warmup 3 --no-cpu-baseline --no-e2e --check-cols 0 > gpurun_out/ncu_full_N4000.log 2>&1
+  echo "ncu N=4000 rc=$?"; tail -3 gpurun_out/ncu_full_N4000.log
+fi
