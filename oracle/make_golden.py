@@ -18,7 +18,27 @@ from oracle import ref_loader, response_oracle as ro   # noqa: E402
 from qcdmet_b200 import workloads as wl                # noqa: E402
 
 
+def subsample(w, idx, name):
+    """Keep the perturbations idx of a workload (golden files store the full N x N response per column)."""
+    hs, hr, hc = [0], [], []
+    for p in idx:
+        a, b = w.h1start[p], w.h1start[p + 1]
+        hr += list(w.h1row[a:b]); hc += list(w.h1col[a:b]); hs.append(len(hr))
+    w.h1start, w.h1row, w.h1col = (np.array(hs, dtype=np.int32), np.array(hr, dtype=np.int32),
+                                   np.array(hc, dtype=np.int32))
+    w.name = name
+    return w
+
+
 def cases():
+    # fragments of more than 8 rows (factorised path of the library): packed 14-row fragments, impurity+bath
+    # rows of a 10- and a 6-orbital impurity, one 100-row fragment (cut into slice pairs by the contraction)
+    w = wl.make_workload("frag14_N42", 42, 15, [14, 14, 14])
+    yield subsample(w, range(0, w.nterms, 7), "frag14_N42")
+    w = wl.make_workload("frag_bath_N40", 40, 17, [10, 6], fit_imp_bath=True)
+    yield subsample(w, range(0, w.nterms, 2), "frag_bath_N40")
+    w = wl.make_workload("bigfrag_N104", 104, 40, [100])
+    yield subsample(w, [0, 1, 100, 2500, 5000, 5049], "bigfrag_N104")
     yield wl.hydrogen_like()
     yield wl.sweep(24)
     yield wl.make_workload("mixed_N30", 30, 11, [5, 3, 7])
@@ -32,7 +52,10 @@ def cases():
 def main():
     out_dir = os.path.join(ROOT, "tests", "golden")
     os.makedirs(out_dir, exist_ok=True)
+    only_missing = "--only-missing" in sys.argv
     for w in cases():
+        if only_missing and os.path.exists(os.path.join(out_dir, f"{w.name}.npz")):
+            continue
         resp, one_rdm = ref_loader.rhf_response(w.norb, w.num_pairs, w.h1start, w.h1row, w.h1col, w.h0, "mkl")
         resp_ob, _ = ref_loader.rhf_response(w.norb, w.num_pairs, w.h1start, w.h1row, w.h1col, w.h0, "openblas")
         assert np.abs(resp - resp_ob).max() < 1e-11, "MKL and OpenBLAS builds of the reference disagree"
