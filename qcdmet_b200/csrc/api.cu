@@ -237,8 +237,14 @@ int ensure_fact(qcdmet_plan *p)
         p->fact_why = buf;
         return QCDMET_OK;
     }
-    QC_TRY(fact_plan_build(&p->fact, p->N, p->no, p->P, p->F, p->rowStart.data(), p->ldo, p->h1start.data(),
-                           p->h1row.data()));
+    const int rc = fact_plan_build(&p->fact, p->N, p->no, p->P, p->F, p->rowStart.data(), p->ldo, p->h1start.data(),
+                                   p->h1row.data());
+    if (rc == QCDMET_E_ALLOC) {                 // e.g. fragmented device memory: keep the general kernel
+        p->fact = nullptr;
+        p->fact_why = g_err;
+        return QCDMET_OK;
+    }
+    QC_TRY(rc);
     p->fact_ok = true;
     return QCDMET_OK;
 }

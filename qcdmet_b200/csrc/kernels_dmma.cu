@@ -31,6 +31,8 @@
 //     J[rows of g, columns of the blocks in t] from the same N values: half the flops, exact.
 //   * multi-GPU: a rank executes a contiguous slice of the block-pair list and stores every J element
 //     into all ranks' buffers (CUDA-IPC-mapped peers, NVLink): the all-gather is fused into the kernel.
+//   * panel mode (template parameter PANEL, end of this file): the same main loop without the epilogue,
+//     M_r[a,o] stored to HBM for the fragments of more than 8 rows that kernels_contract.cu contracts.
 #include "common.cuh"
 #include <algorithm>
 #include <cstdint>

@@ -1,9 +1,10 @@
 // kernels_general.cu -- general FP64 fragment-block response kernel.
 //
 // Correct for arbitrary CSR perturbations (nnz_p >= 1, translation-invariant lists included),
-// arbitrary fragment row lists and dense projector rows (fitImpBath).  Used for the shapes the
-// site-factorised DMMA kernel does not cover and as the on-device cross-check of that kernel at
-// sizes the CPU oracle cannot reach.  Plain FP64-FMA-pipe kernel (on B200 the DFMA and DMMA rates are the
+// arbitrary fragment row lists and dense projector rows (fitImpBath).  Used for the shapes neither the
+// fused DMMA kernel (kernels_dmma.cu) nor the factorised path (panel mode + kernels_contract.cu) covers
+// -- perturbations of more than 64 elements, panels that do not fit in device memory -- and as the
+// on-device cross-check of both at sizes the CPU oracle cannot reach.  Plain FP64-FMA-pipe kernel (on B200 the DFMA and DMMA rates are the
 // same pipe: 33.7 vs 36.9 TFLOP/s measured), shared-memory tiled, 64 x 64 output tile, 4 x 4 per thread.
 //
 // Per column p (lib/rhf_response.cc:82-108 restricted to the fragment rows):
