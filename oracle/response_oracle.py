@@ -19,7 +19,7 @@ This is a numpy *restatement* (written from the mathematics, not a copy) of
 
 Parity pinning: the reference ships no tests or golden vectors for this path
 (SURVEY.md 4, 8c).  The oracle is pinned against the UNMODIFIED reference kernel compiled
-into oracle/_ref/ (oracle/build_ref.sh) by tests/test_oracle_vs_ref.py, and against the
+into oracle/_ref/ (oracle/build_ref.sh) by tests/test_oracle.py, and against the
 fixtures under tests/golden/ that oracle/make_golden.py generated from that compiled
 reference in the build container.
 """
