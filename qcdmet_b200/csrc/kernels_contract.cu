@@ -16,6 +16,7 @@
 // no atomics, blocks exactly symmetric, run-to-run bit-reproducible.
 #include "common.cuh"
 #include <algorithm>
+#include <cstdint>
 
 namespace qcdmet {
 
@@ -38,7 +39,34 @@ constexpr int CCB = 8;                 // columns per CTA
 constexpr int CSTG = 4;                // staging tasks in flight per thread (loads issued before they are used)
 constexpr int CMAXE = QCDMET_CONTRACT_MAX_NNZ;
 constexpr int CSMEM = 2 * CBUF * 8 + CCB * CMAXE * 16 + CCB * 4 + CSLOTS * 4;
+// warp-specialised variant (contract_panels_ws_kernel): 4 staging warps + 8 DMMA warps, 2 stages
+constexpr int WS_STAGE_WARPS = 4;
+constexpr int WS_NT = 32 * (WS_STAGE_WARPS + CWARPS);       // 384
+constexpr int WS_TASKS = CSLOTS / 4 * 2 / WS_STAGE_WARPS;   // staging tasks per thread and chunk: 16
+constexpr int WS_BATCH = 8;                                 // of which in flight (the staging warps hold no accumulators)
+constexpr int WS_SMEM = 4 * CBUF * 8 + CCB * CMAXE * 16 + CCB * 4 + CSLOTS * 4 + 4 * 8;
 __device__ __forceinline__ double2 ld2(const double *p) { return *reinterpret_cast<const double2 *>(p); }
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "CWAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra CWAIT_DONE;\n"
+        "bra CWAIT_LOOP;\n"
+        "CWAIT_DONE:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
 __device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double b)
 {
     asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
@@ -317,6 +345,187 @@ contract_panels_kernel(const JacView v, const double *__restrict__ M, const int 
     }
 }
 
+// Warp-specialised variant, OFF by default (QCDMET_B200_CONTRACT_WS=1 selects it; prepared at the end of
+// round 1 without GPU time left to measure it -- see DESIGN.md 10).  Same schedule, same arithmetic per
+// accumulator and the same stores as contract_panels_kernel, hence bit-identical results; the difference is
+// who waits for whom: warps 0-3 only stage (Y, PO chunks into two shared-memory stages, 8 tasks x 3 LDG.128
+// in flight per thread), warps 4-11 only run their strips, and the two groups meet on full/empty mbarriers
+// per stage instead of CTA-wide barriers, so the L2 latency of the panels overlaps the DMMA work of the
+// previous chunk and a slow strip does not hold the other DMMA warps.
+template <bool NNZ2>
+__global__ void __launch_bounds__(WS_NT, 1)
+contract_panels_ws_kernel(const JacView v, const double *__restrict__ M, const int *__restrict__ elU,
+                          const int4 *__restrict__ tileInfo, const int *__restrict__ slotRowG,
+                          const int *__restrict__ stripsG)
+{
+    extern __shared__ __align__(16) unsigned char csm[];
+    double *Ys = reinterpret_cast<double *>(csm);                    // [stage][slot][o]: Ys, Ps of stage 0, then of stage 1
+    long long *elM = reinterpret_cast<long long *>(Ys + 4 * CBUF);   // [CCB][CMAXE]
+    long long *elC = elM + CCB * CMAXE;
+    int *nnzs = reinterpret_cast<int *>(elC + CCB * CMAXE);
+    int *srow = nnzs + CCB;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(srow + CSLOTS);    // full[0], full[1], empty[0], empty[1]
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int4 ti = tileInfo[blockIdx.x];
+    const int pl0 = blockIdx.y * CCB;
+    const int ncb = min(CCB, v.colEnd - v.colBegin - pl0);
+
+    if (tid == 0) {
+        mbar_init(smem_addr(&bars[0]), WS_STAGE_WARPS);   // full: one arrival per staging warp
+        mbar_init(smem_addr(&bars[1]), WS_STAGE_WARPS);
+        mbar_init(smem_addr(&bars[2]), CWARPS);           // empty: one arrival per DMMA warp
+        mbar_init(smem_addr(&bars[3]), CWARPS);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (tid < CSLOTS) srow[tid] = tid < ti.y ? slotRowG[ti.x + tid] : -1;
+    for (int i = tid; i < ncb * CMAXE; i += WS_NT) {
+        const int cb = i / CMAXE, e = i % CMAXE;
+        const int p = v.colBegin + pl0 + cb;
+        const int eb = v.h1start[p], n = v.h1start[p + 1] - eb;
+        if (e == 0) nnzs[cb] = n;
+        if (e < n) {
+            elM[i] = (long long)elU[eb + e] * v.S * v.ldo;
+            elC[i] = (long long)v.h1col[eb + e] * v.ldo;
+        }
+    }
+    // padding slots of ragged blocks stay zero in both stages: staging never touches them
+    for (int i = tid; i < 2 * CBUF; i += WS_NT) *reinterpret_cast<double2 *>(Ys + 2 * i) = make_double2(0.0, 0.0);
+    __syncthreads();
+
+    const int nChunks = (v.no + CTO - 1) / CTO;
+    const int nIt = ncb * nChunks;
+
+    if (warp < WS_STAGE_WARPS) {
+        // ================= staging warps =================
+        // task = (4 consecutive slots, 16-orbital half of the chunk); lane = (slot of the group, orbital pair).
+        // Warp w serves half w & 1 of the groups (w >> 1) + 2 i, i < 16.
+        const int ls = lane & 3, lo = lane >> 2;
+        const int half = warp & 1;
+        const int colo = 16 * half + 2 * lo;
+        const int dst0 = (4 * (warp >> 1) + ls) * CLD + colo;
+        int roff[WS_TASKS];
+#pragma unroll
+        for (int i = 0; i < WS_TASKS; ++i) {
+            const int slot = 4 * ((warp >> 1) + 2 * i) + ls;
+            const int row = slot < ti.y ? srow[slot] : -1;
+            roff[i] = row >= 0 ? row * v.ldo + colo : -1;
+        }
+        int cb = 0, ch = 0;
+        for (int it = 0; it < nIt; ++it) {
+            const int st = it & 1, o0 = ch * CTO;
+            double *ys = Ys + 2 * st * CBUF, *ps = ys + CBUF;
+            mbar_wait(smem_addr(&bars[2 + st]), ((it >> 1) & 1) ^ 1);      // the DMMA warps are done with this stage
+            if (o0 + 16 * half < v.ldo) {
+                const int nnz = nnzs[cb];
+                const long long *eM = elM + cb * CMAXE, *eC = elC + cb * CMAXE;
+                const double *pM0 = M + (nnz > 0 ? eM[0] : 0), *pM1 = M + (nnz > 1 ? eM[1] : 0);
+                double2 c0 = make_double2(0.0, 0.0), c1 = make_double2(0.0, 0.0);
+                if (nnz > 0) c0 = ld2(v.CoT + eC[0] + o0 + colo);
+                if (nnz > 1) c1 = ld2(v.CoT + eC[1] + o0 + colo);
+#pragma unroll
+                for (int i0 = 0; i0 < WS_TASKS; i0 += WS_BATCH) {
+                    double2 m0[WS_BATCH], m1[WS_BATCH], po[WS_BATCH];
+#pragma unroll
+                    for (int k = 0; k < WS_BATCH; ++k) {
+                        m0[k] = m1[k] = po[k] = make_double2(0.0, 0.0);
+                        if (roff[i0 + k] >= 0) {
+                            po[k] = ld2(v.PO + roff[i0 + k] + o0);
+                            if (nnz > 0) m0[k] = ld2(pM0 + roff[i0 + k] + o0);
+                            if (nnz > 1) m1[k] = ld2(pM1 + roff[i0 + k] + o0);
+                        }
+                    }
+#pragma unroll
+                    for (int k = 0; k < WS_BATCH; ++k) {
+                        if (roff[i0 + k] < 0) continue;
+                        double2 y;
+                        y.x = fma(m1[k].x, c1.x, m0[k].x * c0.x);
+                        y.y = fma(m1[k].y, c1.y, m0[k].y * c0.y);
+                        if constexpr (!NNZ2) {
+                            for (int e = 2; e < nnz; ++e) {
+                                const double2 m = ld2(M + eM[e] + roff[i0 + k] + o0), c = ld2(v.CoT + eC[e] + o0 + colo);
+                                y.x = fma(m.x, c.x, y.x); y.y = fma(m.y, c.y, y.y);
+                            }
+                        }
+                        *reinterpret_cast<double2 *>(ys + dst0 + (i0 + k) * 8 * CLD) = y;
+                        *reinterpret_cast<double2 *>(ps + dst0 + (i0 + k) * 8 * CLD) = po[k];
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_addr(&bars[st]));
+            if (++ch == nChunks) { ch = 0; ++cb; }
+        }
+        return;
+    }
+
+    // ================= DMMA warps =================
+    const int dw = warp - WS_STAGE_WARPS;
+    const int g4 = lane >> 2, t4 = lane & 3;
+    int sw[CMAXS], offA[CMAXS], offB[CMAXS];
+#pragma unroll
+    for (int s = 0; s < CMAXS; ++s) {
+        sw[s] = stripsG[ti.z + dw * CMAXS + s];
+        offA[s] = ((sw[s] & 0xFF) * CB8 + g4) * CLD + t4;
+        offB[s] = (((sw[s] >> 8) & 0xFF) * CB8 + g4) * CLD + t4;
+    }
+    double acc[CMAXS][CMAXN2][2];
+#pragma unroll
+    for (int s = 0; s < CMAXS; ++s)
+#pragma unroll
+        for (int j = 0; j < CMAXN2; ++j) acc[s][j][0] = acc[s][j][1] = 0.0;
+    int cb = 0, ch = 0;
+    for (int it = 0; it < nIt; ++it) {
+        const int st = it & 1;
+        const double *ys = Ys + 2 * st * CBUF, *ps = ys + CBUF;
+        mbar_wait(smem_addr(&bars[st]), (it >> 1) & 1);                    // the chunk is staged
+        const int nk = (min(CTO, v.no - ch * CTO) + 3) / 4;
+#pragma unroll
+        for (int s = 0; s < CMAXS; ++s) {
+            if (sw[s] < 0) continue;
+            const double *ya = ys + offA[s], *pa = ps + offA[s], *yb = ys + offB[s], *pb = ps + offB[s];
+            switch (sw[s] >> 16) {
+            case 4: strip_steps<4>(acc[s], ya, pa, yb, pb, nk); break;
+            case 3: strip_steps<3>(acc[s], ya, pa, yb, pb, nk); break;
+            case 2: strip_steps<2>(acc[s], ya, pa, yb, pb, nk); break;
+            default: strip_steps<1>(acc[s], ya, pa, yb, pb, nk); break;
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_addr(&bars[2 + st]));              // this warp no longer reads the stage
+        if (ch == nChunks - 1) {
+            double *Jc = v.J + (size_t)v.Q * (pl0 + cb);
+#pragma unroll
+            for (int s = 0; s < CMAXS; ++s) {
+                if (sw[s] < 0) continue;
+                const int b1 = sw[s] & 0xFF, b2 = (sw[s] >> 8) & 0xFF, n2 = sw[s] >> 16;
+                const int f = v.rowFrag[srow[b1 * CB8]];
+                const int rs = v.rowStart[f], rf = v.rowStart[f + 1] - rs;
+                const int ra = srow[b1 * CB8 + g4];
+                double *Jp = Jc + v.qoff[f];
+#pragma unroll
+                for (int j = 0; j < CMAXN2; ++j) {
+                    if (j < n2) {
+                        const bool diag = (b2 + j == b1);
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const int rb = srow[(b2 + j) * CB8 + 2 * t4 + e];
+                            if (ra >= 0 && rb >= 0 && !(diag && 2 * t4 + e < g4)) {
+                                const long long al = ra - rs, bl = rb - rs;
+                                const double val = 2.0 * acc[s][j][e];
+                                Jp[al + rf * bl] = val;
+                                Jp[bl + rf * al] = val;
+                            }
+                        }
+                    }
+                    acc[s][j][0] = acc[s][j][1] = 0.0;
+                }
+            }
+        }
+        if (++ch == nChunks) { ch = 0; ++cb; }
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // host: plan, launch
 // ------------------------------------------------------------------------------------------
@@ -365,6 +574,13 @@ int launch_contract_panels(const ContractPlan *c, const JacView &v, const double
     // per device (function attributes live in the context of the current device): set on every launch
     QC_CUDA(cudaFuncSetAttribute(contract_panels_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CSMEM));
     QC_CUDA(cudaFuncSetAttribute(contract_panels_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CSMEM));
+    // unmeasured warp-specialised variant (see the kernel's comment): only on request
+    const char *wsEnv = getenv("QCDMET_B200_CONTRACT_WS");
+    const bool ws = wsEnv && wsEnv[0] == '1';
+    if (ws) {
+        QC_CUDA(cudaFuncSetAttribute(contract_panels_ws_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM));
+        QC_CUDA(cudaFuncSetAttribute(contract_panels_ws_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM));
+    }
     // gridDim.y is limited to 65535 batches of CCB columns: chunk the columns
     const int chunk = 65535 * CCB;
     for (int c0 = 0; c0 < ncols; c0 += chunk) {
@@ -374,7 +590,13 @@ int launch_contract_panels(const ContractPlan *c, const JacView &v, const double
         w.colEnd = w.colBegin + nc;
         w.J = v.J + (size_t)v.Q * c0;
         const dim3 grid((unsigned)s.nTiles, (unsigned)((nc + CCB - 1) / CCB));
-        if (nnzAtMost2)
+        if (ws && nnzAtMost2)
+            contract_panels_ws_kernel<true><<<grid, WS_NT, WS_SMEM, st>>>(
+                w, M, elU, reinterpret_cast<const int4 *>(c->d_tileInfo), c->d_slotRow, c->d_strips);
+        else if (ws)
+            contract_panels_ws_kernel<false><<<grid, WS_NT, WS_SMEM, st>>>(
+                w, M, elU, reinterpret_cast<const int4 *>(c->d_tileInfo), c->d_slotRow, c->d_strips);
+        else if (nnzAtMost2)
             contract_panels_kernel<true><<<grid, CNT, CSMEM, st>>>(
                 w, M, elU, reinterpret_cast<const int4 *>(c->d_tileInfo), c->d_slotRow, c->d_strips);
         else

@@ -20,3 +20,11 @@ if [ "${NCU4000:-0}" = "1" ]; then
     python bench.py --norb 4000 --steps 1 --warmup 3 --no-cpu-baseline --no-e2e --check-cols 0 > gpurun_out/ncu_full_N4000.log 2>&1
   echo "ncu N=4000 rc=$?"; tail -3 gpurun_out/ncu_full_N4000.log
 fi
+if [ "${WS:-0}" = "1" ]; then   # the unmeasured warp-specialised contraction variant
+  QCDMET_TEST_EXPERIMENTAL=1 timeout 200 python -m pytest tests -m gpu -q --tb=short -k experimental > gpurun_out/pytest_ws.log 2>&1
+  echo "pytest ws rc=$?"; tail -5 gpurun_out/pytest_ws.log
+  for wl in sn2 polyyne; do
+    QCDMET_B200_CONTRACT_WS=1 timeout 100 python bench.py --workload $wl --steps 5 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/bench_ws_$wl.json 2> gpurun_out/bench_ws_$wl.err
+    echo "bench ws $wl rc=$?"; cat gpurun_out/bench_ws_$wl.json
+  done
+fi
