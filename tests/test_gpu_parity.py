@@ -467,7 +467,7 @@ def test_compat_full_response_sliced():
 
 
 @pytest.mark.skipif(os.environ.get("QCDMET_TEST_EXPERIMENTAL") != "1",
-                    reason="unmeasured warp-specialised contraction kernel: set QCDMET_TEST_EXPERIMENTAL=1")
+                    reason="opt-in warp-specialised contraction kernel: set QCDMET_TEST_EXPERIMENTAL=1")
 @pytest.mark.parametrize("shape", ["sn2", "polyyne", "frag100", "ti_m5", "random_lists"])
 def test_experimental_ws_contraction_is_bit_identical(shape, monkeypatch):
     """QCDMET_B200_CONTRACT_WS=1 (staging warps + DMMA warps) must reproduce the default

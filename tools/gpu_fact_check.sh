@@ -20,7 +20,7 @@ if [ "${NCU4000:-0}" = "1" ]; then
     python bench.py --norb 4000 --steps 1 --warmup 3 --no-cpu-baseline --no-e2e --check-cols 0 > gpurun_out/ncu_full_N4000.log 2>&1
   echo "ncu N=4000 rc=$?"; tail -3 gpurun_out/ncu_full_N4000.log
 fi
-if [ "${WS:-0}" = "1" ]; then   # the unmeasured warp-specialised contraction variant
+if [ "${WS:-0}" = "1" ]; then   # the opt-in warp-specialised contraction variant
   QCDMET_TEST_EXPERIMENTAL=1 timeout 200 python -m pytest tests -m gpu -q --tb=short -k experimental > gpurun_out/pytest_ws.log 2>&1
   echo "pytest ws rc=$?"; tail -5 gpurun_out/pytest_ws.log
   for wl in sn2 polyyne; do
