@@ -188,6 +188,13 @@ int  qcdmet_plan_kernel_time_ms(qcdmet_plan *plan, double *ms);
 int qcdmet_schedule_info(int Norb, int Nterms, int numPairs, const int *H1start, const int *H1row,
                          const int *H1col, int Nfrag, const int *rowStart, const int *rowIdx, int *info);
 
+/* Host-only: the kernel QCDMET_KERNEL_AUTO selects for these lists (QCDMET_KERNEL_DMMA, _FACTORISED or _GENERAL)
+ * and, for the factorised path, the device memory its site panels and tiled operands need (panel_bytes, may be
+ * NULL).  At plan creation the factorised path is additionally refused -- and the general kernel used -- when
+ * panel_bytes exceeds half of the free device memory.  rowIdx == NULL means dense projector rows. */
+int qcdmet_auto_kernel(int Norb, int Nterms, int numPairs, const int *H1start, const int *H1row, const int *H1col,
+                       int Nfrag, const int *rowStart, const int *rowIdx, int *kernel, long long *panel_bytes);
+
 /* Host-only: the tile schedule of the factorised path's contraction kernel (csrc/kernels_contract.cu) for
  * these fragment rows.  counts[3] = { tiles, row slots, strip-table entries (24 per tile) }; the arrays may be
  * NULL (size query), else tileInfo[4 * tiles] = { slotBegin, nSlots, first strip-table entry, nStrips } per

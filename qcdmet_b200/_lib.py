@@ -69,6 +69,9 @@ SIGNATURES = {
     "qcdmet_plan_kernel_time_ms": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     "qcdmet_schedule_info": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
                                             ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "qcdmet_auto_kernel": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
+                                          ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
+                                          ctypes.c_void_p, ctypes.c_void_p]),
     "qcdmet_contract_schedule": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                                 ctypes.c_void_p, ctypes.c_void_p]),
     "qcdmet_last_error": (ctypes.c_char_p, []),
@@ -133,6 +136,19 @@ def schedule_info(norb, num_pairs, h1start, h1row, h1col, row_start, row_idx=Non
     out = dict(zip(keys, (int(v) for v in info)))
     out["why"] = lib.qcdmet_last_error().decode() if not out["eligible"] else ""
     return out
+
+
+def auto_kernel(norb, num_pairs, h1start, h1row, h1col, row_start, row_idx=None):
+    """Host-only: (kernel id AUTO would select, bytes of site panels + tiled operands for the factorised path)."""
+    lib = load()
+    hs, hr, hc, rs, ri = as_i32(h1start), as_i32(h1row), as_i32(h1col), as_i32(row_start), as_i32(row_idx)
+    if hr.size == 0:
+        hr = hc = np.zeros(1, dtype=np.int32)
+    kernel = ctypes.c_int(-1)
+    nbytes = ctypes.c_longlong(0)
+    check(lib.qcdmet_auto_kernel(int(norb), len(hs) - 1, int(num_pairs), _ptr(hs), _ptr(hr), _ptr(hc), len(rs) - 1,
+                                 _ptr(rs), _ptr(ri), ctypes.byref(kernel), ctypes.byref(nbytes)))
+    return kernel.value, nbytes.value
 
 
 def contract_schedule(row_start):

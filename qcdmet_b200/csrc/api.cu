@@ -281,6 +281,33 @@ int qcdmet_schedule_info(int Norb, int Nterms, int numPairs, const int *H1start,
     return QCDMET_OK;
 }
 
+int qcdmet_auto_kernel(int Norb, int Nterms, int numPairs, const int *H1start, const int *H1row, const int *H1col,
+                       int Nfrag, const int *rowStart, const int *rowIdx, int *kernel, long long *panel_bytes)
+{
+    QC_CHECK(kernel != nullptr, QCDMET_E_ARG, "kernel is NULL");
+    static const double dummyR = 0.0;
+    QC_TRY(validate_lists(Norb, Nterms, numPairs, H1start, H1row, H1col, Nfrag, rowStart,
+                          rowIdx ? nullptr : &dummyR, rowIdx));
+    if (panel_bytes) *panel_bytes = 0;
+    const int S = Nfrag > 0 ? rowStart[Nfrag] : 0;
+    std::string why;
+    if (dmma_eligible(Norb, Nterms, Nfrag, H1start, H1row, H1col, rowStart, rowIdx, rowIdx == nullptr, &why)) {
+        *kernel = QCDMET_KERNEL_DMMA;
+        return QCDMET_OK;
+    }
+    *kernel = QCDMET_KERNEL_GENERAL;
+    if (Nterms == 0 || S == 0) { set_error("general kernel: empty problem"); return QCDMET_OK; }
+    std::string fwhy;
+    if (!fact_eligible(Nterms, H1start, &fwhy)) { set_error("general kernel: %s", fwhy.c_str()); return QCDMET_OK; }
+    if ((long long)S * round_up(numPairs, 16) >= (1LL << 31)) {
+        set_error("general kernel: fragment rows x occupied orbitals >= 2^31");
+        return QCDMET_OK;
+    }
+    *kernel = QCDMET_KERNEL_FACTORISED;
+    if (panel_bytes) *panel_bytes = (long long)fact_plan_bytes(Norb, numPairs, Nterms, S, H1start, H1row);
+    return QCDMET_OK;
+}
+
 int qcdmet_contract_schedule(int Nfrag, const int *rowStart, int *counts, int *tileInfo, int *slotRow, int *strips)
 {
     QC_CHECK(counts != nullptr, QCDMET_E_ARG, "counts is NULL");

@@ -195,3 +195,31 @@ def test_contraction_schedule_covers_every_block_element_once():
     # a whole fragment stays in one tile up to 12 blocks (96 rows); beyond that it is cut into slice pairs
     assert len(_lib.contract_schedule(np.array([0, 96]))) == 1
     assert len(_lib.contract_schedule(np.array([0, 97]))) == 3
+
+
+def test_auto_kernel_selection_rules():
+    """Host-only mirror of the selection made at plan creation (qcdmet_auto_kernel): fused DMMA kernel for
+    impurities of <= 4 orbitals (<= 8 rows with bath), factorised path for larger fragments with <= 64 elements
+    per perturbation, general kernel otherwise."""
+    from qcdmet_b200 import _lib
+    dmma, fact, general = _lib.KERNEL_DMMA, _lib.KERNEL_FACTORISED, _lib.KERNEL_GENERAL
+    cases = [
+        (wl.sweep(64), dmma), (wl.hubbard24(False, l=8), dmma), (wl.hubbard24(True, l=8), dmma),
+        (wl.hubbard24(True, fit_imp_bath=True, l=8), dmma), (wl.hydrogen_like(), dmma),
+        (wl.make_workload("b4", 44, 20, [4, 4], fit_imp_bath=True), dmma),
+        (wl.polyyne_like(), fact), (wl.sn2_like(), fact), (wl.make_workload("f5", 40, 17, [5, 4, 3]), fact),
+        (wl.make_workload("b5", 44, 20, [5, 3], fit_imp_bath=True), fact),
+        (wl.make_workload("ti5", 40, 18, [5] * 8, trans_inv=True), fact),          # 8 cells: 8 / 16 elements
+        (wl.make_workload("ti5g", 200, 90, [5] * 40, trans_inv=True), general),    # 40 cells: 80 elements
+    ]
+    for w, expect in cases:
+        kernel, nbytes = _lib.auto_kernel(w.norb, w.num_pairs, w.h1start, w.h1row, w.h1col, w.row_start, w.row_idx)
+        assert kernel == expect, w.name
+        assert (nbytes > 0) == (expect == fact)
+    # site panels of the sn2-like shape: 324 site slots x 321 rows x 64 occupied columns x 8 bytes + tiled operands
+    _, nbytes = _lib.auto_kernel(321, 58, *(lambda w: (w.h1start, w.h1row, w.h1col, w.row_start, w.row_idx))(wl.sn2_like()))
+    assert 324 * 321 * 64 * 8 <= nbytes < 1.1 * 324 * 321 * 64 * 8
+    # the compat full response (one fragment holding every site) goes through the factorised path
+    w = wl.sweep(100, nterms=23)
+    kernel, _ = _lib.auto_kernel(100, 50, w.h1start, w.h1row, w.h1col, np.array([0, 100]), np.arange(100))
+    assert kernel == fact
