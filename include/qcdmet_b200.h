@@ -26,6 +26,8 @@
 #ifndef QCDMET_B200_H
 #define QCDMET_B200_H
 
+#include <stddef.h>
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -110,6 +112,29 @@ int qcdmet_plan_create(qcdmet_plan **plan, int device, int Norb, int Nterms, int
                        int Nfrag, const int *rowStart, const double *R, const int *rowIdx);
 int qcdmet_plan_destroy(qcdmet_plan *plan);
 
+/* ---- Single-process multi-GPU: the in-library parallel region of lib/rhf_response.cc:73-79 -------------
+ * The reference parallelises inside the library call (an OpenMP team over the perturbations); here a plan
+ * can span several GPUs of one node the same way, so the ctypes boundary stays a drop-in:
+ *   qcdmet_set_devices(n)        process-wide default for plans created afterwards on the current device
+ *                                (device < 0 in qcdmet_plan_create, i.e. also qcdmet_jacobian* and the Python
+ *                                helper); n = -1: every visible device.  $QCDMET_B200_DEVICES = n | "all" sets
+ *                                the same default without touching the caller's code.
+ *   qcdmet_plan_set_devices      the same for one plan (devices plan->device, +1, ... mod the device count).
+ * One eigensolve on the first device, (C, e) copied to the others over NVLink (bit-identical orbitals);
+ * every device launches its share from the caller's thread; an event barrier replaces the collective.
+ * Fused DMMA kernel: each device executes 1/n of the block-pair list and stores every Jacobian element into all
+ * devices' buffers (NVLink peer stores).  Other kernels: contiguous column slices, copied to the first device.
+ * qcdmet_plan_get_jacobian ships 1/n of the columns from every device over its own PCIe link. */
+int qcdmet_set_devices(int n);
+int qcdmet_get_devices(void);
+int qcdmet_plan_set_devices(qcdmet_plan *plan, int n);
+int qcdmet_plan_num_devices(qcdmet_plan *plan);
+
+/* Page-locked host memory (cudaHostAlloc, portable): destination buffers that the device->host copy of the
+ * Jacobian reaches at full PCIe rate from every device. */
+void *qcdmet_host_alloc(size_t bytes);
+int qcdmet_host_free(void *ptr);
+
 /* Restrict the plan to Jacobian columns [colBegin, colEnd) (multi-GPU column sharding). */
 int qcdmet_plan_set_columns(qcdmet_plan *plan, int colBegin, int colEnd);
 /* QCDMET_KERNEL_*; default AUTO. */
@@ -142,6 +167,12 @@ int qcdmet_plan_set_h0(qcdmet_plan *plan, const double *H0);
 /* Upload orbitals (host; layout as in qcdmet_jacobian_from_orbitals), build the panels. */
 int qcdmet_plan_set_orbitals(qcdmet_plan *plan, const double *C, const double *e);
 
+/* Device pointers of the plan's orbital buffers (C: column-major Norb x Norb, eigenvector k in column k; e:
+ * ascending) so that a caller can fill them in place -- e.g. an NCCL broadcast from the rank that ran the
+ * eigensolve (set_h0) -- and then, after synchronising its own stream, commit them (panels are rebuilt). */
+int qcdmet_plan_orbitals_device(qcdmet_plan *plan, void **C, void **e);
+int qcdmet_plan_commit_orbitals(qcdmet_plan *plan);
+
 /* Launch the Jacobian kernels for the plan's column range (asynchronous on the plan stream;
  * inputs and output stay in HBM). */
 int qcdmet_plan_compute(qcdmet_plan *plan);
@@ -152,6 +183,8 @@ int qcdmet_plan_sync(qcdmet_plan *plan);
 void *qcdmet_plan_jacobian_device(qcdmet_plan *plan);
 /* Blocking device->host copies. */
 int qcdmet_plan_get_jacobian(qcdmet_plan *plan, double *J);
+/* Columns [c0, c1) of the computed slice only (J points at the first of them). */
+int qcdmet_plan_get_jacobian_columns(qcdmet_plan *plan, int c0, int c1, double *J);
 int qcdmet_plan_get_dblocks(qcdmet_plan *plan, double *D_blocks);
 int qcdmet_plan_get_eigenvalues(qcdmet_plan *plan, double *e);
 int qcdmet_plan_get_orbitals(qcdmet_plan *plan, double *C);
@@ -180,6 +213,26 @@ double qcdmet_plan_flops(qcdmet_plan *plan);               /* FP64 flops execute
 /* Device time of the dominant kernel of the last compute (CUDA events recorded on the plan
  * stream around that launch; synchronises the stream).  ms < 0 if nothing was computed. */
 int  qcdmet_plan_kernel_time_ms(qcdmet_plan *plan, double *ms);
+
+/* Breakdown of the last step in ms (-1 = not measured): ms[5] = { H2D of H0, cuSOLVER syevd, panel build
+ * (CUDA events inside qcdmet_plan_set_h0), dominant kernel of the first device's share, device->host copy of the
+ * Jacobian (wall clock of the last qcdmet_plan_get_jacobian*) }.  Synchronises the plan. */
+int  qcdmet_plan_timings(qcdmet_plan *plan, double *ms);
+/* Checksum of the computed slice on the device: out[2] = { sum, sum of squares } in a fixed reduction order
+ * (reproducible run to run and device to device), *bits = xor of the 64-bit patterns of all elements.
+ * identical (may be NULL): 1 if every device of a multi-device plan holds a bit-identical Jacobian. */
+int  qcdmet_plan_jacobian_checksum(qcdmet_plan *plan, double *out, unsigned long long *bits, int *identical);
+/* Benchmark utility: overwrite a 256 MB scratch buffer on every device of the plan (on the plan's streams), so
+ * that the next step does not start from a warm 126 MB L2. */
+int  qcdmet_plan_flush_l2(qcdmet_plan *plan);
+/* Note left by QCDMET_KERNEL_AUTO when it had to use the general FP64 kernel (why the fused and the
+ * factorised path do not apply); empty string otherwise. */
+const char *qcdmet_plan_info(qcdmet_plan *plan);
+
+/* Sustained DMMA.8x8x4 (mma.sync.m8n8k4.f64) issue rate of a device in TFLOP/s, measured for about `seconds`:
+ * the FP64 tensor-pipe ceiling the roofline of the Jacobian kernel is quoted against (MEASURED_PEAKS.json has no
+ * FP64 entry).  device < 0: current device. */
+int qcdmet_measure_fp64_peak(int device, double seconds, double *tflops);
 
 /* Host-only (no device needed): the schedule the DMMA kernel would use for these lists.
  * info[10] = { eligible, rows-per-fragment variant (4|8), 8-column fragments per warp (8|6|4), components,

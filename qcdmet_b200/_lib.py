@@ -74,6 +74,22 @@ SIGNATURES = {
                                           ctypes.c_void_p, ctypes.c_void_p]),
     "qcdmet_contract_schedule": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                                 ctypes.c_void_p, ctypes.c_void_p]),
+    "qcdmet_set_devices": (ctypes.c_int, [ctypes.c_int]),
+    "qcdmet_get_devices": (ctypes.c_int, []),
+    "qcdmet_plan_set_devices": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
+    "qcdmet_plan_num_devices": (ctypes.c_int, [ctypes.c_void_p]),
+    "qcdmet_host_alloc": (ctypes.c_void_p, [ctypes.c_size_t]),
+    "qcdmet_host_free": (ctypes.c_int, [ctypes.c_void_p]),
+    "qcdmet_plan_orbitals_device": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p),
+                                                   ctypes.POINTER(ctypes.c_void_p)]),
+    "qcdmet_plan_commit_orbitals": (ctypes.c_int, [ctypes.c_void_p]),
+    "qcdmet_plan_get_jacobian_columns": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
+    "qcdmet_plan_timings": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
+    "qcdmet_plan_jacobian_checksum": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p,
+                                                     ctypes.POINTER(ctypes.c_ulonglong), ctypes.POINTER(ctypes.c_int)]),
+    "qcdmet_plan_info": (ctypes.c_char_p, [ctypes.c_void_p]),
+    "qcdmet_plan_flush_l2": (ctypes.c_int, [ctypes.c_void_p]),
+    "qcdmet_measure_fp64_peak": (ctypes.c_int, [ctypes.c_int, ctypes.c_double, ctypes.POINTER(ctypes.c_double)]),
     "qcdmet_last_error": (ctypes.c_char_p, []),
     "qcdmet_version": (ctypes.c_char_p, []),
     "qcdmet_device_count": (ctypes.c_int, []),
@@ -175,11 +191,59 @@ def contract_schedule(row_start):
     return tiles
 
 
+def set_devices(n):
+    """Process-wide default number of GPUs per plan (plans created afterwards with device=-1); -1 = all."""
+    check(load().qcdmet_set_devices(int(n)))
+
+
+def get_devices():
+    return int(load().qcdmet_get_devices())
+
+
+def measure_fp64_peak(device=-1, seconds=0.3):
+    """Sustained DMMA.8x8x4 rate of the device in TFLOP/s (the roofline denominator, measured in-process)."""
+    out = ctypes.c_double(0.0)
+    check(load().qcdmet_measure_fp64_peak(int(device), float(seconds), ctypes.byref(out)))
+    return out.value
+
+
+class _PinnedHolder:
+    """Owns one cudaHostAlloc block; freed when the last numpy view of it is collected."""
+
+    def __init__(self, nbytes):
+        self.lib = load()
+        self.ptr = self.lib.qcdmet_host_alloc(int(nbytes))
+        if not self.ptr:
+            raise QcdmetError(-4, self.lib.qcdmet_last_error().decode())
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                self.lib.qcdmet_host_free(ctypes.c_void_p(self.ptr))
+                self.ptr = None
+        except (AttributeError, TypeError):
+            pass
+
+
+def pinned_empty(shape, order="F"):
+    """float64 numpy array in page-locked host memory (cudaHostAlloc): device<->host copies reach it at the
+    full PCIe rate of every GPU.  The memory lives as long as any view of the array."""
+    shape = tuple(int(x) for x in (shape if isinstance(shape, (tuple, list)) else (shape,)))
+    n = int(np.prod(shape)) if shape else 1
+    holder = _PinnedHolder(8 * max(n, 1))
+    carr = (ctypes.c_double * max(n, 1)).from_address(holder.ptr)
+    carr._holder = holder                       # numpy keeps carr alive, carr keeps the allocation alive
+    return np.frombuffer(carr, dtype=np.float64, count=n).reshape(shape, order=order)
+
+
 class Plan:
-    """Thin RAII wrapper over qcdmet_plan_* (device-resident perturbation list + fragment rows)."""
+    """Thin RAII wrapper over qcdmet_plan_* (device-resident perturbation list + fragment rows).
+
+    devices: number of GPUs the plan spans inside this process (None: the library default, i.e. 1 unless
+    qcdmet_set_devices / $QCDMET_B200_DEVICES says otherwise and device == -1)."""
 
     def __init__(self, norb, num_pairs, h1start, h1row, h1col, row_start, rows=None, row_idx=None,
-                 device=-1):
+                 device=-1, devices=None):
         self.lib = load()
         self.norb, self.num_pairs = int(norb), int(num_pairs)
         self._keep = [as_i32(h1start), as_i32(h1row), as_i32(h1col), as_i32(row_start), as_f64(rows),
@@ -195,6 +259,16 @@ class Plan:
                                           _ptr(rs), _ptr(r), _ptr(ri)))
         self.nresid = int(self.lib.qcdmet_plan_num_residuals(self.handle))
         self.col_begin, self.col_end = 0, self.nterms
+        self._pinned_out = None
+        if devices is not None:
+            self.set_devices(devices)
+
+    def set_devices(self, n):
+        check(self.lib.qcdmet_plan_set_devices(self.handle, int(n)))
+
+    @property
+    def num_devices(self):
+        return int(self.lib.qcdmet_plan_num_devices(self.handle))
 
     def close(self):
         try:
@@ -257,14 +331,60 @@ class Plan:
     def sync(self):
         check(self.lib.qcdmet_plan_sync(self.handle))
 
-    def jacobian(self, out=None):
-        """(Q, ncols) float64, Fortran order: the memory of the reference's returned array."""
+    def jacobian(self, out=None, pinned=False):
+        """(Q, ncols) float64, Fortran order: the memory of the reference's returned array.
+
+        out: caller's array (any host memory).  pinned=True (and out None): the plan's own page-locked
+        buffer is reused -- the returned array is overwritten by the next call with pinned=True."""
         ncols = self.col_end - self.col_begin
-        if out is None:
+        if out is None and pinned:
+            if self._pinned_out is None or self._pinned_out.shape != (self.nresid, ncols):
+                self._pinned_out = pinned_empty((self.nresid, ncols), order="F")
+            out = self._pinned_out
+        elif out is None:
             out = np.empty((self.nresid, ncols), dtype=np.float64, order="F")
         assert out.flags.f_contiguous and out.shape == (self.nresid, ncols)
         check(self.lib.qcdmet_plan_get_jacobian(self.handle, _ptr(out)))
         return out
+
+    def jacobian_columns(self, c0, c1, out=None):
+        """Columns [c0, c1) of the computed slice, (Q, c1 - c0) Fortran order."""
+        if out is None:
+            out = np.empty((self.nresid, c1 - c0), dtype=np.float64, order="F")
+        assert out.flags.f_contiguous and out.shape == (self.nresid, c1 - c0)
+        check(self.lib.qcdmet_plan_get_jacobian_columns(self.handle, int(c0), int(c1), _ptr(out)))
+        return out
+
+    def timings(self):
+        """dict of the last step's breakdown in ms (None = not measured)."""
+        ms = np.zeros(5, dtype=np.float64)
+        check(self.lib.qcdmet_plan_timings(self.handle, _ptr(ms)))
+        keys = ("h2d_ms", "syevd_ms", "panels_ms", "kernel_ms", "d2h_ms")
+        return {k: (float(v) if v >= 0 else None) for k, v in zip(keys, ms)}
+
+    def checksum(self):
+        """(sum, sum of squares, xor of the bit patterns, all devices identical) of the Jacobian on the device."""
+        out = np.zeros(2, dtype=np.float64)
+        bits = ctypes.c_ulonglong(0)
+        same = ctypes.c_int(1)
+        check(self.lib.qcdmet_plan_jacobian_checksum(self.handle, _ptr(out), ctypes.byref(bits), ctypes.byref(same)))
+        return float(out[0]), float(out[1]), int(bits.value), bool(same.value)
+
+    def flush_l2(self):
+        check(self.lib.qcdmet_plan_flush_l2(self.handle))
+
+    @property
+    def info(self):
+        return self.lib.qcdmet_plan_info(self.handle).decode()
+
+    def orbitals_device(self):
+        """(address of C, address of e) on the plan's (first) device."""
+        c, e = ctypes.c_void_p(), ctypes.c_void_p()
+        check(self.lib.qcdmet_plan_orbitals_device(self.handle, ctypes.byref(c), ctypes.byref(e)))
+        return c.value, e.value
+
+    def commit_orbitals(self):
+        check(self.lib.qcdmet_plan_commit_orbitals(self.handle))
 
     def lm_step(self, resid, lam):
         """Damped normal-equation step from the device-resident Jacobian.  Returns (step, max|J^T r|, g.step)."""

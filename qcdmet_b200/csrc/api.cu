@@ -1,9 +1,12 @@
-// api.cu -- C ABI of libqcdmet_b200.so: plans, host-buffer wrappers, compat rhf_response.
+// api.cu -- C ABI of libqcdmet_b200.so: plans, single-process multi-GPU groups, host-buffer wrappers,
+// compat rhf_response.
 #include "common.cuh"
 #include <cstdarg>
 #include <algorithm>
+#include <chrono>
 #include <numeric>
 #include <mutex>
+#include <thread>
 #include <cstdint>
 
 namespace qcdmet {
@@ -32,9 +35,11 @@ struct qcdmet_plan {
     bool denseRows = false;
     bool dmma_ok = false;
     std::string dmma_why;
+    std::string info;               // why AUTO left the fused / factorised kernel (qcdmet_plan_info)
     cudaStream_t stream = nullptr;
-    // host copies of the index arrays (schedule building, flop counts)
+    // host copies of the index arrays (schedule building, flop counts, plan-cache comparison)
     std::vector<int> h1start, h1row, h1col, rowStart, rowIdx;
+    uint64_t rHash[2] = {0, 0};     // two independent hashes of the dense projector rows R
     // device
     int *d_h1start = nullptr, *d_h1row = nullptr, *d_h1col = nullptr;
     int *d_rowStart = nullptr, *d_rowFrag = nullptr, *d_rowIdx = nullptr;
@@ -44,11 +49,12 @@ struct qcdmet_plan {
     double *d_CoT = nullptr, *d_CvT = nullptr, *d_PO = nullptr, *d_PV = nullptr;
     double *d_W = nullptr;              // [nv][ldo] denominators for the general kernel (built on first use)
     bool w_valid = false;
-    double *d_J = nullptr;          // where the Jacobian slice is written (own buffer or external)
+    double *d_J = nullptr;          // base of the Jacobian buffer in use (own buffer or external)
     double *d_J_own = nullptr;
     size_t J_capacity = 0;          // capacity of d_J_own
     double *d_J_ext = nullptr;
     size_t J_ext_capacity = 0;
+    bool fullLayout = false;        // d_J is laid out for all P columns (column p at Q p) whatever [colBegin, colEnd) is
     double *d_D = nullptr;
     double *d_work = nullptr;
     int lwork = 0;
@@ -66,6 +72,8 @@ struct qcdmet_plan {
     bool symmetric_used = false;
     // Levenberg-Marquardt normal equations on the device (qcdmet_plan_lm_step)
     double *d_A = nullptr, *d_Awork = nullptr, *d_g = nullptr, *d_r = nullptr, *d_potrf = nullptr;
+    double *d_Apart = nullptr;          // group members: this device's row block of J^T J
+    size_t Apart_capacity = 0;
     int potrf_lwork = 0;
     bool normal_valid = false;          // d_A = J^T J of the Jacobian in memory
     bool jac_in_memory = false;         // d_J holds a complete Jacobian (possibly of earlier orbitals)
@@ -73,6 +81,22 @@ struct qcdmet_plan {
     PeerSet peers;
     void *ipc_opened[QCDMET_MAX_PEERS] = {nullptr};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;   // around the dominant kernel of the last compute
+    // step breakdown (qcdmet_plan_timings): events on the plan stream around H2D / syevd / panel build
+    cudaEvent_t evT[4] = {nullptr, nullptr, nullptr, nullptr};
+    bool evT_valid = false;
+    double d2h_ms = -1.0;
+    // checksum scratch
+    double *d_ck = nullptr;
+    // L2 flush scratch (qcdmet_plan_flush_l2: bench / tests)
+    void *d_flush = nullptr;
+    // ---- single-process multi-GPU group: the in-library parallel region of lib/rhf_response.cc:73-79 ----
+    qcdmet_plan *leader = nullptr;            // set on member plans (devices 1 .. n-1 of the group)
+    std::vector<qcdmet_plan *> members;       // leader: every plan of the group, members[0] == this
+    cudaStream_t ownStream = nullptr;         // members: their own non-blocking stream
+    cudaEvent_t evOrb = nullptr;              // leader: orbitals are in d_C / d_e
+    cudaEvent_t evStart = nullptr;            // leader: start of a compute (earlier work on the leader stream is done)
+    cudaEvent_t evDone = nullptr;             // this plan's share of the last compute (kernels + shard exchange)
+    bool group_fused = false;                 // last group compute: fused all-gather (peer stores) vs column shards
 };
 
 namespace {
@@ -107,6 +131,14 @@ int dev_alloc(T **dst, size_t n)
     return dev_alloc_copy<T>(dst, nullptr, n);
 }
 
+bool in_group(const qcdmet_plan *p) { return p->members.size() > 1; }
+
+// first element of the column slice [colBegin, colEnd) inside the Jacobian buffer
+double *jac_slice(const qcdmet_plan *p)
+{
+    return p->fullLayout ? p->d_J + (size_t)p->Q * p->colBegin : p->d_J;
+}
+
 JacView make_view(const qcdmet_plan *p)
 {
     JacView v;
@@ -117,7 +149,7 @@ JacView make_view(const qcdmet_plan *p)
     v.rowStart = p->d_rowStart; v.rowFrag = p->d_rowFrag; v.qoff = p->d_qoff;
     v.CoT = p->d_CoT; v.CvT = p->d_CvT; v.PO = p->d_PO; v.PV = p->d_PV; v.e = p->d_e;
     v.W = p->d_W;
-    v.J = p->d_J;
+    v.J = jac_slice(p);
     return v;
 }
 
@@ -153,9 +185,18 @@ int validate_lists(int N, int P, int no, const int *h1start, const int *h1row, c
     return QCDMET_OK;
 }
 
+void release_fact(qcdmet_plan *p)
+{
+    if (p->fact) fact_plan_free(p->fact);
+    p->fact = nullptr;
+    p->fact_ok = false;
+    p->fact_orbitals_valid = false;
+}
+
 int ensure_jacobian_buffer(qcdmet_plan *p)
 {
-    const size_t need = (size_t)std::max<long long>(p->Q, 1) * std::max(p->colEnd - p->colBegin, 1);
+    const size_t cols = p->fullLayout ? (size_t)std::max(p->P, 1) : (size_t)std::max(p->colEnd - p->colBegin, 1);
+    const size_t need = (size_t)std::max<long long>(p->Q, 1) * cols;
     if (p->d_J_ext) {
         QC_CHECK(need <= p->J_ext_capacity, QCDMET_E_ARG,
                  "external Jacobian buffer too small: %zu doubles needed, %zu given", need, p->J_ext_capacity);
@@ -166,8 +207,18 @@ int ensure_jacobian_buffer(qcdmet_plan *p)
         if (p->d_J_own) cudaFree(p->d_J_own);
         p->d_J_own = nullptr;
         p->J_capacity = 0;
-        if (cudaMalloc((void **)&p->d_J_own, sizeof(double) * need) != cudaSuccess) {
+        cudaError_t err = cudaMalloc((void **)&p->d_J_own, sizeof(double) * need);
+        if (err != cudaSuccess && p->fact && p->kernel_req == QCDMET_KERNEL_AUTO) {
+            // the site panels of the factorised path took the room: give them back and let AUTO use the general kernel
             cudaGetLastError();
+            release_fact(p);
+            p->fact_tried = true;
+            p->fact_why = "site panels released: the Jacobian buffer did not fit next to them";
+            err = cudaMalloc((void **)&p->d_J_own, sizeof(double) * need);
+        }
+        if (err != cudaSuccess) {
+            cudaGetLastError();
+            p->d_J_own = nullptr;
             set_error("cudaMalloc of the Jacobian slice (%zu doubles) failed", need);
             return QCDMET_E_ALLOC;
         }
@@ -177,8 +228,18 @@ int ensure_jacobian_buffer(qcdmet_plan *p)
     return QCDMET_OK;
 }
 
-// Build the panels from d_C / d_e (already on the device).
-int build_panels(qcdmet_plan *p)
+// Everything derived from (C, e) is stale: called before the device orbitals are overwritten and on every
+// error path, so that a failed set_h0 / set_orbitals can never be combined with panels of other orbitals.
+void invalidate_orbitals(qcdmet_plan *p)
+{
+    p->have_orbitals = false;
+    p->have_jac = false;
+    p->w_valid = false;
+    p->fact_orbitals_valid = false;
+}
+
+// Operand panels from d_C / d_e (already on the device); asynchronous on the plan stream.
+int build_panels_async(qcdmet_plan *p)
 {
     QC_TRY(launch_split_transpose(p->d_C, p->N, p->no, p->d_CoT, p->ldo, p->d_CvT, p->ldv, p->stream));
     if (p->S > 0) {
@@ -203,22 +264,65 @@ int build_panels(qcdmet_plan *p)
     JacView v = make_view(p);
     QC_TRY(launch_dblocks(v, p->d_D, p->stream));
     if (p->dmma) QC_TRY(dmma_prepare_orbitals(p->dmma, v, p->stream));
-    // gap check (the response diverges for a vanishing HOMO-LUMO gap, lib/rhf_response.cc:66-71)
+    return QCDMET_OK;
+}
+
+// gap check (the response diverges for a vanishing HOMO-LUMO gap, lib/rhf_response.cc:66-71); synchronises.
+// solverInfo: also fetch the devInfo word of the eigensolver and report it first.
+int check_gap(qcdmet_plan *p, bool solverInfo = false)
+{
     double eg[2];
+    int info = 0;
+    if (solverInfo) QC_CUDA(cudaMemcpyAsync(&info, p->d_info, sizeof(int), cudaMemcpyDeviceToHost, p->stream));
     QC_CUDA(cudaMemcpyAsync(eg, p->d_e + p->no - 1, 2 * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
     QC_CUDA(cudaStreamSynchronize(p->stream));
+    QC_CHECK(info == 0, QCDMET_E_SOLVER, "cusolverDnDsyevd: info = %d", info);
     QC_CHECK(eg[1] - eg[0] > 0.0, QCDMET_E_GAP,
              "HOMO-LUMO gap %.3e is not positive: the RHF response is undefined", eg[1] - eg[0]);
-    p->have_orbitals = true;
-    p->have_jac = false;
-    p->w_valid = false;
-    p->fact_orbitals_valid = false;
     return QCDMET_OK;
+}
+
+int ensure_timing_events(qcdmet_plan *p)
+{
+    if (!p->evT[0])
+        for (int i = 0; i < 4; ++i) QC_CUDA(cudaEventCreate(&p->evT[i]));
+    return QCDMET_OK;
+}
+
+// Members of a group: receive (C, e) from the leader over NVLink once the leader's stream has produced them,
+// and build their own panels.  One eigensolve per step for the whole group: bit-identical orbitals everywhere.
+int group_broadcast_orbitals(qcdmet_plan *p)
+{
+    if (!in_group(p)) return QCDMET_OK;
+    QC_CUDA(cudaEventRecord(p->evOrb, p->stream));
+    for (size_t m = 1; m < p->members.size(); ++m) {
+        qcdmet_plan *q = p->members[m];
+        DeviceGuard guard(q->device);
+        invalidate_orbitals(q);
+        QC_CUDA(cudaStreamWaitEvent(q->stream, p->evOrb, 0));
+        QC_CUDA(cudaMemcpyPeerAsync(q->d_C, q->device, p->d_C, p->device, sizeof(double) * (size_t)p->N * p->N, q->stream));
+        QC_CUDA(cudaMemcpyPeerAsync(q->d_e, q->device, p->d_e, p->device, sizeof(double) * (size_t)p->N, q->stream));
+        QC_TRY(build_panels_async(q));
+    }
+    return QCDMET_OK;
+}
+
+void group_mark_orbitals(qcdmet_plan *p, bool ok)
+{
+    for (qcdmet_plan *q : p->members) {
+        if (ok) q->have_orbitals = true;
+        else invalidate_orbitals(q);
+    }
+    if (p->members.empty()) {
+        if (ok) p->have_orbitals = true;
+        else invalidate_orbitals(p);
+    }
 }
 
 // Build the factorised-path schedule and buffers on first use.  Not an error if the path does not apply
 // (too many elements per perturbation, panel array larger than half of the free device memory): the plan
-// then keeps the general kernel; fact_why says why.
+// then keeps the general kernel; fact_why says why.  Called when the Jacobian buffer has been allocated,
+// so the memory test sees what is really left.
 int ensure_fact(qcdmet_plan *p)
 {
     if (p->fact_tried) return QCDMET_OK;
@@ -229,11 +333,15 @@ int ensure_fact(qcdmet_plan *p)
     if ((long long)p->S * p->ldo >= (1LL << 31)) { p->fact_why = "fragment rows x occupied orbitals >= 2^31"; return QCDMET_OK; }
     size_t freeB = 0, totalB = 0;
     QC_CUDA(cudaMemGetInfo(&freeB, &totalB));
+    // what compute() still has to allocate next to the panels: the Jacobian buffer if it is not there yet
+    const size_t cols = p->fullLayout ? (size_t)p->P : (size_t)std::max(p->colEnd - p->colBegin, 1);
+    const size_t jac = (size_t)std::max<long long>(p->Q, 1) * cols;
+    const size_t pending = (p->d_J_ext || jac <= p->J_capacity) ? 0 : jac * sizeof(double);
     const size_t need = fact_plan_bytes(p->N, p->no, p->P, p->S, p->h1start.data(), p->h1row.data());
-    if (need > freeB / 2) {
-        char buf[160];
-        snprintf(buf, sizeof(buf), "site panels need %.2f GB, more than half of the free device memory (%.2f GB)",
-                 need * 1e-9, freeB * 1e-9);
+    if (pending >= freeB || need > (freeB - pending) / 2) {
+        char buf[200];
+        snprintf(buf, sizeof(buf), "site panels need %.2f GB, more than half of the free device memory (%.2f GB free, "
+                 "%.2f GB reserved for the Jacobian)", need * 1e-9, freeB * 1e-9, pending * 1e-9);
         p->fact_why = buf;
         return QCDMET_OK;
     }
@@ -261,12 +369,350 @@ double count_flops_general(const qcdmet_plan *p)
     return total;
 }
 
+uint64_t fnv1a(uint64_t h, const void *data, size_t bytes)
+{
+    const unsigned char *p = (const unsigned char *)data;
+    for (size_t i = 0; i < bytes; ++i) { h ^= p[i]; h *= 1099511628211ULL; }
+    return h;
+}
+// second, independent hash (64-bit words, multiply-xorshift mixing) of the dense projector rows
+uint64_t mix64(uint64_t h, const void *data, size_t bytes)
+{
+    const unsigned char *p = (const unsigned char *)data;
+    size_t i = 0;
+    for (; i + 8 <= bytes; i += 8) {
+        uint64_t w;
+        memcpy(&w, p + i, 8);
+        h = (h ^ w) * 0x9E3779B97F4A7C15ULL;
+        h ^= h >> 29;
+    }
+    for (; i < bytes; ++i) { h = (h ^ p[i]) * 0xBF58476D1CE4E5B9ULL; h ^= h >> 31; }
+    return h;
+}
+
+// process-wide default number of devices per plan: qcdmet_set_devices() or $QCDMET_B200_DEVICES (0 = not set yet)
+int g_default_devices = 0;
+std::mutex g_dev_mu;
+
+int default_devices()
+{
+    std::lock_guard<std::mutex> lock(g_dev_mu);
+    if (g_default_devices == 0) {
+        g_default_devices = 1;
+        const char *env = getenv("QCDMET_B200_DEVICES");
+        if (env && *env) {
+            int n = !strcmp(env, "all") ? -1 : atoi(env);
+            int ndev = 0;
+            if (cudaGetDeviceCount(&ndev) != cudaSuccess) { cudaGetLastError(); ndev = 0; }
+            if (n < 0) n = ndev;
+            g_default_devices = std::max(1, std::min(n, std::min(ndev, QCDMET_MAX_PEERS)));
+        }
+    }
+    return g_default_devices;
+}
+
+// deterministic checksum of a device array: per-block partial (sum, sum of squares, xor of the bit patterns)
+// in a fixed reduction order; the host adds the partials in block order
+constexpr int CK_BLOCKS = 512, CK_THREADS = 256;
+__global__ void checksum_kernel(const double *__restrict__ x, size_t n, double *__restrict__ out)
+{
+    __shared__ double s1[CK_THREADS], s2[CK_THREADS];
+    __shared__ unsigned long long sx[CK_THREADS];
+    double a = 0.0, b = 0.0;
+    unsigned long long c = 0ULL;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const double v = x[i];
+        a += v;
+        b += v * v;
+        c ^= (unsigned long long)__double_as_longlong(v);
+    }
+    s1[threadIdx.x] = a; s2[threadIdx.x] = b; sx[threadIdx.x] = c;
+    __syncthreads();
+    for (int off = CK_THREADS / 2; off > 0; off >>= 1) {
+        if (threadIdx.x < off) {
+            s1[threadIdx.x] += s1[threadIdx.x + off];
+            s2[threadIdx.x] += s2[threadIdx.x + off];
+            sx[threadIdx.x] ^= sx[threadIdx.x + off];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        out[3 * blockIdx.x] = s1[0];
+        out[3 * blockIdx.x + 1] = s2[0];
+        out[3 * blockIdx.x + 2] = __longlong_as_double((long long)sx[0]);
+    }
+}
+
+// sum, sum of squares, xor of the bits of x[0..n) on the plan's device
+int device_checksum(qcdmet_plan *p, const double *x, size_t n, double *sum, double *sumsq, unsigned long long *bits)
+{
+    DeviceGuard guard(p->device);
+    if (!p->d_ck) QC_TRY(dev_alloc(&p->d_ck, (size_t)3 * CK_BLOCKS));
+    checksum_kernel<<<CK_BLOCKS, CK_THREADS, 0, p->stream>>>(x, n, p->d_ck);
+    QC_CUDA(cudaGetLastError());
+    std::vector<double> h(3 * CK_BLOCKS);
+    QC_CUDA(cudaMemcpyAsync(h.data(), p->d_ck, sizeof(double) * h.size(), cudaMemcpyDeviceToHost, p->stream));
+    QC_CUDA(cudaStreamSynchronize(p->stream));
+    double a = 0.0, b = 0.0;
+    unsigned long long c = 0ULL;
+    for (int k = 0; k < CK_BLOCKS; ++k) {
+        a += h[3 * k];
+        b += h[3 * k + 1];
+        unsigned long long w;
+        memcpy(&w, &h[3 * k + 2], 8);
+        c ^= w;
+    }
+    *sum = a; *sumsq = b; *bits = c;
+    return QCDMET_OK;
+}
+
+int plan_create_single(qcdmet_plan **out, int device, int Norb, int Nterms, int numPairs,
+                       const int *H1start, const int *H1row, const int *H1col,
+                       int Nfrag, const int *rowStart, const double *R, const int *rowIdx);
+void plan_destroy_single(qcdmet_plan *p);
+
+// columns [lo, hi) of member m when the range [colBegin, colEnd) is split evenly over n members
+void shard_of(int colBegin, int colEnd, int n, int m, int *lo, int *hi)
+{
+    const long long len = colEnd - colBegin;
+    *lo = colBegin + (int)(len * m / n);
+    *hi = colBegin + (int)(len * (m + 1) / n);
+}
+
+void group_release(qcdmet_plan *p)
+{
+    for (size_t m = 1; m < p->members.size(); ++m) plan_destroy_single(p->members[m]);
+    p->members.clear();
+    p->peers_on = false;
+    p->peers = PeerSet();
+    if (p->evOrb) { DeviceGuard guard(p->device); cudaEventDestroy(p->evOrb); cudaEventDestroy(p->evStart); }
+    p->evOrb = p->evStart = nullptr;
+}
+
+// Turn p into the leader of a group of n plans on devices p->device, p->device + 1, ... (mod the device count):
+// the same lists on every device, peer access between all pairs, every member's full (Q x P) Jacobian buffer
+// known to every other member (raw peer pointers: one process, no IPC handles needed).
+int group_build(qcdmet_plan *p, int n)
+{
+    int ndev = 0;
+    QC_CUDA(cudaGetDeviceCount(&ndev));
+    // test hook: QCDMET_B200_OVERSUBSCRIBE=1 lets the members of a group wrap around the visible devices (several
+    // members per GPU), so that the group logic -- streams, events, shards, threaded D2H -- runs on a one-GPU box
+    const char *overEnv = getenv("QCDMET_B200_OVERSUBSCRIBE");
+    const bool over = overEnv && overEnv[0] == '1';
+    QC_CHECK(n >= 1 && (n <= ndev || over) && n <= QCDMET_MAX_PEERS, QCDMET_E_ARG,
+             "%d devices requested, %d visible (at most %d per plan)", n, ndev, QCDMET_MAX_PEERS);
+    QC_CHECK(!p->d_J_ext && !p->peers_on, QCDMET_E_STATE,
+             "a plan with an external output buffer or attached IPC peers cannot span several devices");
+    group_release(p);
+    p->fullLayout = (n > 1);
+    if (n == 1) return QCDMET_OK;
+    std::vector<int> devs(n);
+    for (int m = 0; m < n; ++m) devs[m] = (p->device + m) % ndev;
+    for (int a = 0; a < n; ++a)
+        for (int b = 0; b < n; ++b) {
+            if (devs[a] == devs[b]) continue;
+            int can = 0;
+            QC_CUDA(cudaDeviceCanAccessPeer(&can, devs[a], devs[b]));
+            QC_CHECK(can, QCDMET_E_CUDA, "device %d cannot access device %d as a peer (NVLink/P2P needed for multi-device plans)",
+                     devs[a], devs[b]);
+            DeviceGuard guard(devs[a]);
+            cudaError_t err = cudaDeviceEnablePeerAccess(devs[b], 0);
+            if (err == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+            else QC_CUDA(err);
+        }
+    p->members.assign(1, p);
+    for (int m = 1; m < n; ++m) {
+        qcdmet_plan *q = nullptr;
+        int rc = plan_create_single(&q, devs[m], p->N, p->P, p->no, p->h1start.data(),
+                                    p->h1row.empty() ? nullptr : p->h1row.data(), p->h1col.empty() ? nullptr : p->h1col.data(),
+                                    p->F, p->rowStart.data(), nullptr, p->denseRows ? nullptr : (p->rowIdx.empty() ? nullptr : p->rowIdx.data()));
+        if (rc == QCDMET_OK && p->denseRows) {
+            // dense projector rows: copied device to device (the leader keeps no host copy of R)
+            DeviceGuard guard(q->device);
+            q->denseRows = true;
+            rc = dev_alloc(&q->d_R, (size_t)p->S * p->N);
+            if (rc == QCDMET_OK &&
+                cudaMemcpyPeer(q->d_R, q->device, p->d_R, p->device, sizeof(double) * (size_t)p->S * p->N) != cudaSuccess) {
+                set_error("cudaMemcpyPeer of the projector rows to device %d failed", q->device);
+                rc = QCDMET_E_CUDA;
+            }
+        }
+        if (rc != QCDMET_OK) {
+            if (q) plan_destroy_single(q);
+            group_release(p);
+            p->fullLayout = false;
+            return rc;
+        }
+        q->leader = p;
+        q->fullLayout = true;
+        q->kernel_req = p->kernel_req;
+        DeviceGuard guard(q->device);
+        if (cudaStreamCreateWithFlags(&q->ownStream, cudaStreamNonBlocking) != cudaSuccess) {
+            set_error("cudaStreamCreate on device %d failed", q->device);
+            plan_destroy_single(q);
+            group_release(p);
+            p->fullLayout = false;
+            return QCDMET_E_CUDA;
+        }
+        q->stream = q->ownStream;
+        p->members.push_back(q);
+    }
+    {
+        DeviceGuard guard(p->device);
+        QC_CUDA(cudaEventCreateWithFlags(&p->evOrb, cudaEventDisableTiming));
+        QC_CUDA(cudaEventCreateWithFlags(&p->evStart, cudaEventDisableTiming));
+    }
+    // every member's full-layout Jacobian buffer, known to every member
+    void *ptrs[QCDMET_MAX_PEERS] = {nullptr};
+    for (int m = 0; m < n; ++m) {
+        qcdmet_plan *q = p->members[m];
+        DeviceGuard guard(q->device);
+        if (!q->evDone) QC_CUDA(cudaEventCreateWithFlags(&q->evDone, cudaEventDisableTiming));
+        // force a reallocation in full layout if an earlier, smaller slice buffer exists
+        int rc = ensure_jacobian_buffer(q);
+        if (rc != QCDMET_OK) { group_release(p); p->fullLayout = false; return rc; }
+        ptrs[m] = q->d_J;
+    }
+    for (int m = 0; m < n; ++m) {
+        qcdmet_plan *q = p->members[m];
+        for (int r = 0; r < n; ++r) q->peers.J[r] = (double *)ptrs[r];
+        q->peers.nranks = n;
+        q->peers.rank = m;
+        q->peers_on = false;      // switched on per compute when the fused mode applies
+    }
+    p->have_jac = false;
+    p->jac_in_memory = false;
+    if (p->have_orbitals) {
+        // orbitals were set before the group existed: ship them now
+        int rc = group_broadcast_orbitals(p);
+        group_mark_orbitals(p, rc == QCDMET_OK);
+        QC_TRY(rc);
+    }
+    return QCDMET_OK;
+}
+
+// One plan's share of a compute: kernels for [p->colBegin, p->colEnd) on p->device / p->stream.
+int compute_single(qcdmet_plan *p)
+{
+    DeviceGuard guard(p->device);
+    QC_TRY(ensure_jacobian_buffer(p));
+    const bool use_dmma = (p->kernel_req == QCDMET_KERNEL_DMMA) || (p->kernel_req == QCDMET_KERNEL_DMMA_NOSYM) ||
+                          (p->kernel_req == QCDMET_KERNEL_AUTO && p->dmma_ok);
+    if (p->peers_on) {
+        QC_CHECK(use_dmma, QCDMET_E_STATE, "peer (fused all-gather) mode needs the DMMA kernel: %s", p->dmma_why.c_str());
+        QC_CHECK(p->colBegin == 0 && p->colEnd == p->P && !p->d_J_ext, QCDMET_E_STATE,
+                 "peer mode works on the full column range with the plan-owned buffer");
+        QC_CHECK(p->peers.J[p->peers.rank] == p->d_J, QCDMET_E_STATE, "own Jacobian buffer moved after export");
+    }
+    if (!p->ev0) {
+        QC_CUDA(cudaEventCreate(&p->ev0));
+        QC_CUDA(cudaEventCreate(&p->ev1));
+    }
+    if (p->kernel_req == QCDMET_KERNEL_AUTO && !p->dmma_ok) {
+        QC_TRY(ensure_fact(p));                 // first use: the Jacobian buffer is already allocated
+        if (!p->fact_ok && p->info.empty())
+            p->info = "AUTO uses the general FP64 kernel: fused DMMA kernel not eligible (" + p->dmma_why +
+                      "); factorised path not available (" + p->fact_why + ")";
+    }
+    JacView v = make_view(p);
+    const bool use_fact = (p->kernel_req == QCDMET_KERNEL_FACTORISED) ||
+                          (p->kernel_req == QCDMET_KERNEL_AUTO && !p->dmma_ok && p->fact_ok);
+    if (use_fact) {
+        if (!p->fact_orbitals_valid) {
+            QC_TRY(fact_prepare_orbitals(p->fact, v, p->stream));
+            p->fact_orbitals_valid = true;
+        }
+        const long long nnzInRange = (long long)p->h1start[p->colEnd] - p->h1start[p->colBegin];
+        QC_TRY(launch_jacobian_factorised(p->fact, v, nnzInRange, p->stream, &p->launches, &p->flops, p->ev0, p->ev1));
+        p->kernel_used = QCDMET_KERNEL_FACTORISED;
+        p->symmetric_used = false;
+    } else if (use_dmma) {
+        QC_TRY(launch_jacobian_dmma(p->dmma, v, p->stream, &p->launches, &p->flops, p->ev0, p->ev1,
+                                    p->kernel_req != QCDMET_KERNEL_DMMA_NOSYM, p->peers_on ? &p->peers : nullptr));
+        p->symmetric_used = dmma_last_launch_symmetric(p->dmma);
+        p->kernel_used = QCDMET_KERNEL_DMMA;
+    } else {
+        if (!p->d_W) QC_TRY(dev_alloc(&p->d_W, (size_t)p->nv * p->ldo));
+        if (!p->w_valid) {
+            QC_TRY(launch_build_w(p->d_e, p->no, p->nv, p->ldo, p->d_W, p->stream));
+            p->w_valid = true;
+        }
+        v.W = p->d_W;
+        QC_TRY(launch_jacobian_general(v, p->stream, &p->launches, &p->flops, p->ev0, p->ev1));
+        p->flops = count_flops_general(p);
+        p->kernel_used = QCDMET_KERNEL_GENERAL;
+        p->symmetric_used = false;
+    }
+    p->have_jac = true;
+    p->jac_in_memory = true;
+    p->normal_valid = false;
+    return QCDMET_OK;
+}
+
+// The group's compute: every member launches its share from the caller thread (asynchronous), then an
+// event barrier makes every member's stream wait for all shares -- no host thread blocks, no NCCL.
+//   fused (DMMA kernel, full column range, list not split): a member executes 1/n of the block-pair list and
+//     stores every Jacobian element into all members' buffers with NVLink peer stores;
+//   otherwise: a member computes a contiguous slice of the columns into its own full-layout buffer and copies the
+//     slice to the leader (cudaMemcpyPeerAsync), which then holds the complete Jacobian.
+int compute_group(qcdmet_plan *p)
+{
+    const int n = (int)p->members.size();
+    const bool use_dmma = (p->kernel_req == QCDMET_KERNEL_DMMA) || (p->kernel_req == QCDMET_KERNEL_DMMA_NOSYM) ||
+                          (p->kernel_req == QCDMET_KERNEL_AUTO && p->dmma_ok);
+    const bool fused = use_dmma && p->dmma && !dmma_plan_expanded(p->dmma) && p->colBegin == 0 && p->colEnd == p->P;
+    p->group_fused = fused;
+    const int cb = p->colBegin, ce = p->colEnd;
+    // the leader's column range is the caller's, whatever share the leader computes below
+    struct Restore { qcdmet_plan *p; int cb, ce; ~Restore() { p->colBegin = cb; p->colEnd = ce; } } restore{p, cb, ce};
+    {
+        DeviceGuard guard(p->device);
+        QC_CUDA(cudaEventRecord(p->evStart, p->stream));
+    }
+    int rc = QCDMET_OK;
+    for (int m = 0; m < n && rc == QCDMET_OK; ++m) {
+        qcdmet_plan *q = p->members[m];
+        DeviceGuard guard(q->device);
+        if (m > 0) {
+            QC_CUDA(cudaStreamWaitEvent(q->stream, p->evStart, 0));
+            q->kernel_req = p->kernel_req;
+        }
+        q->peers_on = fused;
+        if (fused) { q->colBegin = 0; q->colEnd = p->P; }
+        else shard_of(cb, ce, n, m, &q->colBegin, &q->colEnd);
+        rc = compute_single(q);
+        if (rc == QCDMET_OK && !fused && m > 0 && q->colEnd > q->colBegin) {
+            const size_t off = (size_t)p->Q * q->colBegin, cnt = (size_t)p->Q * (q->colEnd - q->colBegin);
+            if (cudaMemcpyPeerAsync(p->d_J + off, p->device, q->d_J + off, q->device, sizeof(double) * cnt, q->stream) != cudaSuccess) {
+                set_error("cudaMemcpyPeerAsync of a column slice to the leader failed");
+                rc = QCDMET_E_CUDA;
+            }
+        }
+        if (rc == QCDMET_OK && cudaEventRecord(q->evDone, q->stream) != cudaSuccess) {
+            set_error("cudaEventRecord failed on device %d", q->device);
+            rc = QCDMET_E_CUDA;
+        }
+    }
+    if (rc != QCDMET_OK) { p->have_jac = false; return rc; }
+    for (int m = 0; m < n; ++m) {
+        qcdmet_plan *q = p->members[m];
+        DeviceGuard guard(q->device);
+        for (int k = 0; k < n; ++k)
+            if (k != m) QC_CUDA(cudaStreamWaitEvent(q->stream, p->members[k]->evDone, 0));
+    }
+    p->have_jac = true;
+    p->jac_in_memory = true;
+    p->normal_valid = false;
+    return QCDMET_OK;
+}
+
 }  // namespace
 
 extern "C" {
 
 const char *qcdmet_last_error(void) { return g_err; }
-const char *qcdmet_version(void) { return "qcdmet_b200 0.1 (sm_100a)"; }
+const char *qcdmet_version(void) { return "qcdmet_b200 0.2 (sm_100a)"; }
 
 int qcdmet_schedule_info(int Norb, int Nterms, int numPairs, const int *H1start, const int *H1row,
                          const int *H1col, int Nfrag, const int *rowStart, const int *rowIdx, int *info)
@@ -331,21 +777,47 @@ int qcdmet_device_count(void)
     return n;
 }
 
-int qcdmet_plan_create(qcdmet_plan **out, int device, int Norb, int Nterms, int numPairs,
+int qcdmet_set_devices(int n)
+{
+    int ndev = qcdmet_device_count();
+    if (n < 0) n = ndev;
+    QC_CHECK(n >= 1 || ndev == 0, QCDMET_E_ARG, "number of devices must be >= 1 (or -1 for all)");
+    const char *overEnv = getenv("QCDMET_B200_OVERSUBSCRIBE");      // test hook, see group_build
+    const bool over = overEnv && overEnv[0] == '1';
+    QC_CHECK((n <= std::max(ndev, 1) || over) && n <= QCDMET_MAX_PEERS, QCDMET_E_ARG,
+             "%d devices requested, %d visible (at most %d per plan)", n, ndev, QCDMET_MAX_PEERS);
+    std::lock_guard<std::mutex> lock(g_dev_mu);
+    g_default_devices = std::max(n, 1);
+    return QCDMET_OK;
+}
+
+int qcdmet_get_devices(void) { return default_devices(); }
+
+void *qcdmet_host_alloc(size_t bytes)
+{
+    void *ptr = nullptr;
+    if (cudaHostAlloc(&ptr, std::max<size_t>(bytes, 1), cudaHostAllocPortable) != cudaSuccess) {
+        cudaGetLastError();
+        set_error("cudaHostAlloc of %zu bytes failed", bytes);
+        return nullptr;
+    }
+    return ptr;
+}
+
+int qcdmet_host_free(void *ptr)
+{
+    if (ptr) QC_CUDA(cudaFreeHost(ptr));
+    return QCDMET_OK;
+}
+
+}  // extern "C"
+
+namespace {
+
+int plan_create_single(qcdmet_plan **out, int device, int Norb, int Nterms, int numPairs,
                        const int *H1start, const int *H1row, const int *H1col,
                        int Nfrag, const int *rowStart, const double *R, const int *rowIdx)
 {
-    QC_CHECK(out != nullptr, QCDMET_E_ARG, "plan output pointer is NULL");
-    *out = nullptr;
-    QC_TRY(validate_lists(Norb, Nterms, numPairs, H1start, H1row, H1col, Nfrag, rowStart, R, rowIdx));
-    int ndev = 0;
-    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
-        cudaGetLastError();
-        set_error("no CUDA device available: libqcdmet_b200 has no CPU fallback");
-        return QCDMET_E_CUDA;
-    }
-    if (device < 0) QC_CUDA(cudaGetDevice(&device));
-    QC_CHECK(device < ndev, QCDMET_E_ARG, "device %d out of range (%d devices)", device, ndev);
     DeviceGuard guard(device);
     QC_CHECK(guard.ok, QCDMET_E_CUDA, "cudaSetDevice(%d) failed", device);
 
@@ -359,11 +831,17 @@ int qcdmet_plan_create(qcdmet_plan **out, int device, int Norb, int Nterms, int 
     p->denseRows = (R != nullptr);
     const int nnz = H1start[Nterms];
     p->h1start.assign(H1start, H1start + Nterms + 1);
-    p->h1row.assign(H1row, H1row + nnz);
-    p->h1col.assign(H1col, H1col + nnz);
+    if (nnz > 0) {
+        p->h1row.assign(H1row, H1row + nnz);
+        p->h1col.assign(H1col, H1col + nnz);
+    }
     if (Nfrag > 0) p->rowStart.assign(rowStart, rowStart + Nfrag + 1);
     else p->rowStart.assign(1, 0);
-    if (!p->denseRows && p->S > 0) p->rowIdx.assign(rowIdx, rowIdx + p->S);
+    if (!p->denseRows && p->S > 0 && rowIdx) p->rowIdx.assign(rowIdx, rowIdx + p->S);
+    if (p->denseRows) {
+        p->rHash[0] = fnv1a(1469598103934665603ULL, R, sizeof(double) * (size_t)p->S * Norb);
+        p->rHash[1] = mix64(0x243F6A8885A308D3ULL, R, sizeof(double) * (size_t)p->S * Norb);
+    }
     std::vector<int> rowFrag(std::max(p->S, 1), 0);
     std::vector<long long> qoff(Nfrag + 1, 0);
     for (int f = 0; f < Nfrag; ++f) {
@@ -374,7 +852,7 @@ int qcdmet_plan_create(qcdmet_plan **out, int device, int Norb, int Nterms, int 
     p->Q = qoff[Nfrag];
 
     int rc = QCDMET_OK;
-    auto fail = [&](int code) { qcdmet_plan_destroy(p); return code; };
+    auto fail = [&](int code) { plan_destroy_single(p); return code; };
     if ((rc = dev_alloc_copy(&p->d_h1start, p->h1start.data(), p->h1start.size()))) return fail(rc);
     if ((rc = dev_alloc_copy(&p->d_h1row, p->h1row.data(), p->h1row.size()))) return fail(rc);
     if ((rc = dev_alloc_copy(&p->d_h1col, p->h1col.data(), p->h1col.size()))) return fail(rc);
@@ -403,16 +881,76 @@ int qcdmet_plan_create(qcdmet_plan **out, int device, int Norb, int Nterms, int 
         set_error("cublasCreate failed");
         return fail(QCDMET_E_CUDA);
     }
-    // site-factorised DMMA schedule, when the perturbation/fragment structure allows it
+    // site-factorised DMMA schedule, when the perturbation/fragment structure allows it (rowIdx == NULL: dense rows).
+    // Members of a group get their dense rows after creation: R == NULL and rowIdx == NULL both mean "dense" here.
+    const bool dense = p->denseRows || (p->S > 0 && rowIdx == nullptr);
+    const int *ridx = dense ? nullptr : (p->rowIdx.empty() ? nullptr : p->rowIdx.data());
     p->dmma_ok = dmma_eligible(Norb, Nterms, Nfrag, p->h1start.data(), p->h1row.data(), p->h1col.data(),
-                               p->rowStart.data(), p->denseRows ? nullptr : p->rowIdx.data(),
-                               p->denseRows, &p->dmma_why);
+                               p->rowStart.data(), ridx, dense, &p->dmma_why);
     if (p->dmma_ok) {
         rc = dmma_plan_build(&p->dmma, Norb, numPairs, Nterms, Nfrag, p->h1start.data(), p->h1row.data(),
-                             p->h1col.data(), p->rowStart.data(), p->rowIdx.data());
+                             p->h1col.data(), p->rowStart.data(), ridx);
         if (rc) return fail(rc);
-    } else if ((rc = ensure_fact(p))) {
-        return fail(rc);
+    }
+    // the factorised path's panels are allocated by the first compute() that uses them (ensure_fact)
+    *out = p;
+    return QCDMET_OK;
+}
+
+void plan_destroy_single(qcdmet_plan *p)
+{
+    if (!p) return;
+    DeviceGuard guard(p->device);
+    for (int r = 0; r < QCDMET_MAX_PEERS; ++r)
+        if (p->ipc_opened[r]) cudaIpcCloseMemHandle(p->ipc_opened[r]);
+    cudaFree(p->d_h1start); cudaFree(p->d_h1row); cudaFree(p->d_h1col);
+    cudaFree(p->d_rowStart); cudaFree(p->d_rowFrag); cudaFree(p->d_rowIdx); cudaFree(p->d_qoff);
+    cudaFree(p->d_R); cudaFree(p->d_C); cudaFree(p->d_e);
+    cudaFree(p->d_CoT); cudaFree(p->d_CvT); cudaFree(p->d_PO); cudaFree(p->d_PV); cudaFree(p->d_W);
+    cudaFree(p->d_A); cudaFree(p->d_Awork); cudaFree(p->d_g); cudaFree(p->d_r); cudaFree(p->d_potrf);
+    cudaFree(p->d_Apart); cudaFree(p->d_ck); cudaFree(p->d_flush);
+    cudaFree(p->d_J_own); cudaFree(p->d_D); cudaFree(p->d_work); cudaFree(p->d_info);
+    if (p->ev0) cudaEventDestroy(p->ev0);
+    if (p->ev1) cudaEventDestroy(p->ev1);
+    for (int i = 0; i < 4; ++i)
+        if (p->evT[i]) cudaEventDestroy(p->evT[i]);
+    if (p->evDone) cudaEventDestroy(p->evDone);
+    if (p->ownStream) cudaStreamDestroy(p->ownStream);
+    if (p->solver) cusolverDnDestroy(p->solver);
+    if (p->blas) cublasDestroy(p->blas);
+    if (p->dmma) dmma_plan_free(p->dmma);
+    if (p->fact) fact_plan_free(p->fact);
+    cudaGetLastError();
+    delete p;
+}
+
+}  // namespace
+
+extern "C" {
+
+int qcdmet_plan_create(qcdmet_plan **out, int device, int Norb, int Nterms, int numPairs,
+                       const int *H1start, const int *H1row, const int *H1col,
+                       int Nfrag, const int *rowStart, const double *R, const int *rowIdx)
+{
+    QC_CHECK(out != nullptr, QCDMET_E_ARG, "plan output pointer is NULL");
+    *out = nullptr;
+    QC_TRY(validate_lists(Norb, Nterms, numPairs, H1start, H1row, H1col, Nfrag, rowStart, R, rowIdx));
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        set_error("no CUDA device available: libqcdmet_b200 has no CPU fallback");
+        return QCDMET_E_CUDA;
+    }
+    const bool explicitDevice = device >= 0;
+    if (device < 0) QC_CUDA(cudaGetDevice(&device));
+    QC_CHECK(device < ndev, QCDMET_E_ARG, "device %d out of range (%d devices)", device, ndev);
+    qcdmet_plan *p = nullptr;
+    QC_TRY(plan_create_single(&p, device, Norb, Nterms, numPairs, H1start, H1row, H1col, Nfrag, rowStart, R, rowIdx));
+    // the process-wide default (qcdmet_set_devices / $QCDMET_B200_DEVICES) applies to plans on the current device
+    const int want = explicitDevice ? 1 : default_devices();
+    if (want > 1) {
+        const int rc = group_build(p, want);
+        if (rc != QCDMET_OK) { qcdmet_plan_destroy(p); return rc; }
     }
     *out = p;
     return QCDMET_OK;
@@ -421,24 +959,22 @@ int qcdmet_plan_create(qcdmet_plan **out, int device, int Norb, int Nterms, int 
 int qcdmet_plan_destroy(qcdmet_plan *p)
 {
     if (!p) return QCDMET_OK;
-    qcdmet_plan_detach_peers(p);
-    DeviceGuard guard(p->device);
-    cudaFree(p->d_h1start); cudaFree(p->d_h1row); cudaFree(p->d_h1col);
-    cudaFree(p->d_rowStart); cudaFree(p->d_rowFrag); cudaFree(p->d_rowIdx); cudaFree(p->d_qoff);
-    cudaFree(p->d_R); cudaFree(p->d_C); cudaFree(p->d_e);
-    cudaFree(p->d_CoT); cudaFree(p->d_CvT); cudaFree(p->d_PO); cudaFree(p->d_PV); cudaFree(p->d_W);
-    cudaFree(p->d_A); cudaFree(p->d_Awork); cudaFree(p->d_g); cudaFree(p->d_r); cudaFree(p->d_potrf);
-    cudaFree(p->d_J_own); cudaFree(p->d_D); cudaFree(p->d_work); cudaFree(p->d_info);
-    if (p->ev0) cudaEventDestroy(p->ev0);
-    if (p->ev1) cudaEventDestroy(p->ev1);
-    if (p->solver) cusolverDnDestroy(p->solver);
-    if (p->blas) cublasDestroy(p->blas);
-    if (p->dmma) dmma_plan_free(p->dmma);
-    if (p->fact) fact_plan_free(p->fact);
-    cudaGetLastError();
-    delete p;
+    QC_CHECK(p->leader == nullptr, QCDMET_E_ARG, "member plans are destroyed with their leader");
+    group_release(p);
+    plan_destroy_single(p);
     return QCDMET_OK;
 }
+
+int qcdmet_plan_set_devices(qcdmet_plan *p, int n)
+{
+    QC_CHECK(p != nullptr && p->leader == nullptr, QCDMET_E_ARG, "plan is NULL or a group member");
+    if (n < 0) n = qcdmet_device_count();
+    DeviceGuard guard(p->device);
+    QC_CUDA(cudaStreamSynchronize(p->stream));
+    return group_build(p, n);
+}
+
+int qcdmet_plan_num_devices(qcdmet_plan *p) { return p ? std::max<int>(1, (int)p->members.size()) : -1; }
 
 int qcdmet_plan_set_columns(qcdmet_plan *p, int colBegin, int colEnd)
 {
@@ -460,11 +996,14 @@ int qcdmet_plan_set_kernel(qcdmet_plan *p, int kernel)
     QC_CHECK((kernel != QCDMET_KERNEL_DMMA && kernel != QCDMET_KERNEL_DMMA_NOSYM) || p->dmma_ok, QCDMET_E_ARG,
              "DMMA kernel not eligible for this plan: %s", p->dmma_why.c_str());
     if (kernel == QCDMET_KERNEL_FACTORISED) {
-        DeviceGuard guard(p->device);
-        QC_TRY(ensure_fact(p));
-        QC_CHECK(p->fact_ok, QCDMET_E_ARG, "factorised path not available for this plan: %s", p->fact_why.c_str());
+        for (qcdmet_plan *q : (in_group(p) ? p->members : std::vector<qcdmet_plan *>{p})) {
+            DeviceGuard guard(q->device);
+            QC_TRY(ensure_fact(q));
+            QC_CHECK(q->fact_ok, QCDMET_E_ARG, "factorised path not available for this plan: %s", q->fact_why.c_str());
+        }
     }
     p->kernel_req = kernel;
+    for (size_t m = 1; m < p->members.size(); ++m) p->members[m]->kernel_req = kernel;
     return QCDMET_OK;
 }
 
@@ -479,6 +1018,7 @@ int qcdmet_plan_set_output_device(qcdmet_plan *p, void *device_ptr, long long ca
 {
     QC_CHECK(p != nullptr, QCDMET_E_ARG, "plan is NULL");
     QC_CHECK(device_ptr == nullptr || capacity > 0, QCDMET_E_ARG, "capacity must be positive");
+    QC_CHECK(!in_group(p) || device_ptr == nullptr, QCDMET_E_STATE, "multi-device plans own their Jacobian buffers");
     p->d_J_ext = (double *)device_ptr;
     p->J_ext_capacity = device_ptr ? (size_t)capacity : 0;
     p->have_jac = false;
@@ -491,7 +1031,12 @@ int qcdmet_plan_set_h0(qcdmet_plan *p, const double *H0)
     QC_CHECK(p != nullptr && H0 != nullptr, QCDMET_E_ARG, "plan or H0 is NULL");
     DeviceGuard guard(p->device);
     const int N = p->N;
+    group_mark_orbitals(p, false);              // d_C is about to be overwritten: nothing derived from it is valid
+    QC_TRY(ensure_timing_events(p));
+    p->evT_valid = false;
+    QC_CUDA(cudaEventRecord(p->evT[0], p->stream));
     QC_CUDA(cudaMemcpyAsync(p->d_C, H0, sizeof(double) * (size_t)N * N, cudaMemcpyHostToDevice, p->stream));
+    QC_CUDA(cudaEventRecord(p->evT[1], p->stream));
     cusolverDnSetStream(p->solver, p->stream);
     int lwork = 0;
     // Upper triangle of the column-major view, as dsyev('V','U') in lib/rhf_response.cc:45-50
@@ -508,74 +1053,65 @@ int qcdmet_plan_set_h0(qcdmet_plan *p, const double *H0)
     cs = cusolverDnDsyevd(p->solver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_UPPER, N, p->d_C, N,
                           p->d_e, p->d_work, p->lwork, p->d_info);
     QC_CHECK(cs == CUSOLVER_STATUS_SUCCESS, QCDMET_E_SOLVER, "cusolverDnDsyevd failed: %d", (int)cs);
-    int info = 0;
-    QC_CUDA(cudaMemcpyAsync(&info, p->d_info, sizeof(int), cudaMemcpyDeviceToHost, p->stream));
-    QC_CUDA(cudaStreamSynchronize(p->stream));
-    QC_CHECK(info == 0, QCDMET_E_SOLVER, "cusolverDnDsyevd: info = %d", info);
-    return build_panels(p);
+    QC_CUDA(cudaEventRecord(p->evT[2], p->stream));
+    // members start receiving (C, e) as soon as the leader's stream has them; the host checks info / the gap below
+    QC_TRY(group_broadcast_orbitals(p));
+    QC_TRY(build_panels_async(p));
+    QC_CUDA(cudaEventRecord(p->evT[3], p->stream));
+    QC_TRY(check_gap(p, true));                 // synchronises the leader stream; solver info first
+    p->evT_valid = true;
+    group_mark_orbitals(p, true);
+    return QCDMET_OK;
 }
 
 int qcdmet_plan_set_orbitals(qcdmet_plan *p, const double *C, const double *e)
 {
     QC_CHECK(p != nullptr && C != nullptr && e != nullptr, QCDMET_E_ARG, "plan, C or e is NULL");
     DeviceGuard guard(p->device);
+    group_mark_orbitals(p, false);
+    p->evT_valid = false;
     QC_CUDA(cudaMemcpyAsync(p->d_C, C, sizeof(double) * (size_t)p->N * p->N, cudaMemcpyHostToDevice, p->stream));
     QC_CUDA(cudaMemcpyAsync(p->d_e, e, sizeof(double) * (size_t)p->N, cudaMemcpyHostToDevice, p->stream));
-    return build_panels(p);
+    QC_TRY(group_broadcast_orbitals(p));
+    QC_TRY(build_panels_async(p));
+    QC_TRY(check_gap(p));
+    group_mark_orbitals(p, true);
+    return QCDMET_OK;
+}
+
+/* Device pointers of the plan's orbital buffers (C: column-major Norb x Norb, eigenvector k in column k; e:
+ * ascending), so that a caller can fill them in place -- e.g. an NCCL broadcast from the rank that ran the
+ * eigensolve -- and then call qcdmet_plan_commit_orbitals(). */
+int qcdmet_plan_orbitals_device(qcdmet_plan *p, void **C, void **e)
+{
+    QC_CHECK(p != nullptr && C != nullptr && e != nullptr, QCDMET_E_ARG, "plan, C or e is NULL");
+    *C = p->d_C;
+    *e = p->d_e;
+    return QCDMET_OK;
+}
+
+int qcdmet_plan_commit_orbitals(qcdmet_plan *p)
+{
+    QC_CHECK(p != nullptr, QCDMET_E_ARG, "plan is NULL");
+    DeviceGuard guard(p->device);
+    group_mark_orbitals(p, false);
+    p->evT_valid = false;
+    QC_TRY(group_broadcast_orbitals(p));
+    QC_TRY(build_panels_async(p));
+    QC_TRY(check_gap(p));
+    group_mark_orbitals(p, true);
+    return QCDMET_OK;
 }
 
 int qcdmet_plan_compute(qcdmet_plan *p)
 {
     QC_CHECK(p != nullptr, QCDMET_E_ARG, "plan is NULL");
     QC_CHECK(p->have_orbitals, QCDMET_E_STATE, "plan has no orbitals: call set_h0/set_orbitals first");
-    DeviceGuard guard(p->device);
-    QC_TRY(ensure_jacobian_buffer(p));
-    JacView v = make_view(p);
-    const bool use_dmma = (p->kernel_req == QCDMET_KERNEL_DMMA) || (p->kernel_req == QCDMET_KERNEL_DMMA_NOSYM) ||
-                          (p->kernel_req == QCDMET_KERNEL_AUTO && p->dmma_ok);
-    if (p->peers_on) {
-        QC_CHECK(use_dmma, QCDMET_E_STATE, "peer (fused all-gather) mode needs the DMMA kernel: %s", p->dmma_why.c_str());
-        QC_CHECK(p->colBegin == 0 && p->colEnd == p->P && !p->d_J_ext, QCDMET_E_STATE,
-                 "peer mode works on the full column range with the plan-owned buffer");
-        QC_CHECK(p->peers.J[p->peers.rank] == p->d_J, QCDMET_E_STATE, "own Jacobian buffer moved after export");
-    }
-    if (!p->ev0) {
-        QC_CUDA(cudaEventCreate(&p->ev0));
-        QC_CUDA(cudaEventCreate(&p->ev1));
-    }
-    const bool use_fact = (p->kernel_req == QCDMET_KERNEL_FACTORISED) ||
-                          (p->kernel_req == QCDMET_KERNEL_AUTO && !p->dmma_ok && p->fact_ok);
-    if (use_fact) {
-        if (!p->fact_orbitals_valid) {
-            QC_TRY(fact_prepare_orbitals(p->fact, v, p->stream));
-            p->fact_orbitals_valid = true;
-        }
-        const long long nnzInRange = (long long)p->h1start[p->colEnd] - p->h1start[p->colBegin];
-        QC_TRY(launch_jacobian_factorised(p->fact, v, nnzInRange, p->stream, &p->launches, &p->flops, p->ev0, p->ev1));
-        p->kernel_used = QCDMET_KERNEL_FACTORISED;
-        p->symmetric_used = false;
-    } else if (use_dmma) {
-        QC_TRY(launch_jacobian_dmma(p->dmma, v, p->stream, &p->launches, &p->flops, p->ev0, p->ev1,
-                                    p->kernel_req != QCDMET_KERNEL_DMMA_NOSYM, p->peers_on ? &p->peers : nullptr));
-        p->symmetric_used = dmma_last_launch_symmetric(p->dmma);
-        p->kernel_used = QCDMET_KERNEL_DMMA;
-    } else {
-        if (!p->d_W) QC_TRY(dev_alloc(&p->d_W, (size_t)p->nv * p->ldo));
-        if (!p->w_valid) {
-            QC_TRY(launch_build_w(p->d_e, p->no, p->nv, p->ldo, p->d_W, p->stream));
-            p->w_valid = true;
-        }
-        v.W = p->d_W;
-        QC_TRY(launch_jacobian_general(v, p->stream, &p->launches, &p->flops, p->ev0, p->ev1));
-        p->flops = count_flops_general(p);
-        p->kernel_used = QCDMET_KERNEL_GENERAL;
-        p->symmetric_used = false;
-    }
-    p->have_jac = true;
-    p->jac_in_memory = true;
-    p->normal_valid = false;
-    return QCDMET_OK;
+    if (in_group(p)) return compute_group(p);
+    return compute_single(p);
 }
+
+}  // extern "C"
 
 // (A + lambda diag(A)) with a floor on the diagonal so that the system stays positive definite along
 // directions the residual does not depend on (the chemical-potential gauge of umat, src/dmet.py:636)
@@ -594,6 +1130,87 @@ __global__ void lm_negate_kernel(const double *__restrict__ g, double *__restric
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) x[i] = -g[i];
 }
+// Jacobi equilibration of the normal matrix: W = D (A + lambda diag(A)) D, D = diag(A)^-1/2 (floored), so that
+// the Cholesky factorisation works on a matrix with unit diagonal (1 + lambda): column scaling of J, which
+// removes the part of cond(J)^2 that comes from badly scaled parameters.
+__global__ void lm_damp_scaled_kernel(const double *__restrict__ A, double *__restrict__ W, double *__restrict__ dscale,
+                                      int n, double lambda, double floor_)
+{
+    const size_t total = (size_t)n * n;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int r = (int)(i % n), c = (int)(i / n);
+        const double dr = rsqrt(fmax(A[(size_t)r * n + r], floor_)), dc = rsqrt(fmax(A[(size_t)c * n + c], floor_));
+        double v = A[i] * dr * dc;
+        if (r == c) { v = fmax(A[i], floor_) * dr * dc * (1.0 + lambda); dscale[r] = dr; }
+        W[i] = v;
+    }
+}
+__global__ void lm_scale_kernel(double *__restrict__ x, const double *__restrict__ d, int n, double sign)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) x[i] = sign * x[i] * d[i];
+}
+
+namespace {
+
+// A = J^T J (upper triangle) on the leader.  Single device: one DSYRK.  Group with a replicated Jacobian (fused
+// mode): member m computes the block row A[lo_m:hi_m, lo_m:n) = J[:, lo_m:hi_m]^T J[:, lo_m:n) with one DGEMM on
+// its own copy of J and ships it to the leader -- the O(Q P^2) part of the least-squares update is sharded.
+int normal_matrix(qcdmet_plan *p, int n, long long Q)
+{
+    const double one = 1.0, zero = 0.0;
+    const double *J = jac_slice(p);
+    if (!in_group(p) || !p->group_fused || n < 2 * (int)p->members.size()) {
+        cublasStatus_t cs = cublasDsyrk(p->blas, CUBLAS_FILL_MODE_UPPER, CUBLAS_OP_T, n, (int)Q, &one, J, (int)Q,
+                                        &zero, p->d_A, n);
+        QC_CHECK(cs == CUBLAS_STATUS_SUCCESS, QCDMET_E_CUDA, "cublasDsyrk failed: %d", (int)cs);
+        return QCDMET_OK;
+    }
+    // balance the trapezoids: block row [lo, hi) costs (hi - lo) (n - (lo + hi) / 2): equal-area cuts
+    const int nm = (int)p->members.size();
+    std::vector<int> cut(nm + 1, 0);
+    for (int m = 1; m < nm; ++m) {
+        const double frac = (double)m / nm;      // area below the cut / total area n^2 / 2
+        cut[m] = (int)(n * (1.0 - sqrt(1.0 - frac)));
+    }
+    cut[nm] = n;
+    QC_CUDA(cudaEventRecord(p->evStart, p->stream));
+    for (int m = 0; m < nm; ++m) {
+        qcdmet_plan *q = p->members[m];
+        const int lo = cut[m], hi = cut[m + 1], rows = hi - lo, cols = n - lo;
+        if (rows <= 0) continue;
+        DeviceGuard guard(q->device);
+        const double *Jq = jac_slice(q) + (size_t)Q * lo;   // full-layout buffer, same column range as the leader
+        double *dst = p->d_A + (size_t)lo * n + lo;           // A[lo, lo], leading dimension n
+        cublasSetStream(q->blas, q->stream);
+        if (m == 0) {
+            cublasStatus_t cs = cublasDgemm(q->blas, CUBLAS_OP_T, CUBLAS_OP_N, rows, cols, (int)Q, &one, Jq, (int)Q, Jq, (int)Q,
+                                            &zero, dst, n);
+            QC_CHECK(cs == CUBLAS_STATUS_SUCCESS, QCDMET_E_CUDA, "cublasDgemm (J^T J block row) failed: %d", (int)cs);
+        } else {
+            QC_CUDA(cudaStreamWaitEvent(q->stream, p->evStart, 0));
+            if ((size_t)rows * cols > q->Apart_capacity) {
+                cudaFree(q->d_Apart);
+                q->d_Apart = nullptr;
+                q->Apart_capacity = 0;
+                QC_TRY(dev_alloc(&q->d_Apart, (size_t)rows * cols));
+                q->Apart_capacity = (size_t)rows * cols;
+            }
+            cublasStatus_t cs = cublasDgemm(q->blas, CUBLAS_OP_T, CUBLAS_OP_N, rows, cols, (int)Q, &one, Jq, (int)Q, Jq, (int)Q,
+                                            &zero, q->d_Apart, rows);
+            QC_CHECK(cs == CUBLAS_STATUS_SUCCESS, QCDMET_E_CUDA, "cublasDgemm (J^T J block row) failed: %d", (int)cs);
+            // rows x cols block (ld rows) -> A[lo:hi, lo:n) on the leader (ld n): 2-D copy over NVLink (UVA, peer access on)
+            QC_CUDA(cudaMemcpy2DAsync(dst, sizeof(double) * n, q->d_Apart, sizeof(double) * rows, sizeof(double) * rows,
+                                      cols, cudaMemcpyDefault, q->stream));
+            QC_CUDA(cudaEventRecord(q->evDone, q->stream));
+        }
+    }
+    for (int m = 1; m < nm; ++m)
+        if (cut[m + 1] > cut[m]) QC_CUDA(cudaStreamWaitEvent(p->stream, p->members[m]->evDone, 0));
+    return QCDMET_OK;
+}
+
+}  // namespace
 
 extern "C" int qcdmet_plan_lm_step(qcdmet_plan *p, const double *resid, double lambda, double *step, double *info)
 {
@@ -610,26 +1227,27 @@ extern "C" int qcdmet_plan_lm_step(qcdmet_plan *p, const double *resid, double l
         QC_TRY(dev_alloc(&p->d_A, (size_t)p->P * p->P));
         QC_TRY(dev_alloc(&p->d_Awork, (size_t)p->P * p->P));
     }
-    if (!p->d_g) QC_TRY(dev_alloc(&p->d_g, (size_t)p->P));
-    if (!p->d_r) QC_TRY(dev_alloc(&p->d_r, (size_t)Q));
+    if (!p->d_g) QC_TRY(dev_alloc(&p->d_g, (size_t)2 * p->P));
+    if (!p->d_r) QC_TRY(dev_alloc(&p->d_r, (size_t)std::max<long long>(Q, p->P)));
     cublasSetStream(p->blas, p->stream);
     cusolverDnSetStream(p->solver, p->stream);
     const double one = 1.0, zero = 0.0;
+    const double *J = jac_slice(p);
     if (!p->normal_valid) {
-        // A = J^T J  (upper triangle), one DSYRK on the column-major (Q x n) Jacobian
-        cublasStatus_t cs = cublasDsyrk(p->blas, CUBLAS_FILL_MODE_UPPER, CUBLAS_OP_T, n, (int)Q, &one, p->d_J, (int)Q,
-                                        &zero, p->d_A, n);
-        QC_CHECK(cs == CUBLAS_STATUS_SUCCESS, QCDMET_E_CUDA, "cublasDsyrk failed: %d", (int)cs);
+        QC_TRY(normal_matrix(p, n, Q));
         p->normal_valid = true;
     }
     QC_CUDA(cudaMemcpyAsync(p->d_r, resid, sizeof(double) * (size_t)Q, cudaMemcpyHostToDevice, p->stream));
-    cublasStatus_t cs = cublasDgemv(p->blas, CUBLAS_OP_T, (int)Q, n, &one, p->d_J, (int)Q, p->d_r, 1, &zero, p->d_g, 1);
+    cublasStatus_t cs = cublasDgemv(p->blas, CUBLAS_OP_T, (int)Q, n, &one, J, (int)Q, p->d_r, 1, &zero, p->d_g, 1);
     QC_CHECK(cs == CUBLAS_STATUS_SUCCESS, QCDMET_E_CUDA, "cublasDgemv failed: %d", (int)cs);
-    lm_damp_kernel<<<1024, 256, 0, p->stream>>>(p->d_A, p->d_Awork, n, lambda, 1e-12);
+    // equilibrated damped normal matrix W = D (A + lambda diag A) D and scale vector D (second half of d_g)
+    double *d_scale = p->d_g + p->P;
+    lm_damp_scaled_kernel<<<1024, 256, 0, p->stream>>>(p->d_A, p->d_Awork, d_scale, n, lambda, 1e-12);
     QC_CUDA(cudaGetLastError());
     int lwork = 0;
     cusolverStatus_t ss = cusolverDnDpotrf_bufferSize(p->solver, CUBLAS_FILL_MODE_UPPER, n, p->d_Awork, n, &lwork);
     QC_CHECK(ss == CUSOLVER_STATUS_SUCCESS, QCDMET_E_SOLVER, "cusolverDnDpotrf_bufferSize failed: %d", (int)ss);
+    lwork = std::max(lwork, n);
     if (lwork > p->potrf_lwork) {
         cudaFree(p->d_potrf);
         p->d_potrf = nullptr;
@@ -643,14 +1261,15 @@ extern "C" int qcdmet_plan_lm_step(qcdmet_plan *p, const double *resid, double l
     QC_CUDA(cudaMemcpyAsync(&hinfo, p->d_info, sizeof(int), cudaMemcpyDeviceToHost, p->stream));
     QC_CUDA(cudaStreamSynchronize(p->stream));
     QC_CHECK(hinfo == 0, QCDMET_E_SOLVER, "damped normal matrix not positive definite (potrf info %d): raise lambda", hinfo);
-    // step = -(A + lambda D)^-1 g   (reuse d_r's head as the right-hand side when it is long enough)
-    double *d_x = p->d_potrf;   // lwork >= n for potrf workspaces; fall back to d_r otherwise
-    if (p->potrf_lwork < n) d_x = p->d_r;
-    QC_CHECK(p->potrf_lwork >= n || Q >= n, QCDMET_E_STATE, "no scratch for the right-hand side");
+    // step = -D (D (A + lambda diag A) D)^-1 D g
+    double *d_x = p->d_potrf;
     lm_negate_kernel<<<(n + 255) / 256, 256, 0, p->stream>>>(p->d_g, d_x, n);
+    lm_scale_kernel<<<(n + 255) / 256, 256, 0, p->stream>>>(d_x, d_scale, n, 1.0);
     QC_CUDA(cudaGetLastError());
     ss = cusolverDnDpotrs(p->solver, CUBLAS_FILL_MODE_UPPER, n, 1, p->d_Awork, n, d_x, n, p->d_info);
     QC_CHECK(ss == CUSOLVER_STATUS_SUCCESS, QCDMET_E_SOLVER, "cusolverDnDpotrs failed: %d", (int)ss);
+    lm_scale_kernel<<<(n + 255) / 256, 256, 0, p->stream>>>(d_x, d_scale, n, 1.0);
+    QC_CUDA(cudaGetLastError());
     QC_CUDA(cudaMemcpyAsync(step, d_x, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, p->stream));
     if (info) {
         // info[0] = max |J^T r|, info[1] = g . step  (the linear model's slope along the step)
@@ -676,21 +1295,24 @@ extern "C" int qcdmet_plan_gradient(qcdmet_plan *p, const double *resid, double 
     const int n = p->colEnd - p->colBegin;
     const long long Q = p->Q;
     QC_CHECK(n > 0 && Q > 0 && Q < (1LL << 31), QCDMET_E_ARG, "empty or oversized problem");
-    if (!p->d_g) QC_TRY(dev_alloc(&p->d_g, (size_t)p->P));
-    if (!p->d_r) QC_TRY(dev_alloc(&p->d_r, (size_t)Q));
+    if (!p->d_g) QC_TRY(dev_alloc(&p->d_g, (size_t)2 * p->P));
+    if (!p->d_r) QC_TRY(dev_alloc(&p->d_r, (size_t)std::max<long long>(Q, p->P)));
     cublasSetStream(p->blas, p->stream);
     const double two = 2.0, zero = 0.0;
     QC_CUDA(cudaMemcpyAsync(p->d_r, resid, sizeof(double) * (size_t)Q, cudaMemcpyHostToDevice, p->stream));
-    cublasStatus_t cs = cublasDgemv(p->blas, CUBLAS_OP_T, (int)Q, n, &two, p->d_J, (int)Q, p->d_r, 1, &zero, p->d_g, 1);
+    cublasStatus_t cs = cublasDgemv(p->blas, CUBLAS_OP_T, (int)Q, n, &two, jac_slice(p), (int)Q, p->d_r, 1, &zero, p->d_g, 1);
     QC_CHECK(cs == CUBLAS_STATUS_SUCCESS, QCDMET_E_CUDA, "cublasDgemv failed: %d", (int)cs);
     QC_CUDA(cudaMemcpyAsync(grad, p->d_g, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, p->stream));
     QC_CUDA(cudaStreamSynchronize(p->stream));
     return QCDMET_OK;
 }
 
+extern "C" {
+
 int qcdmet_plan_detach_peers(qcdmet_plan *p)
 {
     QC_CHECK(p != nullptr, QCDMET_E_ARG, "plan is NULL");
+    QC_CHECK(!in_group(p), QCDMET_E_STATE, "multi-device plans manage their own peers");
     DeviceGuard guard(p->device);
     for (int r = 0; r < QCDMET_MAX_PEERS; ++r) {
         if (p->ipc_opened[r]) cudaIpcCloseMemHandle(p->ipc_opened[r]);
@@ -707,6 +1329,7 @@ int qcdmet_plan_detach_peers(qcdmet_plan *p)
 int qcdmet_plan_export_jacobian(qcdmet_plan *p, void *handle)
 {
     QC_CHECK(p != nullptr && handle != nullptr, QCDMET_E_ARG, "plan or handle is NULL");
+    QC_CHECK(!in_group(p), QCDMET_E_STATE, "multi-device plans manage their own peers");
     QC_CHECK(p->colBegin == 0 && p->colEnd == p->P && !p->d_J_ext, QCDMET_E_STATE,
              "export needs the full column range and the plan-owned buffer");
     DeviceGuard guard(p->device);
@@ -721,6 +1344,7 @@ int qcdmet_plan_export_jacobian(qcdmet_plan *p, void *handle)
 int qcdmet_plan_attach_peer_pointers(qcdmet_plan *p, int nranks, int rank, void *const *ptrs)
 {
     QC_CHECK(p != nullptr && ptrs != nullptr, QCDMET_E_ARG, "plan or pointer list is NULL");
+    QC_CHECK(!in_group(p), QCDMET_E_STATE, "multi-device plans manage their own peers");
     QC_CHECK(nranks >= 1 && nranks <= QCDMET_MAX_PEERS && rank >= 0 && rank < nranks, QCDMET_E_ARG,
              "invalid rank %d of %d (at most %d ranks)", rank, nranks, QCDMET_MAX_PEERS);
     QC_CHECK(p->dmma_ok, QCDMET_E_STATE, "peer mode needs the DMMA kernel: %s", p->dmma_why.c_str());
@@ -773,23 +1397,69 @@ int qcdmet_plan_attach_peers(qcdmet_plan *p, int nranks, int rank, const void *h
 int qcdmet_plan_sync(qcdmet_plan *p)
 {
     QC_CHECK(p != nullptr, QCDMET_E_ARG, "plan is NULL");
+    for (size_t m = 1; m < p->members.size(); ++m) {
+        DeviceGuard guard(p->members[m]->device);
+        QC_CUDA(cudaStreamSynchronize(p->members[m]->stream));
+    }
     DeviceGuard guard(p->device);
     QC_CUDA(cudaStreamSynchronize(p->stream));
     QC_CUDA(cudaGetLastError());
     return QCDMET_OK;
 }
 
-void *qcdmet_plan_jacobian_device(qcdmet_plan *p) { return p ? (void *)p->d_J : nullptr; }
+void *qcdmet_plan_jacobian_device(qcdmet_plan *p) { return p && p->d_J ? (void *)jac_slice(p) : nullptr; }
+
+/* Blocking copy of columns [colBegin + c0, colBegin + c1) of the computed slice to the host (J points at the
+ * first of them).  Multi-device plans: every device ships its share of the range from its own copy over its own
+ * PCIe link, one host thread per device (works for pageable and pinned destinations alike). */
+int qcdmet_plan_get_jacobian_columns(qcdmet_plan *p, int c0, int c1, double *J)
+{
+    QC_CHECK(p != nullptr && J != nullptr, QCDMET_E_ARG, "plan or J is NULL");
+    QC_CHECK(p->have_jac, QCDMET_E_STATE, "no Jacobian computed yet");
+    const int ncols = p->colEnd - p->colBegin;
+    QC_CHECK(0 <= c0 && c0 <= c1 && c1 <= ncols, QCDMET_E_ARG, "column range [%d,%d) outside the %d computed columns", c0, c1, ncols);
+    const auto t0 = std::chrono::steady_clock::now();
+    int rc = QCDMET_OK;
+    if (in_group(p) && c1 > c0) {
+        const int n = (int)p->members.size();
+        std::vector<int> rcs(n, QCDMET_OK);
+        std::vector<std::thread> th;
+        for (int m = 0; m < n; ++m) {
+            qcdmet_plan *q = p->members[m];
+            int lo, hi;
+            if (p->group_fused) shard_of(p->colBegin + c0, p->colBegin + c1, n, m, &lo, &hi);      // any member holds any column
+            else {                                                                               // a member holds its own shard
+                shard_of(p->colBegin, p->colEnd, n, m, &lo, &hi);
+                lo = std::max(lo, p->colBegin + c0);
+                hi = std::min(hi, p->colBegin + c1);
+            }
+            if (hi <= lo) continue;
+            double *dst = J + (size_t)p->Q * (lo - p->colBegin - c0);
+            th.emplace_back([q, lo, hi, dst, &rcs, m]() {
+                if (cudaSetDevice(q->device) != cudaSuccess ||
+                    cudaStreamSynchronize(q->stream) != cudaSuccess ||
+                    cudaMemcpy(dst, q->d_J + (size_t)q->Q * lo, sizeof(double) * (size_t)q->Q * (hi - lo),
+                               cudaMemcpyDeviceToHost) != cudaSuccess)
+                    rcs[m] = QCDMET_E_CUDA;
+            });
+        }
+        for (std::thread &t : th) t.join();
+        for (int m = 0; m < n; ++m)
+            if (rcs[m] != QCDMET_OK) { set_error("device-to-host copy of the Jacobian failed on device %d", p->members[m]->device); rc = rcs[m]; }
+    } else {
+        DeviceGuard guard(p->device);
+        const size_t n = (size_t)p->Q * (c1 - c0);
+        if (n) QC_CUDA(cudaMemcpyAsync(J, jac_slice(p) + (size_t)p->Q * c0, sizeof(double) * n, cudaMemcpyDeviceToHost, p->stream));
+        QC_CUDA(cudaStreamSynchronize(p->stream));
+    }
+    p->d2h_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    return rc;
+}
 
 int qcdmet_plan_get_jacobian(qcdmet_plan *p, double *J)
 {
     QC_CHECK(p != nullptr && J != nullptr, QCDMET_E_ARG, "plan or J is NULL");
-    QC_CHECK(p->have_jac, QCDMET_E_STATE, "no Jacobian computed yet");
-    DeviceGuard guard(p->device);
-    const size_t n = (size_t)p->Q * (p->colEnd - p->colBegin);
-    if (n) QC_CUDA(cudaMemcpyAsync(J, p->d_J, sizeof(double) * n, cudaMemcpyDeviceToHost, p->stream));
-    QC_CUDA(cudaStreamSynchronize(p->stream));
-    return QCDMET_OK;
+    return qcdmet_plan_get_jacobian_columns(p, 0, p->colEnd - p->colBegin, J);
 }
 
 int qcdmet_plan_get_dblocks(qcdmet_plan *p, double *D)
@@ -824,9 +1494,16 @@ int qcdmet_plan_get_orbitals(qcdmet_plan *p, double *C)
 
 long long qcdmet_plan_num_residuals(qcdmet_plan *p) { return p ? p->Q : -1; }
 int qcdmet_plan_kernel_used(qcdmet_plan *p) { return p ? p->kernel_used : -1; }
-int qcdmet_plan_launches(qcdmet_plan *p) { return p ? p->launches : -1; }
+int qcdmet_plan_launches(qcdmet_plan *p)
+{
+    if (!p) return -1;
+    int n = p->launches;
+    for (size_t m = 1; m < p->members.size(); ++m) n += p->members[m]->launches;
+    return n;
+}
 int qcdmet_plan_symmetric_used(qcdmet_plan *p) { return p ? (p->symmetric_used ? 1 : 0) : -1; }
 double qcdmet_plan_flops(qcdmet_plan *p) { return p ? p->flops : -1.0; }
+const char *qcdmet_plan_info(qcdmet_plan *p) { return p ? p->info.c_str() : ""; }
 
 int qcdmet_plan_kernel_time_ms(qcdmet_plan *p, double *ms)
 {
@@ -838,6 +1515,75 @@ int qcdmet_plan_kernel_time_ms(qcdmet_plan *p, double *ms)
     float f = 0.f;
     QC_CUDA(cudaEventElapsedTime(&f, p->ev0, p->ev1));
     *ms = f;
+    return QCDMET_OK;
+}
+
+/* Device-side breakdown of the last step (ms, -1 = not measured): H2D of H0, cuSOLVER syevd, panel build (set_h0),
+ * dominant kernel of the leader's share (compute), device->host copy of the Jacobian (wall clock of the last
+ * qcdmet_plan_get_jacobian*).  Synchronises the plan. */
+int qcdmet_plan_timings(qcdmet_plan *p, double *ms)
+{
+    QC_CHECK(p != nullptr && ms != nullptr, QCDMET_E_ARG, "plan or ms is NULL");
+    for (int i = 0; i < 5; ++i) ms[i] = -1.0;
+    QC_TRY(qcdmet_plan_sync(p));
+    DeviceGuard guard(p->device);
+    if (p->evT_valid) {
+        for (int i = 0; i < 3; ++i) {
+            float f = 0.f;
+            QC_CUDA(cudaEventElapsedTime(&f, p->evT[i], p->evT[i + 1]));
+            ms[i] = f;
+        }
+    }
+    QC_TRY(qcdmet_plan_kernel_time_ms(p, &ms[3]));
+    ms[4] = p->d2h_ms;
+    return QCDMET_OK;
+}
+
+/* Benchmark utility: evict the L2 of every device of the plan by overwriting a 256 MB scratch buffer on the
+ * plan's stream(s) (126 MB L2 on B200), so that a timed step does not start from a warm cache. */
+int qcdmet_plan_flush_l2(qcdmet_plan *p)
+{
+    QC_CHECK(p != nullptr, QCDMET_E_ARG, "plan is NULL");
+    const size_t bytes = (size_t)256 << 20;
+    if (in_group(p)) {
+        DeviceGuard guard(p->device);
+        QC_CUDA(cudaEventRecord(p->evStart, p->stream));
+    }
+    for (qcdmet_plan *q : (in_group(p) ? p->members : std::vector<qcdmet_plan *>{p})) {
+        DeviceGuard guard(q->device);
+        if (!q->d_flush && cudaMalloc(&q->d_flush, bytes) != cudaSuccess) {
+            cudaGetLastError();
+            set_error("cudaMalloc of the L2 flush buffer failed");
+            return QCDMET_E_ALLOC;
+        }
+        if (q != p) QC_CUDA(cudaStreamWaitEvent(q->stream, p->evStart, 0));
+        QC_CUDA(cudaMemsetAsync(q->d_flush, 0, bytes, q->stream));
+    }
+    return QCDMET_OK;
+}
+
+/* Checksum of the computed Jacobian slice on the device: out[0] = sum, out[1] = sum of squares (fixed reduction
+ * order: run-to-run and device-to-device reproducible), *bits = xor of the 64-bit patterns of every element.
+ * Multi-device plans with a replicated Jacobian: identical (may be NULL) receives 1 if every device holds a
+ * bit-identical copy. */
+int qcdmet_plan_jacobian_checksum(qcdmet_plan *p, double *out, unsigned long long *bits, int *identical)
+{
+    QC_CHECK(p != nullptr && out != nullptr && bits != nullptr, QCDMET_E_ARG, "plan, out or bits is NULL");
+    QC_CHECK(p->have_jac, QCDMET_E_STATE, "no Jacobian computed yet");
+    QC_TRY(qcdmet_plan_sync(p));
+    const size_t n = (size_t)p->Q * (p->colEnd - p->colBegin);
+    QC_TRY(device_checksum(p, jac_slice(p), n, &out[0], &out[1], bits));
+    if (identical) {
+        *identical = 1;
+        if (in_group(p) && p->group_fused)
+            for (size_t m = 1; m < p->members.size(); ++m) {
+                qcdmet_plan *q = p->members[m];
+                double a, b;
+                unsigned long long c;
+                QC_TRY(device_checksum(q, q->d_J + (size_t)q->Q * p->colBegin, n, &a, &b, &c));
+                if (memcmp(&a, &out[0], 8) || memcmp(&b, &out[1], 8) || c != *bits) *identical = 0;
+            }
+    }
     return QCDMET_OK;
 }
 
@@ -865,17 +1611,16 @@ int qcdmet_plan_get_full_response(qcdmet_plan *p, double *rdm_deriv, double *one
 // The stateless entry points keep the plan of the last call (lazily created per-process context,
 // SURVEY.md 8b "Ownership"): a Levenberg-Marquardt loop calls them many times with the same perturbation
 // list and fragment rows, and re-creating the device buffers (1.5 GB at N = 4000) and library handles on
-// every call would cost more than the kernels at small sizes.  Keyed on a hash of every index array (and
-// of R); released by qcdmet_shutdown().
+// every call would cost more than the kernels at small sizes.  Looked up by a hash of every index array and
+// confirmed by comparing the plan's own host copies (and two independent hashes of R); released by
+// qcdmet_shutdown().
 static std::mutex g_cache_mu;
 static qcdmet_plan *g_cached_plan = nullptr;
 static uint64_t g_cached_key = 0;
 
-static uint64_t fnv1a(uint64_t h, const void *data, size_t bytes)
+static bool same_ints(const std::vector<int> &have, const int *given, size_t n)
 {
-    const unsigned char *p = (const unsigned char *)data;
-    for (size_t i = 0; i < bytes; ++i) { h ^= p[i]; h *= 1099511628211ULL; }
-    return h;
+    return have.size() == n && (n == 0 || memcmp(have.data(), given, sizeof(int) * n) == 0);
 }
 
 static int jacobian_impl(int Norb, int Nterms, int numPairs, const int *H1start, const int *H1row,
@@ -888,17 +1633,32 @@ static int jacobian_impl(int Norb, int Nterms, int numPairs, const int *H1start,
     if (cudaGetDevice(&dev) != cudaSuccess) dev = -1;
     cudaGetLastError();
     const int S = Nfrag > 0 ? rowStart[Nfrag] : 0;
-    const int head[6] = {Norb, Nterms, numPairs, Nfrag, dev, R ? 1 : 0};
+    const int head[7] = {Norb, Nterms, numPairs, Nfrag, dev, R ? 1 : 0, default_devices()};
     uint64_t key = fnv1a(1469598103934665603ULL, head, sizeof(head));
     key = fnv1a(key, H1start, sizeof(int) * (size_t)(Nterms + 1));
     key = fnv1a(key, H1row, sizeof(int) * (size_t)H1start[Nterms]);
     key = fnv1a(key, H1col, sizeof(int) * (size_t)H1start[Nterms]);
     if (Nfrag > 0) key = fnv1a(key, rowStart, sizeof(int) * (size_t)(Nfrag + 1));
-    if (R) key = fnv1a(key, R, sizeof(double) * (size_t)S * Norb);
-    else if (S > 0) key = fnv1a(key, rowIdx, sizeof(int) * (size_t)S);
+    uint64_t rh[2] = {0, 0};
+    if (R) {
+        rh[0] = fnv1a(1469598103934665603ULL, R, sizeof(double) * (size_t)S * Norb);
+        rh[1] = mix64(0x243F6A8885A308D3ULL, R, sizeof(double) * (size_t)S * Norb);
+        key = fnv1a(key, rh, sizeof(rh));
+    } else if (S > 0) key = fnv1a(key, rowIdx, sizeof(int) * (size_t)S);
 
     std::lock_guard<std::mutex> lock(g_cache_mu);
-    if (!g_cached_plan || g_cached_key != key) {
+    bool reuse = g_cached_plan && g_cached_key == key;
+    if (reuse) {
+        // a 64-bit hash alone could collide: confirm against the plan's own host copies
+        const qcdmet_plan *c = g_cached_plan;
+        const size_t nnz = (size_t)H1start[Nterms];
+        reuse = c->N == Norb && c->P == Nterms && c->no == numPairs && c->F == Nfrag && c->device == dev &&
+                c->denseRows == (R != nullptr) && same_ints(c->h1start, H1start, (size_t)Nterms + 1) &&
+                same_ints(c->h1row, H1row, nnz) && same_ints(c->h1col, H1col, nnz) &&
+                (Nfrag == 0 || same_ints(c->rowStart, rowStart, (size_t)Nfrag + 1)) &&
+                (R ? (c->rHash[0] == rh[0] && c->rHash[1] == rh[1]) : same_ints(c->rowIdx, rowIdx, (size_t)S));
+    }
+    if (!reuse) {
         if (g_cached_plan) qcdmet_plan_destroy(g_cached_plan);
         g_cached_plan = nullptr;
         QC_TRY(qcdmet_plan_create(&g_cached_plan, -1, Norb, Nterms, numPairs, H1start, H1row, H1col, Nfrag,

@@ -1028,6 +1028,7 @@ int launch_jacobian_dmma(DmmaPlanData *d, const JacView &v, cudaStream_t st, int
 }
 
 bool dmma_last_launch_symmetric(const DmmaPlanData *d) { return d && d->launchSym; }
+bool dmma_plan_expanded(const DmmaPlanData *d) { return d && d->expanded; }
 
 // Host-only description of the schedule the DMMA kernel would use (no device needed): tests and tooling.
 void dmma_schedule_info(int N, int no, int P, int F, const int *h1start, const int *h1row, const int *h1col,

@@ -9,6 +9,7 @@ Mirrors src/dmet.py for everything on the correlation-potential (umat) fit path:
     rdm_differences_derivative                       src/dmet.py:477-525   <- fused GPU Jacobian
     costfunction / costfunction_derivative           src/dmet.py:361-363,381-388
     verify_gradient / hessian_eigenvalues            src/dmet.py:527-558
+    constructNOrotation                              src/dmet.py:343-359
     fit_umat (the SCmethod dispatch of doselfconsistent, src/dmet.py:626-636)
 
 The impurity solvers (PyCheMPS2 / pyscf wrappers, src/chemps2.py, src/pyscf_*.py) and the
@@ -62,6 +63,9 @@ class dmet:
 
         self.print_u = True
         self.print_rdm = True
+        self.print_hessian = False    # src/dmet.py:622-623: Hessian spectrum of the cost function per DMET iteration
+        self.last_hessian_eigenvalues = None
+        self.NOvecs = None
 
         allOne = self.testclusters()
         if not allOne:
@@ -73,6 +77,8 @@ class dmet:
         self.imp_size = self.make_imp_size()
         self.mu_imp = 0.0
         self.mask = self.make_mask()
+        self._mask_rc = None
+        self._imp_rows = None
         self.helper = qcdmethelper.qcdmethelper(self.ints, self.makelist_H1(), self.altcostfunc, self.minFunc)
 
         self.time_ed = 0.0
@@ -212,6 +218,12 @@ class dmet:
             start_ed = time.time()
             self.mu_imp = optimize.newton(self.numeleccostfunction, self.mu_imp)
             self.time_ed += time.time() - start_ed
+            # src/dmet.py:622-623 runs hessian_eigenvalues here on every iteration (P + 1 Jacobians for a
+            # debug print); kept behind a flag, off by default
+            if self.print_hessian and self.SCmethod != 'NONE' and not self.altcostfunc:
+                self.last_hessian_eigenvalues = self.hessian_eigenvalues(self.square2flat(self.umat))
+                if verbose:
+                    print("   Hessian eigenvalues (min, max) =", self.last_hessian_eigenvalues[[0, -1]])
             if self.SCmethod != 'NONE':
                 self.fit_umat()
             u_diff = np.linalg.norm(umat_old - self.umat)
@@ -226,29 +238,68 @@ class dmet:
 
     # ------------------------------------------------------------------ src/dmet.py:560-587
     def flat2square(self, umatflat):
-        umatsquare = np.zeros([self.Norb, self.Norb], dtype=float)
-        umatsquare[self.mask] = umatflat
-        umatsquare = umatsquare.T.copy()
-        umatsquare[self.mask] = umatflat
+        """umat = sum_p x_p H1_p: parameter p sits at the masked (row <= col) position p of the row-major
+        scan and at its mirror image; TI repeats cell 0 along the diagonal; an optional natural-orbital
+        rotation R maps the parameter basis to the lattice basis (R u R^T)."""
+        x = np.asarray(umatflat, dtype=float)
+        if self._mask_rc is None:
+            self._mask_rc = np.nonzero(self.mask)       # row-major order == the order of makelist_H1
+        rows, cols = self._mask_rc
+        u = np.zeros((self.Norb, self.Norb))
+        u[rows, cols] = x
+        u[cols, rows] = x
         if self.TransInv:
-            size = int(self.imp_size[0])
-            for it in range(1, self.Norb // size):
-                umatsquare[it * size:(it + 1) * size, it * size:(it + 1) * size] = umatsquare[0:size, 0:size]
+            m = int(self.imp_size[0])
+            ncell = self.Norb // m
+            u = np.kron(np.eye(ncell), u[:m, :m])
+            if ncell * m < self.Norb:
+                full = np.zeros((self.Norb, self.Norb))
+                full[:ncell * m, :ncell * m] = u
+                u = full
         if self.NOrotation is not None:
-            umatsquare = np.dot(np.dot(self.NOrotation, umatsquare), self.NOrotation.T)
-        return umatsquare
+            u = self.NOrotation @ u @ self.NOrotation.T
+        return u
 
     def square2flat(self, umatsquare):
-        umatsquare_bis = np.array(umatsquare, copy=True)
+        """Inverse of flat2square on its range: the masked upper-triangle entries in the parameter basis."""
+        u = np.asarray(umatsquare, dtype=float)
         if self.NOrotation is not None:
-            umatsquare_bis = np.dot(np.dot(self.NOrotation.T, umatsquare_bis), self.NOrotation)
-        return umatsquare_bis[self.mask]
+            u = self.NOrotation.T @ u @ self.NOrotation
+        return np.array(u[self.mask], copy=True)
+
+    # ------------------------------------------------------------------ src/dmet.py:343-359
+    def constructNOrotation(self, NOvecs=None):
+        """Block-diagonal orthogonal matrix holding the natural-orbital vectors of every fitted impurity
+        (identity on orbitals outside all impurities; TI: the first block repeated in every cell)."""
+        vecs = self.NOvecs if NOvecs is None else NOvecs
+        rot = np.eye(self.Norb)
+        pos = 0
+        for count, m in enumerate(int(x) for x in self.imp_size):
+            rot[pos:pos + m, pos:pos + m] = np.asarray(vecs[count], dtype=float)
+            pos += m
+        if self.TransInv:
+            m = int(self.imp_size[0])
+            for cell in range(1, self.Norb // m):
+                rot[cell * m:(cell + 1) * m, cell * m:(cell + 1) * m] = rot[:m, :m]
+        return rot
 
     # ------------------------------------------------------------------ fragment rows
+    def _umat_key(self, umatflat):
+        """Identity of Fock + umat(x) for the helper's eigensolve cache: the parameter vector itself (the Fock
+        matrix and the NO rotation are fixed while a fit runs; dmetOrbs changes select another plan)."""
+        nor = None if self.NOrotation is None else hash(np.asarray(self.NOrotation).tobytes())
+        return (np.asarray(umatflat, dtype=float).tobytes(), nor, id(self.ints))
+
     def _fragment_rows(self):
         """Residual rows per fragment: dmetOrbs[f]^T (fitImpBath, src/dmet.py:502) or the impurity
         site indices flatnonzero(impClust[f]) (src/dmet.py:509)."""
         nfit = len(self.imp_size)
+        if not self.fitImpBath:
+            if self._imp_rows is None:
+                idx = [np.flatnonzero(self.impClust[f]) for f in range(nfit)]
+                self._imp_rows = (np.concatenate([[0], np.cumsum([len(i) for i in idx])]).astype(np.int32), None,
+                                  np.concatenate(idx).astype(np.int32))
+            return self._imp_rows
         if self.fitImpBath:
             assert len(self.dmetOrbs) >= nfit, "fitImpBath needs dmetOrbs (run doexact first)"
             blocks = [np.ascontiguousarray(np.asarray(self.dmetOrbs[f], dtype=float).T) for f in range(nfit)]
@@ -266,10 +317,14 @@ class dmet:
         eigensolve that the Jacobian at the same umat reuses; otherwise the reference's
         host route (numpy eigh of the full matrix, src/qcdmethelper.py:114-122) is followed line by line."""
         if self.gpu_residual and not self.altcostfunc:
+            # E_GAP: unlike numpy's eigh on the host route, the device path refuses a vanishing HOMO-LUMO gap
+            # (the response at that umat is undefined anyway, lib/rhf_response.cc:66-71)
             start_func = time.time()
             row_start, rows, row_idx = self._fragment_rows()
+            # lattice basis, as src/dmet.py:399-421 (flat2square already carries the NO rotation of umat); the
+            # Jacobian call below passes NOrotation, so the two only share the eigensolve when it is None
             mf = self.helper.construct1RDM_blocks(self.flat2square(newumatflat), row_start, rows=rows,
-                                                  row_idx=row_idx, NOrotation=self.NOrotation)
+                                                  row_idx=row_idx, NOrotation=None, cache_key=self._umat_key(newumatflat))
             pieces = []
             for count in range(len(self.imp_size)):
                 if self.fitImpBath:
@@ -343,7 +398,7 @@ class dmet:
         newumatsquare_loc = self.flat2square(newumatflat)
         row_start, rows, row_idx = self._fragment_rows()
         gradient = self.helper.response_jacobian(newumatsquare_loc, row_start, rows=rows, row_idx=row_idx,
-                                                 NOrotation=self.NOrotation)
+                                                 NOrotation=self.NOrotation, cache_key=self._umat_key(newumatflat))
         self.time_grad += time.time() - start_grad
         return gradient
 
@@ -357,35 +412,34 @@ class dmet:
         start_grad = time.time()
         row_start, rows, row_idx = self._fragment_rows()
         plan = self.helper.response_jacobian_device(self.flat2square(newumatflat), row_start, rows=rows,
-                                                    row_idx=row_idx, NOrotation=self.NOrotation)
+                                                    row_idx=row_idx, NOrotation=self.NOrotation,
+                                                    cache_key=self._umat_key(newumatflat))
         thegradient = plan.gradient(errors)
         self.time_grad += time.time() - start_grad
         return thegradient
 
     # ------------------------------------------------------------------ src/dmet.py:527-539
-    def verify_gradient(self, umatflat):
-        gradient = self.costfunction_derivative(umatflat)
-        cost_reference = self.costfunction(umatflat)
-        gradientbis = np.zeros([len(gradient)], dtype=float)
-        stepsize = 1e-7
-        for cnt in range(len(gradient)):
-            umatbis = np.array(umatflat, copy=True)
-            umatbis[cnt] += stepsize
-            gradientbis[cnt] = (self.costfunction(umatbis) - cost_reference) / stepsize
-        return np.linalg.norm(gradient - gradientbis), np.linalg.norm(gradient)
+    def _unit_steps(self, x, h):
+        """x + h e_k for every parameter k (one row each)."""
+        x = np.asarray(x, dtype=float)
+        return x[None, :] + h * np.eye(x.size)
+
+    def verify_gradient(self, umatflat, stepsize=1e-7):
+        """Forward finite differences of the cost function against the analytic 2 J^T r.
+        Returns (|analytic - numeric|, |analytic|); the reference prints the two norms."""
+        analytic = self.costfunction_derivative(umatflat)
+        f0 = self.costfunction(umatflat)
+        numeric = np.array([(self.costfunction(xk) - f0) / stepsize for xk in self._unit_steps(umatflat, stepsize)])
+        return float(np.linalg.norm(analytic - numeric)), float(np.linalg.norm(analytic))
 
     # ------------------------------------------------------------------ src/dmet.py:541-558
-    def hessian_eigenvalues(self, umatflat):
-        stepsize = 1e-7
-        gradient_reference = self.costfunction_derivative(umatflat)
-        hessian = np.zeros([len(umatflat), len(umatflat)], dtype=float)
-        for cnt in range(len(umatflat)):
-            gradient = np.array(umatflat, copy=True)
-            gradient[cnt] += stepsize
-            gradient = self.costfunction_derivative(gradient)
-            hessian[:, cnt] = (gradient - gradient_reference) / stepsize
-        hessian = 0.5 * (hessian + hessian.T)
-        return np.sort(np.linalg.eigvalsh(hessian))
+    def hessian_eigenvalues(self, umatflat, stepsize=1e-7):
+        """Spectrum of the symmetrised forward-difference Hessian of the cost function: P + 1 analytic
+        gradients, each of which is one fused Jacobian + one device-side J^T r (no Jacobian leaves HBM)."""
+        g0 = self.costfunction_derivative(umatflat)
+        cols = [(self.costfunction_derivative(xk) - g0) / stepsize for xk in self._unit_steps(umatflat, stepsize)]
+        hess = np.stack(cols, axis=1) if cols else np.zeros((0, 0))
+        return np.linalg.eigvalsh(0.5 * (hess + hess.T))
 
     # ------------------------------------------------------------------ SURVEY.md 8 f-3
     def leastsq_gpu(self, x0, xtol=1e-13, gtol=1e-13, max_iter=100, verbose=False):
@@ -405,7 +459,7 @@ class dmet:
         for it in range(max_iter):
             start_grad = time.time()
             plan = self.helper.response_jacobian_device(self.flat2square(x), row_start, rows=rows, row_idx=row_idx,
-                                                        NOrotation=self.NOrotation)
+                                                        NOrotation=self.NOrotation, cache_key=self._umat_key(x))
             self.time_grad += time.time() - start_grad
             self.lm_iterations += 1
             accepted = False
