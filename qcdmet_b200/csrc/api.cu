@@ -502,9 +502,9 @@ int group_build(qcdmet_plan *p, int n)
     const bool over = overEnv && overEnv[0] == '1';
     QC_CHECK(n >= 1 && (n <= ndev || over) && n <= QCDMET_MAX_PEERS, QCDMET_E_ARG,
              "%d devices requested, %d visible (at most %d per plan)", n, ndev, QCDMET_MAX_PEERS);
+    if (in_group(p)) group_release(p);          // an existing group manages its own peer table
     QC_CHECK(!p->d_J_ext && !p->peers_on, QCDMET_E_STATE,
              "a plan with an external output buffer or attached IPC peers cannot span several devices");
-    group_release(p);
     p->fullLayout = (n > 1);
     if (n == 1) return QCDMET_OK;
     std::vector<int> devs(n);
@@ -1418,6 +1418,7 @@ int qcdmet_plan_get_jacobian_columns(qcdmet_plan *p, int c0, int c1, double *J)
     QC_CHECK(p->have_jac, QCDMET_E_STATE, "no Jacobian computed yet");
     const int ncols = p->colEnd - p->colBegin;
     QC_CHECK(0 <= c0 && c0 <= c1 && c1 <= ncols, QCDMET_E_ARG, "column range [%d,%d) outside the %d computed columns", c0, c1, ncols);
+    QC_TRY(qcdmet_plan_sync(p));                // the kernels are done: what is timed below is the copy alone
     const auto t0 = std::chrono::steady_clock::now();
     int rc = QCDMET_OK;
     if (in_group(p) && c1 > c0) {

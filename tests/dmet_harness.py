@@ -40,8 +40,31 @@ CASES = {
     "chain16_U4_single_site": (16, 4.0, 1, False, False, "LSTSQ"),
 }
 
+# 2-D Hubbard, l x l sites at half filling (PBC x anti-PBC: closed shell), 2 x 2 impurities: the shape of
+# BASELINE.json configs[1].  The embedded problem has 4 impurity + 4 bath orbitals (FCI dimension 4900, Davidson
+# route of fci_solver).  relaxation: the reference's umat damping attribute (src/dmet.py:40,652); the
+# impurity+bath fit oscillates without it on these lattices.
+#   name: (l, U, translation invariant, fitImpBath, relaxation)
+CASES_2D = {
+    "square8_TI_imp_only": (8, 4.0, True, False, 0.0),
+    "square8_TI_bath_damped": (8, 4.0, True, True, 0.5),
+    "square8_nonTI_imp_only": (8, 4.0, False, False, 0.0),
+    "square12_TI_imp_only": (12, 4.0, True, False, 0.0),
+    "square12_nonTI_imp_only": (12, 6.0, False, False, 0.0),
+    "square24_TI_imp_only": (24, 4.0, True, False, 0.0),
+    "square24_TI_bath_damped": (24, 2.0, True, True, 0.5),
+}
+
 
 def build(case, cls):
+    if case in CASES_2D:
+        from qcdmet_b200 import workloads as wl
+        l, u, ti, bath, relax = CASES_2D[case]
+        n = l * l
+        ints = lh.localintegrals_hubbard(wl.hubbard2d_hopping(l, l), u, n)
+        d = cls(ints, chain_clusters(n, 4), ti, method='ED', SCmethod='LSTSQ', fitImpBath=bath)
+        d.relaxation = relax
+        return d
     n, u, m, ti, bath, sc = CASES[case]
     ints = lh.localintegrals_hubbard(lh.hubbard_chain(n), u, n)
     return cls(ints, chain_clusters(n, m), ti, method='ED', SCmethod=sc, fitImpBath=bath)

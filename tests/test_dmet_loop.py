@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 
 from qcdmet_b200 import dmet as dmet_mod, fci_solver, localintegrals_hubbard as lh
-from dmet_harness import CASES, OracleDmet, build, chain_clusters
+from dmet_harness import CASES, CASES_2D, OracleDmet, build, chain_clusters
 
 
 def test_fci_standin_known_answers():
@@ -20,6 +20,37 @@ def test_fci_standin_known_answers():
     h4 = lh.hubbard_chain(4)
     e4, d4 = fci_solver.solve(0.0, h4, h4, np.zeros((4, 4, 4, 4)), 4, 4, 4)
     assert abs(e4 - 2 * np.sort(np.linalg.eigvalsh(h4))[:2].sum()) < 1e-12
+
+
+def test_fci_davidson_route_matches_dense_route(monkeypatch):
+    """The Kronecker-sum Davidson route (7..10 orbitals) against the dense route on a 6-orbital problem with a
+    dense two-electron tensor, then an 8-orbital known answer (non-interacting: sum of the lowest levels)."""
+    rng = np.random.default_rng(5)
+    n = 6
+    h = rng.standard_normal((n, n))
+    h = h + h.T
+    x = 0.3 * rng.standard_normal((n, n, 3))
+    x = x + x.transpose(1, 0, 2)
+    tei = np.einsum('ijx,klx->ijkl', x, x)                               # (ij|kl) with the 8-fold symmetry
+    e_dense, d_dense = fci_solver.solve(0.1, h, h, tei, n, 6, 3, chempot_imp=0.2)
+    monkeypatch.setattr(fci_solver, "DENSE_MAX_ORBITALS", 2)
+    e_dav, d_dav = fci_solver.solve(0.1, h, h, tei, n, 6, 3, chempot_imp=0.2)
+    assert abs(e_dav - e_dense) < 1e-10
+    assert np.abs(d_dav - d_dense).max() < 1e-8
+    monkeypatch.undo()
+    h8 = lh.hubbard_chain(8) + np.diag(0.05 * np.arange(8))
+    e8, d8 = fci_solver.solve(0.0, h8, h8, np.zeros((8,) * 4), 8, 8, 8)
+    assert abs(e8 - 2 * np.sort(np.linalg.eigvalsh(h8))[:4].sum()) < 1e-9
+    assert abs(np.trace(d8) - 8.0) < 1e-9
+
+
+def test_square_lattice_loop_runs_with_8_orbital_impurity_problem():
+    """configs[1] shape on CPU: 2 x 2 impurity + 4 bath orbitals (FCI dimension 4900) on the 8 x 8 lattice."""
+    d = build("square8_TI_imp_only", OracleDmet)
+    e = d.doselfconsistent()
+    assert d.dmetOrbs[0].shape == (64, 8)
+    assert e < d.ints.fullEhf - 1.0
+    assert np.abs(d.umat[:4, :4]).max() > 0.1 and abs(np.trace(d.umat)) < 1e-9
 
 
 def test_bath_construction_properties():
@@ -66,6 +97,21 @@ def test_converged_energy_matches_oracle_loop(case):
     assert abs(e_gpu - e_ref) <= 1e-8                                     # 1e-8 Hartree
     assert np.abs(gpu.umat - ref.umat).max() <= 1e-7
     assert gpu.time_grad > 0.0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", list(CASES_2D))
+def test_converged_energy_matches_oracle_loop_square_lattice(case):
+    """2-D Hubbard with 2 x 2 impurities (BASELINE.json configs[1]: 24 x 24 included): the 8-orbital embedded
+    problems go through the Davidson route of the FCI stand-in on both sides."""
+    ref = build(case, OracleDmet)
+    e_ref = ref.doselfconsistent()
+    gpu = build(case, dmet_mod.dmet)
+    e_gpu = gpu.doselfconsistent()
+    assert ref.iterations < 50 and gpu.iterations == ref.iterations
+    assert abs(e_gpu - e_ref) <= 1e-8                                     # 1e-8 Hartree
+    assert np.abs(gpu.umat - ref.umat).max() <= 1e-7
+    assert gpu.dmetOrbs[0].shape[1] == 8
 
 
 @pytest.mark.gpu
