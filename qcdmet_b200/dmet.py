@@ -58,6 +58,7 @@ class dmet:
             assert self.fitImpBath is False
             assert self.SCmethod in ('BFGS', 'NONE')
         self.solver = solver
+        self.solver_threads = 1            # > 1: the embedded problems of one doexact pass are solved in a thread pool
         self.gpu_residual = True      # residual blocks from the device eigensolve shared with the Jacobian
         self.fit_on_gpu = False       # LSTSQ: Levenberg-Marquardt with the normal equations solved on the device
 
@@ -164,6 +165,7 @@ class dmet:
             solver = fci_solver.solve
         maxiter = 1 if self.TransInv else len(self.impClust)
         remainingOrbs = np.ones([len(self.impClust[0])], dtype=float)
+        problems = []
         for counter in range(maxiter):
             impurityOrbs = np.abs(self.impClust[counter])
             numImpOrbs = int(np.sum(impurityOrbs))
@@ -186,11 +188,19 @@ class dmet:
             dmetOEI = self.ints.dmet_oei(loc2dmet, Norb_in_imp)
             dmetFOCK = self.ints.dmet_fock(loc2dmet, Norb_in_imp, core1RDM_loc)
             dmetTEI = self.ints.dmet_tei(loc2dmet, Norb_in_imp)
-            IMP_energy, IMP_1RDM = solver(0.0, dmetOEI, dmetFOCK, dmetTEI, Norb_in_imp, Nelec_in_imp,
-                                          numImpOrbs, chempot_imp)
+            problems.append((0.0, dmetOEI, dmetFOCK, dmetTEI, Norb_in_imp, Nelec_in_imp, numImpOrbs, chempot_imp))
+            remainingOrbs -= impurityOrbs
+        # the embedded problems are independent: solve them side by side (results are collected in fragment
+        # order, so the energy sum does not depend on the number of threads)
+        if self.solver_threads > 1 and len(problems) > 1:
+            from concurrent.futures import ThreadPoolExecutor
+            with ThreadPoolExecutor(max_workers=self.solver_threads) as pool:
+                solutions = list(pool.map(lambda args: solver(*args), problems))
+        else:
+            solutions = [solver(*args) for args in problems]
+        for IMP_energy, IMP_1RDM in solutions:
             self.energy += IMP_energy
             self.imp_1RDM.append(IMP_1RDM)
-            remainingOrbs -= impurityOrbs
         Nelectrons = 0.0
         for counter in range(maxiter):
             m = int(self.imp_size[counter])
