@@ -192,6 +192,25 @@ int qcdmet_plan_get_orbitals(qcdmet_plan *plan, double *C);
  * the 1-RDM (N*N) if one_rdm != NULL. */
 int qcdmet_plan_get_full_response(qcdmet_plan *plan, double *rdm_deriv, double *one_rdm);
 
+/* Mean-field 1-RDM 2 C_o C_o^T of the plan's orbitals, Norb x Norb doubles (symmetric); the matrix
+ * qcdmethelper.construct1RDM_loc returns (src/qcdmethelper.py:67-82,114-122). */
+int qcdmet_plan_get_one_rdm(qcdmet_plan *plan, double *one_rdm);
+
+/* Schmidt baths of Nfrag impurities in one call, from the plan's current orbitals.  Replaces
+ * qcdmethelper.constructbath (src/qcdmethelper.py:124-168: numpy eigh of the (N-m) x (N-m) environment block per
+ * fragment) by one m x m eigenproblem per fragment + one DGEMM, exact for the idempotent mean-field 1-RDM.
+ *   impStart[Nfrag+1], impIdx[S]: impurity orbitals of fragment f are impIdx[impStart[f] .. impStart[f+1]), m_f <= 64
+ *   numBathReq[Nfrag] (or NULL = m_f): bath orbitals wanted; threshold: the reference's 1e-13 (:124)
+ *   numBath[Nfrag]  out: bath orbitals kept = min(numBathReq, #candidates with min(occ, 2 - occ) > threshold) (:141-144)
+ *   occ[S]          out (may be NULL): environment occupations of the m_f candidates of each fragment, in rank order
+ *                   (closest to 1 first, :139-140); the first numBath[f] belong to the bath orbitals
+ *   bath[S * Norb]  out: row impStart[f] + k = k-th bath orbital of fragment f over the Norb lattice orbitals (zero on
+ *                   the fragment's own impurity orbitals, unit norm); rows k >= numBath[f] are zero.
+ * The reference's loc2dmet[:, :m+nb] is [unit vectors of the impurity orbitals | these rows^T]; eigenvector signs are
+ * arbitrary in both. */
+int qcdmet_plan_construct_baths(qcdmet_plan *plan, int Nfrag, const int *impStart, const int *impIdx,
+                                const int *numBathReq, double threshold, int *numBath, double *occ, double *bath);
+
 /* Levenberg-Marquardt step from the Jacobian resident on the device (no 8 Q P byte D2H):
  *   (J^T J + lambda diag(J^T J)) step = -J^T resid        resid: Q doubles (host), step: ncols doubles (host)
  * cuBLAS DSYRK/DGEMV + cuSOLVER potrf/potrs; J^T J is kept until the next compute, so retries with a

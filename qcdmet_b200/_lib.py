@@ -58,6 +58,10 @@ SIGNATURES = {
     "qcdmet_plan_get_eigenvalues": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     "qcdmet_plan_get_orbitals": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     "qcdmet_plan_get_full_response": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "qcdmet_plan_get_one_rdm": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
+    "qcdmet_plan_construct_baths": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
+                                                   ctypes.c_void_p, ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p,
+                                                   ctypes.c_void_p]),
     "qcdmet_plan_lm_step": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_double, ctypes.c_void_p,
                                            ctypes.c_void_p]),
     "qcdmet_plan_gradient": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
@@ -407,6 +411,26 @@ class Plan:
         out = np.empty(self.nresid, dtype=np.float64)
         check(self.lib.qcdmet_plan_get_dblocks(self.handle, _ptr(out)))
         return out
+
+    def one_rdm(self):
+        """Mean-field 1-RDM 2 C_o C_o^T of the plan's orbitals (what construct1RDM_loc returns)."""
+        out = np.empty((self.norb, self.norb), dtype=np.float64)
+        check(self.lib.qcdmet_plan_get_one_rdm(self.handle, _ptr(out)))
+        return out
+
+    def construct_baths(self, imp_start, imp_idx, num_bath_req=None, threshold=1e-13):
+        """Schmidt baths of all fragments from the plan's orbitals (qcdmet_plan_construct_baths).  Returns
+        (num_bath [F], occupations [S] in rank order, bath [S, Norb]: row imp_start[f] + k = k-th bath orbital)."""
+        imp_start, imp_idx = as_i32(imp_start), as_i32(imp_idx)
+        nfrag = imp_start.size - 1
+        req = as_i32(num_bath_req)
+        total = int(imp_start[-1])
+        num_bath = np.zeros(nfrag, dtype=np.int32)
+        occ = np.zeros(total, dtype=np.float64)
+        bath = np.zeros((total, self.norb), dtype=np.float64)
+        check(self.lib.qcdmet_plan_construct_baths(self.handle, nfrag, _ptr(imp_start), _ptr(imp_idx), _ptr(req),
+                                                   float(threshold), _ptr(num_bath), _ptr(occ), _ptr(bath)))
+        return num_bath, occ, bath
 
     def eigenvalues(self):
         out = np.empty(self.norb, dtype=np.float64)

@@ -1493,6 +1493,86 @@ int qcdmet_plan_get_orbitals(qcdmet_plan *p, double *C)
     return QCDMET_OK;
 }
 
+/* Mean-field 1-RDM 2 C_o C_o^T of the plan's orbitals (Norb x Norb, symmetric): src/qcdmethelper.py:114-122. */
+int qcdmet_plan_get_one_rdm(qcdmet_plan *p, double *one_rdm)
+{
+    QC_CHECK(p != nullptr && one_rdm != nullptr, QCDMET_E_ARG, "plan or one_rdm is NULL");
+    QC_CHECK(p->have_orbitals, QCDMET_E_STATE, "plan has no orbitals");
+    DeviceGuard guard(p->device);
+    double *d_full = nullptr;
+    QC_TRY(dev_alloc(&d_full, (size_t)p->N * p->N));
+    int rc = launch_one_rdm(p->d_CoT, p->ldo, p->N, p->no, d_full, p->stream);
+    if (rc == QCDMET_OK &&
+        cudaMemcpyAsync(one_rdm, d_full, sizeof(double) * (size_t)p->N * p->N, cudaMemcpyDeviceToHost, p->stream) != cudaSuccess)
+        rc = QCDMET_E_CUDA;
+    if (cudaStreamSynchronize(p->stream) != cudaSuccess) rc = QCDMET_E_CUDA;
+    cudaFree(d_full);
+    if (rc) { set_error("1-RDM construction failed"); return rc; }
+    return QCDMET_OK;
+}
+
+/* Schmidt bath orbitals of Nfrag impurities at once, from the plan's current orbitals (replaces the
+ * eigh of the environment block per fragment in src/qcdmethelper.py:124-168, see kernels_bath.cu for the algebra). */
+int qcdmet_plan_construct_baths(qcdmet_plan *p, int Nfrag, const int *impStart, const int *impIdx, const int *numBathReq,
+                                double threshold, int *numBath, double *occ, double *bath)
+{
+    QC_CHECK(p != nullptr && numBath != nullptr && bath != nullptr, QCDMET_E_ARG, "plan, numBath or bath is NULL");
+    QC_CHECK(p->have_orbitals, QCDMET_E_STATE, "plan has no orbitals: call set_h0/set_orbitals first");
+    QC_CHECK(Nfrag >= 0 && (Nfrag == 0 || (impStart != nullptr && impStart[0] == 0)), QCDMET_E_ARG, "impStart[0] must be 0");
+    if (Nfrag == 0) return QCDMET_OK;
+    int maxM = 0;
+    for (int f = 0; f < Nfrag; ++f) {
+        const int m = impStart[f + 1] - impStart[f];
+        QC_CHECK(m >= 0, QCDMET_E_ARG, "impStart not monotone at %d", f);
+        QC_CHECK(m <= QCDMET_BATH_MAX_IMP, QCDMET_E_ARG, "fragment %d has %d impurity orbitals (at most %d)", f, m,
+                 QCDMET_BATH_MAX_IMP);
+        QC_CHECK(!numBathReq || numBathReq[f] >= 0, QCDMET_E_ARG, "numBathReq[%d] is negative", f);
+        maxM = std::max(maxM, m);
+    }
+    const int S = impStart[Nfrag];
+    if (S == 0) { std::fill(numBath, numBath + Nfrag, 0); return QCDMET_OK; }
+    QC_CHECK(impIdx != nullptr, QCDMET_E_ARG, "impIdx is NULL");
+    std::vector<int> rowFrag(S);
+    for (int f = 0; f < Nfrag; ++f) {
+        for (int a = impStart[f]; a < impStart[f + 1]; ++a) {
+            QC_CHECK(impIdx[a] >= 0 && impIdx[a] < p->N, QCDMET_E_ARG, "impIdx[%d] = %d out of range", a, impIdx[a]);
+            for (int b = impStart[f]; b < a; ++b)
+                QC_CHECK(impIdx[b] != impIdx[a], QCDMET_E_ARG, "orbital %d listed twice in fragment %d", impIdx[a], f);
+            rowFrag[a] = f;
+        }
+    }
+    DeviceGuard guard(p->device);
+    int *d_impStart = nullptr, *d_impIdx = nullptr, *d_rowFrag = nullptr, *d_req = nullptr, *d_kept = nullptr, *d_sweeps = nullptr;
+    double *d_Y = nullptr, *d_occ = nullptr, *d_B = nullptr;
+    int rc = QCDMET_OK;
+    std::vector<int> sweeps(Nfrag, 0);
+    do {
+        if ((rc = dev_alloc_copy(&d_impStart, impStart, (size_t)Nfrag + 1))) break;
+        if ((rc = dev_alloc_copy(&d_impIdx, impIdx, (size_t)S))) break;
+        if ((rc = dev_alloc_copy(&d_rowFrag, rowFrag.data(), (size_t)S))) break;
+        if (numBathReq && (rc = dev_alloc_copy(&d_req, numBathReq, (size_t)Nfrag))) break;
+        if ((rc = dev_alloc(&d_kept, (size_t)Nfrag)) || (rc = dev_alloc(&d_sweeps, (size_t)Nfrag))) break;
+        if ((rc = dev_alloc(&d_Y, (size_t)S * p->ldo)) || (rc = dev_alloc(&d_occ, (size_t)S)) ||
+            (rc = dev_alloc(&d_B, (size_t)S * p->N))) break;
+        if ((rc = launch_construct_baths(p->blas, p->d_CoT, p->ldo, p->N, p->no, Nfrag, S, maxM, d_impStart, d_impIdx, d_rowFrag,
+                                         d_req, threshold, d_Y, d_occ, d_kept, d_sweeps, d_B, p->stream))) break;
+        if (cudaMemcpyAsync(numBath, d_kept, sizeof(int) * (size_t)Nfrag, cudaMemcpyDeviceToHost, p->stream) != cudaSuccess ||
+            cudaMemcpyAsync(sweeps.data(), d_sweeps, sizeof(int) * (size_t)Nfrag, cudaMemcpyDeviceToHost, p->stream) != cudaSuccess ||
+            (occ && cudaMemcpyAsync(occ, d_occ, sizeof(double) * (size_t)S, cudaMemcpyDeviceToHost, p->stream) != cudaSuccess) ||
+            cudaMemcpyAsync(bath, d_B, sizeof(double) * (size_t)S * p->N, cudaMemcpyDeviceToHost, p->stream) != cudaSuccess ||
+            cudaStreamSynchronize(p->stream) != cudaSuccess) {
+            set_error("bath construction failed: %s", cudaGetErrorString(cudaGetLastError()));
+            rc = QCDMET_E_CUDA;
+        }
+    } while (0);
+    cudaFree(d_impStart); cudaFree(d_impIdx); cudaFree(d_rowFrag); cudaFree(d_req); cudaFree(d_kept); cudaFree(d_sweeps);
+    cudaFree(d_Y); cudaFree(d_occ); cudaFree(d_B);
+    QC_TRY(rc);
+    for (int f = 0; f < Nfrag; ++f)
+        QC_CHECK(sweeps[f] < 60, QCDMET_E_SOLVER, "Jacobi iteration of fragment %d did not converge in 60 sweeps", f);
+    return QCDMET_OK;
+}
+
 long long qcdmet_plan_num_residuals(qcdmet_plan *p) { return p ? p->Q : -1; }
 int qcdmet_plan_kernel_used(qcdmet_plan *p) { return p ? p->kernel_used : -1; }
 int qcdmet_plan_launches(qcdmet_plan *p)

@@ -79,6 +79,13 @@ int launch_build_w(const double *e, int no, int nv, int ldo, double *W, cudaStre
 int launch_jacobian_general(const JacView &v, cudaStream_t st, int *launches, double *flops,
                             cudaEvent_t ev0, cudaEvent_t ev1);
 
+// kernels_bath.cu: Schmidt baths of all fragments from the occupied orbitals (m x m Jacobi per fragment + one DGEMM)
+#define QCDMET_BATH_MAX_IMP 64          // impurity orbitals per fragment the batched bath kernel handles
+int launch_construct_baths(cublasHandle_t blas, const double *CoT, int ldo, int N, int no, int F, int S, int maxM,
+                           const int *d_impStart, const int *d_impIdx, const int *d_rowFrag, const int *d_numReq,
+                           double threshold, double *d_Y, double *d_occ, int *d_numKept, int *d_sweeps, double *d_B,
+                           cudaStream_t st);
+
 // Destinations of the fused all-gather: every rank of a node maps every rank's full Jacobian buffer;
 // the DMMA kernel stores each element it produces into all of them (NVLink peer stores).
 #define QCDMET_MAX_PEERS 8

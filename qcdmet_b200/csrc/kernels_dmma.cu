@@ -45,7 +45,7 @@ namespace qcdmet {
 namespace {
 
 constexpr int KC = 16;        // virtual orbitals per pipeline stage
-constexpr int STAGES = 4;
+constexpr int MIN_STAGES = 4, MAX_STAGES = 8;   // TMA ring depth: as deep as shared memory allows (Cfg::STAGES)
 constexpr int RT = 4;         // site slots per component  (= M-warps)
 constexpr int AT = 32;        // row slots per a-tile
 constexpr int MAXRF = 8;      // max rows per fragment over all variants
@@ -56,6 +56,27 @@ constexpr int NTHREADS = NCONS + 32;
 constexpr int TP = 128;       // max perturbations over the blocks of one tile
 constexpr int PV_STAGE = KC * AT;
 constexpr int CV_STAGE = KC * RT;
+
+// Item tables: everything a CTA needs to know about a work item (component, tile) lives in two contiguous blobs,
+// one per tile and one per component, which the producer copies into shared memory with two TMA bulk copies
+// (TABS-deep ring), so the persistent CTA never waits on a dependent global load between two items.
+constexpr int TT_QROW = 0;                               // long long [AT]        qoff[f] + a_loc
+constexpr int TT_TROW = TT_QROW + AT * 8;                // int [AT]              fragment-row index or -1
+constexpr int TT_TP = TT_TROW + AT * 4;                  // int [TP]              perturbations of the blocks in the tile (sym mode)
+constexpr int TT_TE = TT_TP + TP * 4;                    // u8 [TP][MAXE]         a_slot | j << 5, 0xFF = none (sym mode)
+constexpr int TT_PARTNER = TT_TE + TP * MAXE;            // u8 [AT][RF]           slot of the j-th row of the fragment, AT = none
+constexpr int TT_SELF = TT_PARTNER + AT * MAXRF;         // u8 [AT]               a_loc | r_f << 4
+constexpr int TILE_TAB_BYTES = TT_SELF + AT;
+constexpr int CT_Q = 0;                                  // long long             qoff of the component's own fragment (sym mode)
+constexpr int CT_TILE = 8;                               // int                   tile holding that fragment (sym mode)
+constexpr int CT_LOC = 12;                               // u8 [RT]               local row index of site slot | r_f << 4 (sym mode)
+constexpr int CT_CP = 16;                                // int [MAXP]            perturbation index or -1
+constexpr int CT_CENT = CT_CP + MAXP * 4;                // u8 [MAXP][MAXE]       rs | cs << 4, 0xFF = none
+constexpr int COMP_TAB_BYTES = CT_CENT + MAXP * MAXE;
+constexpr int ITEM_TAB_BYTES = TILE_TAB_BYTES + COMP_TAB_BYTES;
+constexpr int TABS = 3;                                  // item-table ring: current item, deferred assembly of the previous one, prefetch
+static_assert(TILE_TAB_BYTES % 16 == 0 && COMP_TAB_BYTES % 16 == 0, "TMA bulk copies move multiples of 16 bytes");
+constexpr int SMEM_LIMIT = 232448;                       // 227 KB: opt-in dynamic shared memory per CTA on sm_100
 
 // Kernel variant: RF = max rows per fragment (4: impurity-only 2x2 fits; 8: impurity+bath rows of a
 // 4-orbital impurity), NJ = 8-column DMMA fragments per warp (column tile BN = 16 NJ: 128 / 96 / 64,
@@ -72,46 +93,46 @@ struct Cfg {
     static constexpr int COS_DOUBLES = RT * BN;
     static constexpr uint32_t EPI_BYTES = (POS_DOUBLES + COS_DOUBLES) * 8;
     static constexpr int NSTRIDE = RT * RF + 2;         // running-sum row stride (conflict-free 16 B slots)
+    static constexpr int NS_DOUBLES = 2 * 128 * NSTRIDE;   // running sums of one item: [column half][site slot][row slot][NSTRIDE]
+    // barriers: full/empty per stage, epilogue operands full/empty, item tables full/empty, running sums done/free, lead
+    static constexpr int BAR_BYTES = (((2 * MAX_STAGES + 2 + 2 * TABS + 4 + 1) * 8 + 15) / 16) * 16;
+    static constexpr int AUX_BYTES = BAR_BYTES + TABS * ITEM_TAB_BYTES;
+    static constexpr int FIXED1 = (POS_DOUBLES + COS_DOUBLES + NS_DOUBLES) * 8 + AUX_BYTES;
+    // two running-sum buffers when they fit next to a minimal ring: the assembly + stores of item k then run inside
+    // item k+1, warp by warp, next to the other warps' DMMAs instead of in a CTA-wide bubble
+    static constexpr int NSBUF = (MIN_STAGES * (int)STAGE_BYTES + FIXED1 + NS_DOUBLES * 8 <= SMEM_LIMIT) ? 2 : 1;
+    static constexpr int FIXED = FIXED1 + (NSBUF - 1) * NS_DOUBLES * 8;
+    // ring depth: the rest of the shared memory.  A deep ring lets the two warps of an SM sub-partition run several
+    // stages apart, so that one of them is in the DMMA main loop while the other one is in its epilogue.
+    static constexpr int STAGES_FIT = (SMEM_LIMIT - FIXED) / (int)STAGE_BYTES;
+    static constexpr int STAGES = STAGES_FIT > MAX_STAGES ? MAX_STAGES : STAGES_FIT;
+    static_assert(STAGES >= MIN_STAGES, "shared memory budget");
     static constexpr int SM_STAGE_OFF = 0;
     static constexpr int SM_POS_OFF = SM_STAGE_OFF + STAGES * STAGE_DOUBLES * 8;
     static constexpr int SM_COS_OFF = SM_POS_OFF + POS_DOUBLES * 8;
     static constexpr int SM_NS_OFF = SM_COS_OFF + COS_DOUBLES * 8;
-    static constexpr int SM_BAR_OFF = SM_NS_OFF + 2 * 128 * NSTRIDE * 8;
-    static constexpr int SM_TAB_OFF = SM_BAR_OFF + (2 * STAGES + 2) * 8;
-    // tables: qrow[32] (8B) | tileRow[32] (4B) | compP[16] (4B) | partner[32][RF] (1B) | self[32] (1B)
-    //         | compEnt[16][4] (1B)
-    static constexpr int TAB_QROW = 0;
-    static constexpr int TAB_TROW = TAB_QROW + AT * 8;
-    static constexpr int TAB_CP = TAB_TROW + AT * 4;
-    static constexpr int TAB_PARTNER = TAB_CP + MAXP * 4;
-    static constexpr int TAB_SELF = TAB_PARTNER + AT * RF;
-    static constexpr int TAB_CENT = TAB_SELF + AT;
-    static constexpr int TAB_BYTES = TAB_CENT + MAXP * MAXE;
-    static constexpr int SMEM_BYTES = SM_TAB_OFF + ((TAB_BYTES + 15) / 16) * 16;
+    static constexpr int SM_BAR_OFF = SM_NS_OFF + NSBUF * NS_DOUBLES * 8;
+    static constexpr int SM_TAB_OFF = SM_BAR_OFF + BAR_BYTES;
+    static constexpr int SMEM_BYTES = SM_TAB_OFF + TABS * ITEM_TAB_BYTES;
+    static_assert(SMEM_BYTES <= SMEM_LIMIT, "shared memory budget");
+    static_assert(SM_TAB_OFF % 16 == 0 && SM_POS_OFF % 16 == 0 && SM_COS_OFF % 16 == 0, "TMA destinations are 16-byte aligned");
 };
 
 struct DmmaArgs {
     int nKc, nOt;
+    int nWork;                          // work items of this launch; CTA b executes items b, b + gridDim.x, ...
+    int lead;                           // stages warps 0-3 run ahead of warps 4-7 (0 = start together), < ring depth
     int colBegin, colEnd;
     int sym;                            // symmetric mode: also store the mirrored patch
     long long Q;
     const double *Wt, *PVt, *CVt, *POt, *COt;
-    const int2 *work;                   // (component, tile) per CTA
-    const int *compTile;                // [nComp] tile holding the component's fragment (sym mode)
-    const long long *compQ;             // [nComp] qoff of that fragment (sym mode)
-    const unsigned char *compLoc;       // [nComp][RT] local row index of site slot | r_f << 4 (sym mode)
-    const int *tileP;                   // [nTiles][TP] perturbations of the blocks in the tile (sym mode)
-    const unsigned char *tileEnt;       // [nTiles][TP][MAXE] a_slot | j << 5, 0xFF = none (sym mode)
-    const int *compSites;               // [nComp][RT]   site or -1
-    const int *compP;                   // [nComp][MAXP] perturbation index or -1
-    const unsigned char *compEnt;       // [nComp][MAXP][MAXE]  rs | cs << 4, 0xFF = none
-    const int *tileRow;                 // [nTiles][AT]  fragment-row index or -1
-    const unsigned char *tilePartner;   // [nTiles][AT][RF] slot of the j-th row of the fragment, AT = none (RF of the variant)
-    const unsigned char *tileSelf;      // [nTiles][AT]  a_loc | r_f << 4
-    const long long *tileQ;             // [nTiles][AT]  qoff[f] + a_loc
+    const int2 *work;                   // (component, tile) per work item
+    const unsigned char *tileTab;       // [nTiles][TILE_TAB_BYTES]
+    const unsigned char *compTab;       // [nComp][COMP_TAB_BYTES]
     // panel mode (large fragments): no epilogue, the M panels go to HBM as Mout[(4 comp + r)][row][ldm]
     double *Mout;
     int mRows, ldm;
+    long long *prof;                    // PROF builds: [gridDim.x][8 warps][8] cycle counters
     int nDest;                          // destinations of every Jacobian store (1, or the ranks of a node)
     double *J[QCDMET_MAX_PEERS];        // J[0..nDest): own buffer and peer-mapped buffers (NVLink P2P stores)
 };
@@ -274,80 +295,89 @@ __global__ void sum_subcolumns_kernel(const double *__restrict__ Jsub, const int
 // ------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------
+// Persistent: one CTA per SM walks the work list with stride gridDim.x.  The producer warp keeps the TMA ring
+// running across work items (the first stages, the item tables and the epilogue operands of the next item are
+// in flight while the consumers finish the current one), and with two running-sum buffers the final assembly
+// + stores of item k are executed by every consumer warp on its own inside item k+1.
 // PANEL = true: no epilogue, the M panels go to HBM (factorised path for large fragments, end of this file)
-template <class C, bool PANEL = false>
+// PROF = true (tuning builds only, $QCDMET_B200_PROFILE): every consumer warp adds up the clock cycles it spends
+// waiting for stages / in the stage bodies / waiting for epilogue operands / in the epilogue / in the assembly.
+template <class C, bool PANEL = false, bool PROF = false>
 __global__ void __launch_bounds__(NTHREADS, 1) jac_dmma_kernel(const DmmaArgs g)
 {
     constexpr int RF = C::RF, NJ = C::NJ, BN = C::BN, PSTRIDE = C::PSTRIDE, NSTRIDE = C::NSTRIDE;
     constexpr int W_STAGE = C::W_STAGE, STAGE_DOUBLES = C::STAGE_DOUBLES;
     constexpr int POS_DOUBLES = C::POS_DOUBLES, COS_DOUBLES = C::COS_DOUBLES;
+    constexpr int NSBUF = C::NSBUF, NS_DOUBLES = C::NS_DOUBLES, STAGES = C::STAGES;
     extern __shared__ __align__(128) unsigned char smem[];
     double *stageBase = reinterpret_cast<double *>(smem + C::SM_STAGE_OFF);
     double *POS = reinterpret_cast<double *>(smem + C::SM_POS_OFF);
     double *CoS = reinterpret_cast<double *>(smem + C::SM_COS_OFF);
     double *Ns = reinterpret_cast<double *>(smem + C::SM_NS_OFF);
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + C::SM_BAR_OFF);
-    unsigned char *tab = smem + C::SM_TAB_OFF;
-    long long *qrow = reinterpret_cast<long long *>(tab + C::TAB_QROW);
-    int *trow = reinterpret_cast<int *>(tab + C::TAB_TROW);
-    int *cp = reinterpret_cast<int *>(tab + C::TAB_CP);
-    unsigned char *partner = tab + C::TAB_PARTNER;
-    unsigned char *selfi = tab + C::TAB_SELF;
-    unsigned char *cent = tab + C::TAB_CENT;
+    unsigned char *tabs = smem + C::SM_TAB_OFF;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int2 wk = g.work[blockIdx.x];
-    const int comp = wk.x, tile = wk.y;
-    const int nKc = g.nKc, nOt = g.nOt;
-    const uint32_t epiFull = smem_u32(&bars[2 * STAGES]), epiEmpty = smem_u32(&bars[2 * STAGES + 1]);
+    const int nKc = g.nKc, nOt = g.nOt, nWork = g.nWork;
+    const uint32_t barBase = smem_u32(bars);
+    const uint32_t epiFull = barBase + 8 * (2 * STAGES), epiEmpty = epiFull + 8;
+    const uint32_t tabFull0 = epiEmpty + 8, tabEmpty0 = tabFull0 + 8 * TABS;
+    const uint32_t nsDone0 = tabEmpty0 + 8 * TABS, nsFree0 = nsDone0 + 8 * 2, leadBar = nsFree0 + 8 * 2;
 
-    // ---- set-up: barriers, tables, zeroed running sums
+    // ---- set-up: barriers
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) {
-            mbar_init(smem_u32(&bars[s]), 1);              // full: producer's expect_tx arrival
-            mbar_init(smem_u32(&bars[STAGES + s]), 8);     // empty: one arrival per consumer warp
+            mbar_init(barBase + 8 * s, 1);                 // full: producer's expect_tx arrival
+            mbar_init(barBase + 8 * (STAGES + s), 8);      // empty: one arrival per consumer warp
         }
         mbar_init(epiFull, 1);
         mbar_init(epiEmpty, 8);
+        for (int t = 0; t < TABS; ++t) { mbar_init(tabFull0 + 8 * t, 1); mbar_init(tabEmpty0 + 8 * t, 8); }
+        for (int b = 0; b < 2; ++b) { mbar_init(nsDone0 + 8 * b, 8); mbar_init(nsFree0 + 8 * b, 8); }
+        mbar_init(leadBar, 4);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (tid < AT) {
-        qrow[tid] = g.tileQ[tile * AT + tid];
-        trow[tid] = g.tileRow[tile * AT + tid];
-        selfi[tid] = g.tileSelf[tile * AT + tid];
-    }
-    if (tid < AT * RF) partner[tid] = g.tilePartner[tile * AT * RF + tid];
-    if (tid < MAXP) cp[tid] = g.compP[comp * MAXP + tid];
-    if (tid < MAXP * MAXE) cent[tid] = g.compEnt[comp * MAXP * MAXE + tid];
-    for (int i = tid; i < 2 * 128 * NSTRIDE; i += NTHREADS) Ns[i] = 0.0;
     __syncthreads();
 
     if (warp == 8) {
         // ================= producer warp: one elected lane drives the TMA pipeline =================
         if (lane == 0) {
-            const double *pvsrc = g.PVt + (size_t)tile * nKc * PV_STAGE;
-            const double *cvsrc = g.CVt + (size_t)comp * nKc * CV_STAGE;
-            const double *posrc = g.POt + (size_t)tile * nOt * POS_DOUBLES;
-            const double *cosrc = g.COt + (size_t)comp * nOt * COS_DOUBLES;
             const int epiAt = nKc > 3 ? nKc - 3 : 0;      // prefetch the epilogue operands near the end of a tile
-            int it = 0;
-            for (int ot = 0; ot < nOt; ++ot) {
-                const double *wsrc = g.Wt + (size_t)ot * nKc * W_STAGE;
-                for (int kc = 0; kc < nKc; ++kc, ++it) {
-                    if (!PANEL && kc == epiAt) {
-                        mbar_wait(epiEmpty, (ot & 1) ^ 1);          // every warp is done with tile ot-1's operands
-                        mbar_expect_tx(epiFull, C::EPI_BYTES);
-                        tma_bulk_g2s(smem_u32(POS), posrc + (size_t)ot * POS_DOUBLES, POS_DOUBLES * 8, epiFull);
-                        tma_bulk_g2s(smem_u32(CoS), cosrc + (size_t)ot * COS_DOUBLES, COS_DOUBLES * 8, epiFull);
+            int rs = 0, rph = 0, T = 0, k = 0;           // ring slot and phase of the next stage
+            int2 wkNext = blockIdx.x < nWork ? g.work[blockIdx.x] : make_int2(0, 0);
+            for (int w = blockIdx.x; w < nWork; w += gridDim.x, ++k) {
+                const int comp = wkNext.x, tile = wkNext.y;
+                if (w + (int)gridDim.x < nWork) wkNext = g.work[w + gridDim.x];
+                // item tables
+                const int tb = k % TABS;
+                mbar_wait(tabEmpty0 + 8 * tb, ((k / TABS) & 1) ^ 1);
+                mbar_expect_tx(tabFull0 + 8 * tb, ITEM_TAB_BYTES);
+                unsigned char *tdst = tabs + tb * ITEM_TAB_BYTES;
+                tma_bulk_g2s(smem_u32(tdst), g.tileTab + (size_t)tile * TILE_TAB_BYTES, TILE_TAB_BYTES, tabFull0 + 8 * tb);
+                tma_bulk_g2s(smem_u32(tdst + TILE_TAB_BYTES), g.compTab + (size_t)comp * COMP_TAB_BYTES, COMP_TAB_BYTES,
+                             tabFull0 + 8 * tb);
+                const double *pvsrc = g.PVt + (size_t)tile * nKc * PV_STAGE;
+                const double *cvsrc = g.CVt + (size_t)comp * nKc * CV_STAGE;
+                const double *posrc = g.POt + (size_t)tile * nOt * POS_DOUBLES;
+                const double *cosrc = g.COt + (size_t)comp * nOt * COS_DOUBLES;
+                for (int ot = 0; ot < nOt; ++ot, ++T) {
+                    const double *wsrc = g.Wt + (size_t)ot * nKc * W_STAGE;
+                    for (int kc = 0; kc < nKc; ++kc) {
+                        if (!PANEL && kc == epiAt) {
+                            mbar_wait(epiEmpty, (T & 1) ^ 1);       // every warp is done with the previous tile's operands
+                            mbar_expect_tx(epiFull, C::EPI_BYTES);
+                            tma_bulk_g2s(smem_u32(POS), posrc + (size_t)ot * POS_DOUBLES, POS_DOUBLES * 8, epiFull);
+                            tma_bulk_g2s(smem_u32(CoS), cosrc + (size_t)ot * COS_DOUBLES, COS_DOUBLES * 8, epiFull);
+                        }
+                        const uint32_t full = barBase + 8 * rs, empty = barBase + 8 * (STAGES + rs);
+                        mbar_wait(empty, rph ^ 1);
+                        mbar_expect_tx(full, C::STAGE_BYTES);
+                        double *dst = stageBase + (size_t)rs * STAGE_DOUBLES;
+                        tma_bulk_g2s(smem_u32(dst), wsrc + (size_t)kc * W_STAGE, W_STAGE * 8, full);
+                        tma_bulk_g2s(smem_u32(dst + W_STAGE), pvsrc + (size_t)kc * PV_STAGE, PV_STAGE * 8, full);
+                        tma_bulk_g2s(smem_u32(dst + W_STAGE + PV_STAGE), cvsrc + (size_t)kc * CV_STAGE, CV_STAGE * 8, full);
+                        if (++rs == STAGES) { rs = 0; rph ^= 1; }
                     }
-                    const int s = it % STAGES;
-                    const uint32_t full = smem_u32(&bars[s]), empty = smem_u32(&bars[STAGES + s]);
-                    mbar_wait(empty, ((it / STAGES) & 1) ^ 1);
-                    mbar_expect_tx(full, C::STAGE_BYTES);
-                    double *dst = stageBase + (size_t)s * STAGE_DOUBLES;
-                    tma_bulk_g2s(smem_u32(dst), wsrc + (size_t)kc * W_STAGE, W_STAGE * 8, full);
-                    tma_bulk_g2s(smem_u32(dst + W_STAGE), pvsrc + (size_t)kc * PV_STAGE, PV_STAGE * 8, full);
-                    tma_bulk_g2s(smem_u32(dst + W_STAGE + PV_STAGE), cvsrc + (size_t)kc * CV_STAGE, CV_STAGE * 8, full);
                 }
             }
         }
@@ -359,173 +389,242 @@ __global__ void __launch_bounds__(NTHREADS, 1) jac_dmma_kernel(const DmmaArgs g)
     const int warp_n = warp & 1;      // column half: NJ fragments of 8 columns
     const int g4 = lane >> 2, t4 = lane & 3;
 
-    double acc[4][NJ][2];
-    int it = 0;
-    for (int ot = 0; ot < nOt; ++ot) {
+    // Assemble G_p of work item j from its running sums, symmetrise, store the item's patches of J.  Every
+    // consumer thread owns the same share of the index space whenever it gets here: no CTA-wide barrier, only
+    // "all eight warps have added their last column tile" (nsDone).
+    auto assemble = [&](int j, int tile) {
+        const int tbj = j % TABS, nbj = j % NSBUF;
+        mbar_wait(nsDone0 + 8 * nbj, (j / NSBUF) & 1);
+        const unsigned char *tab = tabs + tbj * ITEM_TAB_BYTES;
+        const long long *qrow = reinterpret_cast<const long long *>(tab + TT_QROW);
+        const int *trow = reinterpret_cast<const int *>(tab + TT_TROW);
+        const unsigned char *partner = tab + TT_PARTNER, *selfi = tab + TT_SELF;
+        const unsigned char *ctab = tab + TILE_TAB_BYTES;
+        const int *cp = reinterpret_cast<const int *>(ctab + CT_CP);
+        const unsigned char *cent = ctab + CT_CENT;
+        const double *Ns0 = Ns + nbj * NS_DOUBLES, *Ns1 = Ns0 + 128 * NSTRIDE;
+        // patch 1: rows of the tile x perturbations of the component
+        for (int idx = tid; idx < MAXP * AT * RF; idx += NCONS) {
+            const int pl = idx / (AT * RF), rem = idx % (AT * RF);
+            const int a_slot = rem / RF, jj = rem % RF;
+            const int p = cp[pl];
+            if (p < g.colBegin || p >= g.colEnd) continue;
+            const int self = selfi[a_slot];
+            const int a_loc = self & 15, rf = self >> 4;
+            if (trow[a_slot] < 0 || jj >= rf) continue;
+            const int b_slot = partner[a_slot * RF + jj];
+            double gab = 0.0, gba = 0.0;
 #pragma unroll
-        for (int mi = 0; mi < 4; ++mi)
-#pragma unroll
-            for (int nj = 0; nj < NJ; ++nj) { acc[mi][nj][0] = 0.0; acc[mi][nj][1] = 0.0; }
-
-        for (int kc = 0; kc < nKc; ++kc, ++it) {
-            const int s = it % STAGES;
-            mbar_wait(smem_u32(&bars[s]), (it / STAGES) & 1);
-            const double *Ws = stageBase + (size_t)s * STAGE_DOUBLES;
-            const double *PVs = Ws + W_STAGE;
-            const double *CVs = PVs + PV_STAGE + warp_m * KC;
-#pragma unroll
-            for (int k4 = 0; k4 < KC / 4; ++k4) {
-                const double2 p01 = *reinterpret_cast<const double2 *>(PVs + ((k4 * 2 + 0) * 32 + lane) * 2);
-                const double2 p23 = *reinterpret_cast<const double2 *>(PVs + ((k4 * 2 + 1) * 32 + lane) * 2);
-                const double cv = CVs[k4 * 4 + t4];
-                double a[4], b[NJ];
-                a[0] = p01.x * cv; a[1] = p01.y * cv; a[2] = p23.x * cv; a[3] = p23.y * cv;
-#pragma unroll
-                for (int j = 0; j < NJ / 2; ++j) {
-                    const double2 bb = *reinterpret_cast<const double2 *>(
-                        Ws + ((k4 * NJ + warp_n * (NJ / 2) + j) * 32 + lane) * 2);
-                    b[2 * j] = bb.x; b[2 * j + 1] = bb.y;
-                }
-#pragma unroll
-                for (int mi = 0; mi < 4; ++mi)
-#pragma unroll
-                    for (int nj = 0; nj < NJ; ++nj) dmma884(acc[mi][nj][0], acc[mi][nj][1], a[mi], b[nj]);
+            for (int e = 0; e < MAXE; ++e) {
+                const unsigned char ent = cent[pl * MAXE + e];
+                if (ent == 0xFF) continue;
+                const int rs = ent & 15, cs = ent >> 4;
+                const int i1 = (rs * AT + a_slot) * NSTRIDE + cs * RF + jj;
+                const int i2 = (rs * AT + b_slot) * NSTRIDE + cs * RF + a_loc;
+                gab += Ns0[i1] + Ns1[i1];
+                gba += Ns0[i2] + Ns1[i2];
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(&bars[STAGES + s]));
+            const size_t off = (size_t)g.Q * (p - g.colBegin) + qrow[a_slot] + (long long)rf * jj;
+            const double val = 2.0 * (gab + gba);
+            for (int dst = 0; dst < g.nDest; ++dst) g.J[dst][off] = val;
         }
-
-        if constexpr (PANEL) {
-            // ---- panel mode: store this tile of M_r[a, o] (fragments too large for the on-chip epilogue)
-            double *mbase = g.Mout + (size_t)(comp * RT + warp_m) * g.mRows * g.ldm;
+        // patch 2 (symmetric mode, off-diagonal block pairs): rows of the component's own fragment x
+        // perturbations of the blocks in the tile, from M_a[r,o] = M_r[a,o]:
+        //   G_p'[r,c] = sum_{(a,b') in p'} N_r[a; c, b']
+        if (g.sym && *reinterpret_cast<const int *>(ctab + CT_TILE) != tile) {
+            const long long q0 = *reinterpret_cast<const long long *>(ctab + CT_Q);
+            const unsigned char *loc = ctab + CT_LOC;
+            const int *tp = reinterpret_cast<const int *>(tab + TT_TP);
+            const unsigned char *te = tab + TT_TE;
+            for (int idx = tid; idx < TP * RT * RT; idx += NCONS) {
+                const int pp = idx / (RT * RT), rem = idx % (RT * RT);
+                const int cs = rem / RT, rs = rem % RT;          // site slots of the component: row r, column c
+                const int p = tp[pp];
+                if (p < g.colBegin || p >= g.colEnd) continue;
+                const int lr = loc[rs], lc = loc[cs];
+                if (lr == 0xFF || lc == 0xFF) continue;
+                const int rf = lr >> 4;
+                double grc = 0.0, gcr = 0.0;
 #pragma unroll
-            for (int mi = 0; mi < 4; ++mi) {
-                const int row = trow[mi * 8 + g4];
-                if (row < 0) continue;
-#pragma unroll
-                for (int nj = 0; nj < NJ; ++nj) {
-                    const int o = ot * BN + warp_n * (BN / 2) + nj * 8 + t4 * 2;
-                    if (o < g.ldm)
-                        *reinterpret_cast<double2 *>(mbase + (size_t)row * g.ldm + o) =
-                            make_double2(acc[mi][nj][0], acc[mi][nj][1]);
+                for (int e = 0; e < MAXE; ++e) {
+                    const unsigned char ent = te[pp * MAXE + e];
+                    if (ent == 0xFF) continue;
+                    const int a_slot = ent & 31, jj = ent >> 5;
+                    const int i1 = (rs * AT + a_slot) * NSTRIDE + cs * RF + jj;
+                    const int i2 = (cs * AT + a_slot) * NSTRIDE + rs * RF + jj;
+                    grc += Ns0[i1] + Ns1[i1];
+                    gcr += Ns0[i2] + Ns1[i2];
                 }
-            }
-            continue;
-        }
-        // ---- epilogue for this column tile (per warp, no CTA-wide barrier)
-        mbar_wait(epiFull, ot & 1);
-#pragma unroll
-        for (int mi = 0; mi < 4; ++mi) {
-            const int a_slot = mi * 8 + g4;
-            const double *pc = CoS + warp_n * (BN / 2) + t4 * 2;
-            double *nsrow = Ns + (warp_n * 128 + warp_m * AT + a_slot) * NSTRIDE + t4 * RF;
-#pragma unroll
-            for (int jh = 0; jh < RF / 4; ++jh) {            // partners in groups of 4 (register budget)
-                const double *pb[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    pb[j] = POS + (int)partner[a_slot * RF + jh * 4 + j] * PSTRIDE + warp_n * (BN / 2) + t4 * 2;
-                double nacc[RT][4];
-#pragma unroll
-                for (int c = 0; c < RT; ++c)
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) nacc[c][j] = 0.0;
-#pragma unroll
-                for (int nj = 0; nj < NJ; ++nj) {
-                    double2 po[4];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) po[j] = *reinterpret_cast<const double2 *>(pb[j] + nj * 8);
-                    const double m0 = acc[mi][nj][0], m1 = acc[mi][nj][1];
-#pragma unroll
-                    for (int c = 0; c < RT; ++c) {
-                        const double2 co = *reinterpret_cast<const double2 *>(pc + c * BN + nj * 8);
-                        const double t0 = m0 * co.x, t1 = m1 * co.y;
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) nacc[c][j] = fma(t0, po[j].x, fma(t1, po[j].y, nacc[c][j]));
-                    }
-                }
-                // reduce over the 4 lanes that share this row; lane t4 keeps the sums of site slot c == t4
-                double keep[4];
-#pragma unroll
-                for (int c = 0; c < RT; ++c)
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        double v = nacc[c][j];
-                        v += __shfl_xor_sync(0xffffffffu, v, 1);
-                        v += __shfl_xor_sync(0xffffffffu, v, 2);
-                        if (t4 == c) keep[j] = v;
-                    }
-                double2 *dst = reinterpret_cast<double2 *>(nsrow + jh * 4);
-                double2 s01 = dst[0], s23 = dst[1];
-                s01.x += keep[0]; s01.y += keep[1]; s23.x += keep[2]; s23.y += keep[3];
-                dst[0] = s01; dst[1] = s23;
+                const size_t off = (size_t)g.Q * (p - g.colBegin) + q0 + (lr & 15) + (long long)rf * (lc & 15);
+                const double val = 2.0 * (grc + gcr);
+                for (int dst = 0; dst < g.nDest; ++dst) g.J[dst][off] = val;
             }
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(epiEmpty);
-    }
+        if (lane == 0) {
+            mbar_arrive(nsFree0 + 8 * nbj);          // this warp no longer reads the running sums of item j
+            mbar_arrive(tabEmpty0 + 8 * tbj);        // ... nor its tables
+        }
+    };
 
-    if constexpr (PANEL) return;
-    // ---- assemble G_p, symmetrise, store the CTA's patches of J
-    consumer_sync();
-    const double *Ns1 = Ns + 128 * NSTRIDE;
-    // patch 1: rows of the tile x perturbations of the component
-    for (int idx = tid; idx < MAXP * AT * RF; idx += NCONS) {
-        const int pl = idx / (AT * RF), rem = idx % (AT * RF);
-        const int a_slot = rem / RF, j = rem % RF;
-        const int p = cp[pl];
-        if (p < g.colBegin || p >= g.colEnd) continue;
-        const int self = selfi[a_slot];
-        const int a_loc = self & 15, rf = self >> 4;
-        if (trow[a_slot] < 0 || j >= rf) continue;
-        const int b_slot = partner[a_slot * RF + j];
-        double gab = 0.0, gba = 0.0;
+    // Stagger the two consumer warps of every SM sub-partition (warps w and w + 4): warps 4-7 start g.lead stages
+    // after warps 0-3 and keep that distance (the ring is deep enough), so one warp of the pair is in the DMMA main
+    // loop while the other one runs its latency-bound epilogue.  Paid once per CTA: the kernel is persistent.
+    int toLead = (warp < 4 && g.lead > 0) ? g.lead : -1;    // stages until warps 0-3 release warps 4-7
+    if (warp >= 4 && g.lead > 0) mbar_wait(leadBar, 0);
+
+    long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long tPrev = PROF ? clock64() : 0;
+    auto lap = [&](int slot) {
+        if constexpr (PROF) { const long long t = clock64(); pc[slot] += t - tPrev; tPrev = t; }
+    };
+    double acc[4][NJ][2];
+    int rs = 0, rph = 0, T = 0, k = 0, prevTile = 0;
+    for (int w = blockIdx.x; w < nWork; w += gridDim.x, ++k) {
+        const int2 wk = g.work[w];
+        const int tb = k % TABS, nb = k % NSBUF;
+        const unsigned char *tab = tabs + tb * ITEM_TAB_BYTES;
+        double *NsK = Ns + nb * NS_DOUBLES;
+        for (int ot = 0; ot < nOt; ++ot, ++T) {
 #pragma unroll
-        for (int e = 0; e < MAXE; ++e) {
-            const unsigned char ent = cent[pl * MAXE + e];
-            if (ent == 0xFF) continue;
-            const int rs = ent & 15, cs = ent >> 4;
-            const int i1 = (rs * AT + a_slot) * NSTRIDE + cs * RF + j;
-            const int i2 = (rs * AT + b_slot) * NSTRIDE + cs * RF + a_loc;
-            gab += Ns[i1] + Ns1[i1];
-            gba += Ns[i2] + Ns1[i2];
-        }
-        const size_t off = (size_t)g.Q * (p - g.colBegin) + qrow[a_slot] + (long long)rf * j;
-        const double val = 2.0 * (gab + gba);
-        for (int dst = 0; dst < g.nDest; ++dst) g.J[dst][off] = val;
-    }
-    // patch 2 (symmetric mode, off-diagonal block pairs): rows of the component's own fragment x
-    // perturbations of the blocks in the tile, from M_a[r,o] = M_r[a,o]:
-    //   G_p'[r,c] = sum_{(a,b') in p'} N_r[a; c, b']
-    if (g.sym && g.compTile[comp] != tile) {
-        const long long q0 = g.compQ[comp];
-        const unsigned char *loc = g.compLoc + comp * RT;
-        const int *tp = g.tileP + (size_t)tile * TP;
-        const unsigned char *te = g.tileEnt + (size_t)tile * TP * MAXE;
-        for (int idx = tid; idx < TP * RT * RT; idx += NCONS) {
-            const int pp = idx / (RT * RT), rem = idx % (RT * RT);
-            const int cs = rem / RT, rs = rem % RT;          // site slots of the component: row r, column c
-            const int p = tp[pp];
-            if (p < g.colBegin || p >= g.colEnd) continue;
-            const int lr = loc[rs], lc = loc[cs];
-            if (lr == 0xFF || lc == 0xFF) continue;
-            const int rf = lr >> 4;
-            double grc = 0.0, gcr = 0.0;
+            for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
-            for (int e = 0; e < MAXE; ++e) {
-                const unsigned char ent = te[pp * MAXE + e];
-                if (ent == 0xFF) continue;
-                const int a_slot = ent & 31, j = ent >> 5;
-                const int i1 = (rs * AT + a_slot) * NSTRIDE + cs * RF + j;
-                const int i2 = (cs * AT + a_slot) * NSTRIDE + rs * RF + j;
-                grc += Ns[i1] + Ns1[i1];
-                gcr += Ns[i2] + Ns1[i2];
+                for (int nj = 0; nj < NJ; ++nj) { acc[mi][nj][0] = 0.0; acc[mi][nj][1] = 0.0; }
+
+            for (int kc = 0; kc < nKc; ++kc) {
+                lap(7);
+                mbar_wait(barBase + 8 * rs, rph);
+                lap(0);
+                const double *Ws = stageBase + (size_t)rs * STAGE_DOUBLES;
+                const double *PVs = Ws + W_STAGE;
+                const double *CVs = PVs + PV_STAGE + warp_m * KC;
+#pragma unroll
+                for (int k4 = 0; k4 < KC / 4; ++k4) {
+                    const double2 p01 = *reinterpret_cast<const double2 *>(PVs + ((k4 * 2 + 0) * 32 + lane) * 2);
+                    const double2 p23 = *reinterpret_cast<const double2 *>(PVs + ((k4 * 2 + 1) * 32 + lane) * 2);
+                    const double cv = CVs[k4 * 4 + t4];
+                    double a[4], b[NJ];
+                    a[0] = p01.x * cv; a[1] = p01.y * cv; a[2] = p23.x * cv; a[3] = p23.y * cv;
+#pragma unroll
+                    for (int j = 0; j < NJ / 2; ++j) {
+                        const double2 bb = *reinterpret_cast<const double2 *>(
+                            Ws + ((k4 * NJ + warp_n * (NJ / 2) + j) * 32 + lane) * 2);
+                        b[2 * j] = bb.x; b[2 * j + 1] = bb.y;
+                    }
+#pragma unroll
+                    for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+                        for (int nj = 0; nj < NJ; ++nj) dmma884(acc[mi][nj][0], acc[mi][nj][1], a[mi], b[nj]);
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(barBase + 8 * (STAGES + rs));
+                if (++rs == STAGES) { rs = 0; rph ^= 1; }
+                if (toLead > 0 && --toLead == 0 && lane == 0) mbar_arrive(leadBar);
+                lap(1);
             }
-            const size_t off = (size_t)g.Q * (p - g.colBegin) + q0 + (lr & 15) + (long long)rf * (lc & 15);
-            const double val = 2.0 * (grc + gcr);
-            for (int dst = 0; dst < g.nDest; ++dst) g.J[dst][off] = val;
+
+            if constexpr (PANEL) {
+                // ---- panel mode: store this tile of M_r[a, o] (fragments too large for the on-chip epilogue)
+                if (ot == 0) mbar_wait(tabFull0 + 8 * tb, (k / TABS) & 1);
+                const int *trow = reinterpret_cast<const int *>(tab + TT_TROW);
+                double *mbase = g.Mout + (size_t)(wk.x * RT + warp_m) * g.mRows * g.ldm;
+#pragma unroll
+                for (int mi = 0; mi < 4; ++mi) {
+                    const int row = trow[mi * 8 + g4];
+                    if (row < 0) continue;
+#pragma unroll
+                    for (int nj = 0; nj < NJ; ++nj) {
+                        const int o = ot * BN + warp_n * (BN / 2) + nj * 8 + t4 * 2;
+                        if (o < g.ldm)
+                            *reinterpret_cast<double2 *>(mbase + (size_t)row * g.ldm + o) =
+                                make_double2(acc[mi][nj][0], acc[mi][nj][1]);
+                    }
+                }
+                continue;
+            }
+            // ---- epilogue for this column tile (per warp, no CTA-wide barrier)
+            if (ot == 0) {
+                mbar_wait(tabFull0 + 8 * tb, (k / TABS) & 1);                  // tables of this item
+                mbar_wait(nsFree0 + 8 * nb, ((k / NSBUF) & 1) ^ 1);            // every warp has assembled the buffer's last item
+            }
+            mbar_wait(epiFull, T & 1);
+            lap(2);
+            const unsigned char *partner = tab + TT_PARTNER;
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi) {
+                const int a_slot = mi * 8 + g4;
+                const double *pc = CoS + warp_n * (BN / 2) + t4 * 2;
+                double *nsrow = NsK + (warp_n * 128 + warp_m * AT + a_slot) * NSTRIDE + t4 * RF;
+#pragma unroll
+                for (int jh = 0; jh < RF / 4; ++jh) {            // partners in groups of 4 (register budget)
+                    const double *pb[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        pb[j] = POS + (int)partner[a_slot * RF + jh * 4 + j] * PSTRIDE + warp_n * (BN / 2) + t4 * 2;
+                    double nacc[RT][4];
+#pragma unroll
+                    for (int c = 0; c < RT; ++c)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) nacc[c][j] = 0.0;
+#pragma unroll
+                    for (int nj = 0; nj < NJ; ++nj) {
+                        double2 po[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) po[j] = *reinterpret_cast<const double2 *>(pb[j] + nj * 8);
+                        const double m0 = acc[mi][nj][0], m1 = acc[mi][nj][1];
+#pragma unroll
+                        for (int c = 0; c < RT; ++c) {
+                            const double2 co = *reinterpret_cast<const double2 *>(pc + c * BN + nj * 8);
+                            const double t0 = m0 * co.x, t1 = m1 * co.y;
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) nacc[c][j] = fma(t0, po[j].x, fma(t1, po[j].y, nacc[c][j]));
+                        }
+                    }
+                    // reduce over the 4 lanes that share this row; lane t4 ends up with the sums of site slot c == t4:
+                    // butterfly -- exchange the half the partner lane keeps, add the half this lane keeps
+                    double half[2][4], keep[4];
+#pragma unroll
+                    for (int cp2 = 0; cp2 < 2; ++cp2)              // site slots {0,1} -> bit 0, {2,3} -> bit 0
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const double mine = (t4 & 1) ? nacc[2 * cp2 + 1][j] : nacc[2 * cp2][j];
+                            const double send = (t4 & 1) ? nacc[2 * cp2][j] : nacc[2 * cp2 + 1][j];
+                            half[cp2][j] = mine + __shfl_xor_sync(0xffffffffu, send, 1);
+                        }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const double mine = (t4 & 2) ? half[1][j] : half[0][j];
+                        const double send = (t4 & 2) ? half[0][j] : half[1][j];
+                        keep[j] = mine + __shfl_xor_sync(0xffffffffu, send, 2);
+                    }
+                    double2 *dst = reinterpret_cast<double2 *>(nsrow + jh * 4);
+                    double2 s01 = make_double2(0.0, 0.0), s23 = make_double2(0.0, 0.0);
+                    if (ot > 0) { s01 = dst[0]; s23 = dst[1]; }      // the first column tile of an item starts the sums
+                    s01.x += keep[0]; s01.y += keep[1]; s23.x += keep[2]; s23.y += keep[3];
+                    dst[0] = s01; dst[1] = s23;
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(epiEmpty);
+            lap(3);
+            if (NSBUF == 2 && ot == 0 && k > 0) { assemble(k - 1, prevTile); lap(4); }   // acc is dead here: no register pressure
         }
+        if constexpr (PANEL) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tabEmpty0 + 8 * tb);
+            continue;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(nsDone0 + 8 * nb);       // this warp has added its last column tile of item k
+        if (NSBUF == 1) { assemble(k, wk.y); lap(4); }
+        prevTile = wk.y;
     }
+    if (toLead > 0 && lane == 0) mbar_arrive(leadBar);       // fewer stages than the lead: release warps 4-7 now
+    if constexpr (!PANEL)
+        if (NSBUF == 2 && k > 0) { assemble(k - 1, prevTile); lap(4); }
+    if constexpr (PROF)
+        if (lane == 0 && g.prof)
+            for (int i = 0; i < 8; ++i) g.prof[((size_t)blockIdx.x * 8 + warp) * 8 + i] = pc[i];
 }
 
 }  // namespace
@@ -561,12 +660,12 @@ struct DmmaPlanData {
     int launchBegin = -1, launchEnd = -1, launchRank = -1, launchRanks = -1;
     bool launchSym = false;
     double launchFlops = 0.0;
-    int *d_compSites = nullptr, *d_compP = nullptr, *d_tileRow = nullptr, *d_compTile = nullptr, *d_tileP = nullptr;
+    std::vector<unsigned char> tileTab, compTab;    // item tables in the kernel's blob layout (pack_item_tables)
+    int *d_compSites = nullptr, *d_tileRow = nullptr;
+    unsigned char *d_tileTab = nullptr, *d_compTab = nullptr;
+    int numSMs = 0;                     // persistent grid: one CTA per SM of the plan's device
     int2 *d_work = nullptr;
     size_t workCapacity = 0;
-    unsigned char *d_compEnt = nullptr, *d_tilePartner = nullptr, *d_tileSelf = nullptr, *d_compLoc = nullptr,
-                  *d_tileEnt = nullptr;
-    long long *d_tileQ = nullptr, *d_compQ = nullptr;
     double *d_Wt = nullptr, *d_PVt = nullptr, *d_CVt = nullptr, *d_POt = nullptr, *d_COt = nullptr;
     bool attrSet = false;
 };
@@ -790,6 +889,62 @@ Schedule build_schedule(int N, int no, int Porig, int F, const int *h1start0, co
     return sc;
 }
 
+// Item tables in the layout the kernel copies into shared memory (TT_* / CT_* offsets).  Tables a schedule does not
+// have (panel mode: no perturbations, no symmetric mode) keep their "none" defaults.
+void pack_item_tables(DmmaPlanData &d)
+{
+    const int RF = d.rf;
+    d.tileTab.assign((size_t)d.nTiles * TILE_TAB_BYTES, 0);
+    for (int t = 0; t < d.nTiles; ++t) {
+        unsigned char *b = d.tileTab.data() + (size_t)t * TILE_TAB_BYTES;
+        long long *qrow = reinterpret_cast<long long *>(b + TT_QROW);
+        int *trow = reinterpret_cast<int *>(b + TT_TROW), *tp = reinterpret_cast<int *>(b + TT_TP);
+        for (int a = 0; a < AT; ++a) {
+            qrow[a] = d.tileQ.empty() ? 0 : d.tileQ[(size_t)t * AT + a];
+            trow[a] = d.tileRow[(size_t)t * AT + a];
+            b[TT_SELF + a] = d.tileSelf.empty() ? 0 : d.tileSelf[(size_t)t * AT + a];
+            for (int j = 0; j < RF; ++j)
+                b[TT_PARTNER + a * RF + j] = d.tilePartner.empty() ? (unsigned char)AT : d.tilePartner[((size_t)t * AT + a) * RF + j];
+        }
+        for (int k = 0; k < TP; ++k) {
+            tp[k] = d.tileP.empty() ? -1 : d.tileP[(size_t)t * TP + k];
+            for (int e = 0; e < MAXE; ++e)
+                b[TT_TE + k * MAXE + e] = d.tileEnt.empty() ? 0xFF : d.tileEnt[((size_t)t * TP + k) * MAXE + e];
+        }
+    }
+    d.compTab.assign((size_t)d.nComp * COMP_TAB_BYTES, 0);
+    for (int c = 0; c < d.nComp; ++c) {
+        unsigned char *b = d.compTab.data() + (size_t)c * COMP_TAB_BYTES;
+        *reinterpret_cast<long long *>(b + CT_Q) = d.compQ.empty() ? 0 : d.compQ[c];
+        *reinterpret_cast<int *>(b + CT_TILE) = d.compTile.empty() ? -1 : d.compTile[c];
+        int *cp = reinterpret_cast<int *>(b + CT_CP);
+        for (int r = 0; r < RT; ++r) b[CT_LOC + r] = d.compLoc.empty() ? 0xFF : d.compLoc[(size_t)c * RT + r];
+        for (int k = 0; k < MAXP; ++k) {
+            cp[k] = d.compP.empty() ? -1 : d.compP[(size_t)c * MAXP + k];
+            for (int e = 0; e < MAXE; ++e)
+                b[CT_CENT + k * MAXE + e] = d.compEnt.empty() ? 0xFF : d.compEnt[((size_t)c * MAXP + k) * MAXE + e];
+        }
+    }
+}
+
+int query_sms(DmmaPlanData &d)
+{
+    int dev = 0, sms = 0;
+    QC_CUDA(cudaGetDevice(&dev));
+    QC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    d.numSMs = sms > 0 ? sms : 1;
+    return QCDMET_OK;
+}
+
+// Stages by which warps 0-3 lead warps 4-7: about (epilogue time) / (time one warp alone needs for a stage, 64 NJ
+// cycles of the DMMA pipe), at most ring depth - 1.  $QCDMET_B200_LEAD overrides (tuning; 0 = start together).
+int consumer_lead(int stages, int nj)
+{
+    int lead = nj >= 8 ? 3 : nj >= 6 ? 4 : 6;
+    if (const char *env = getenv("QCDMET_B200_LEAD")) lead = atoi(env);
+    return std::max(0, std::min(lead, stages - 1));
+}
+
 template <typename T>
 int upload(T **dst, const std::vector<T> &src)
 {
@@ -820,13 +975,10 @@ int dmma_plan_build(DmmaPlanData **out, int N, int no, int P, int F, const int *
     Schedule sc = build_schedule(N, no, P, F, h1start, h1row, h1col, rowStart, rowIdx);
     QC_CHECK(sc.ok, QCDMET_E_ARG, "DMMA kernel not eligible: %s", sc.why.c_str());
     DmmaPlanData *d = new DmmaPlanData(std::move(sc.d));
+    pack_item_tables(*d);
     int rc = QCDMET_OK;
-    if ((rc = upload(&d->d_compSites, d->compSites)) || (rc = upload(&d->d_compP, d->compP)) ||
-        (rc = upload(&d->d_compEnt, d->compEnt)) || (rc = upload(&d->d_tileRow, d->tileRow)) ||
-        (rc = upload(&d->d_tilePartner, d->tilePartner)) || (rc = upload(&d->d_tileSelf, d->tileSelf)) ||
-        (rc = upload(&d->d_tileQ, d->tileQ)) || (rc = upload(&d->d_compTile, d->compTile)) ||
-        (rc = upload(&d->d_compQ, d->compQ)) || (rc = upload(&d->d_compLoc, d->compLoc)) ||
-        (rc = upload(&d->d_tileP, d->tileP)) || (rc = upload(&d->d_tileEnt, d->tileEnt)) ||
+    if ((rc = query_sms(*d)) || (rc = upload(&d->d_compSites, d->compSites)) || (rc = upload(&d->d_tileRow, d->tileRow)) ||
+        (rc = upload(&d->d_tileTab, d->tileTab)) || (rc = upload(&d->d_compTab, d->compTab)) ||
         (rc = upload(&d->d_subStart, d->subStart))) {
         dmma_plan_free(d);
         return rc;
@@ -849,9 +1001,7 @@ int dmma_plan_build(DmmaPlanData **out, int N, int no, int P, int F, const int *
 void dmma_plan_free(DmmaPlanData *d)
 {
     if (!d) return;
-    cudaFree(d->d_compSites); cudaFree(d->d_compP); cudaFree(d->d_compEnt); cudaFree(d->d_tileRow);
-    cudaFree(d->d_tilePartner); cudaFree(d->d_tileSelf); cudaFree(d->d_tileQ); cudaFree(d->d_work);
-    cudaFree(d->d_compTile); cudaFree(d->d_compQ); cudaFree(d->d_compLoc); cudaFree(d->d_tileP); cudaFree(d->d_tileEnt);
+    cudaFree(d->d_compSites); cudaFree(d->d_tileRow); cudaFree(d->d_tileTab); cudaFree(d->d_compTab); cudaFree(d->d_work);
     cudaFree(d->d_Wt); cudaFree(d->d_PVt); cudaFree(d->d_CVt); cudaFree(d->d_POt); cudaFree(d->d_COt);
     cudaFree(d->d_emptyCols); cudaFree(d->d_subStart); cudaFree(d->d_Jsub);
     cudaGetLastError();
@@ -986,16 +1136,23 @@ int launch_jacobian_dmma(DmmaPlanData *d, const JacView &v, cudaStream_t st, int
         a.nKc = d->nKc; a.nOt = d->nOt;
         a.colBegin = cb; a.colEnd = ce; a.sym = d->launchSym ? 1 : 0; a.Q = v.Q;
         a.Wt = d->d_Wt; a.PVt = d->d_PVt; a.CVt = d->d_CVt; a.POt = d->d_POt; a.COt = d->d_COt;
-        a.work = d->d_work; a.compTile = d->d_compTile; a.compQ = d->d_compQ; a.compLoc = d->d_compLoc;
-        a.tileP = d->d_tileP; a.tileEnt = d->d_tileEnt;
-        a.compSites = d->d_compSites; a.compP = d->d_compP;
-        a.compEnt = d->d_compEnt; a.tileRow = d->d_tileRow; a.tilePartner = d->d_tilePartner;
-        a.tileSelf = d->d_tileSelf; a.tileQ = d->d_tileQ;
+        a.work = d->d_work; a.nWork = (int)d->work.size();
+        a.tileTab = d->d_tileTab; a.compTab = d->d_compTab;
         a.Mout = nullptr; a.mRows = 0; a.ldm = 0;
         a.nDest = z.nDest;
         for (int r = 0; r < QCDMET_MAX_PEERS; ++r) a.J[r] = z.J[r];
+        // tuning aid: $QCDMET_B200_PROFILE=<file> runs the instrumented instantiation and appends the per-phase cycle
+        // counts of the consumer warps (averages over CTAs) to <file>; never set in production or in the bench
+        const char *profPath = getenv("QCDMET_B200_PROFILE");
+        const unsigned gridForProf = (unsigned)std::min<size_t>(d->work.size(), (size_t)d->numSMs);
+        a.prof = nullptr;
+        if (profPath && d->rf == 4 && d->nj >= 6) {
+            QC_CUDA(cudaMalloc((void **)&a.prof, (size_t)gridForProf * 64 * sizeof(long long)));
+            QC_CUDA(cudaMemsetAsync(a.prof, 0, (size_t)gridForProf * 64 * sizeof(long long), st));
+        }
         if (ev0) QC_CUDA(cudaEventRecord(ev0, st));
-        const unsigned grid = (unsigned)d->work.size();
+        // persistent CTAs, one per SM: CTA b executes items b, b + grid, ... (equal-cost items)
+        const unsigned grid = (unsigned)std::min<size_t>(d->work.size(), (size_t)d->numSMs);
         int rc = QCDMET_E_STATE;
 #define QC_LAUNCH_VARIANT(RFV, NJV)                                                                           \
         if (d->rf == RFV && d->nj == NJV) {                                                                   \
@@ -1005,7 +1162,13 @@ int launch_jacobian_dmma(DmmaPlanData *d, const JacView &v, cudaStream_t st, int
                                              K::SMEM_BYTES));                                                 \
                 d->attrSet = true;                                                                            \
             }                                                                                                 \
-            jac_dmma_kernel<K><<<grid, NTHREADS, K::SMEM_BYTES, st>>>(a);                                     \
+            a.lead = consumer_lead(K::STAGES, NJV);                                                           \
+            if (profPath && RFV == 4 && NJV >= 6) {                                                           \
+                QC_CUDA(cudaFuncSetAttribute(jac_dmma_kernel<Cfg<4, (NJV >= 6 ? NJV : 6)>, false, true>,      \
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM_BYTES));    \
+                jac_dmma_kernel<Cfg<4, (NJV >= 6 ? NJV : 6)>, false, true><<<grid, NTHREADS, K::SMEM_BYTES, st>>>(a); \
+            } else                                                                                            \
+                jac_dmma_kernel<K><<<grid, NTHREADS, K::SMEM_BYTES, st>>>(a);                                 \
             rc = QCDMET_OK;                                                                                   \
         }
         QC_LAUNCH_VARIANT(4, 8) QC_LAUNCH_VARIANT(4, 6) QC_LAUNCH_VARIANT(4, 4)
@@ -1014,6 +1177,29 @@ int launch_jacobian_dmma(DmmaPlanData *d, const JacView &v, cudaStream_t st, int
         QC_CHECK(rc == QCDMET_OK, QCDMET_E_STATE, "no DMMA kernel variant for rf=%d nj=%d", d->rf, d->nj);
         QC_CUDA(cudaGetLastError());
         if (ev1) QC_CUDA(cudaEventRecord(ev1, st));
+        if (a.prof) {
+            std::vector<long long> h((size_t)gridForProf * 64);
+            QC_CUDA(cudaMemcpyAsync(h.data(), a.prof, h.size() * sizeof(long long), cudaMemcpyDeviceToHost, st));
+            QC_CUDA(cudaStreamSynchronize(st));
+            cudaFree(a.prof);
+            if (FILE *fp = fopen(profPath, "a")) {
+                static const char *names[8] = {"wait_full", "stage_body", "wait_epi", "epilogue", "assembly", "-", "-", "loop_overhead"};
+                fprintf(fp, "items %zu ctas %u nKc %d nOt %d nj %d lead %d\n", d->work.size(), gridForProf, d->nKc, d->nOt, d->nj, a.lead);
+                for (int grp = 0; grp < 2; ++grp) {
+                    double sum[8] = {0};
+                    for (unsigned b = 0; b < gridForProf; ++b)
+                        for (int wq = 4 * grp; wq < 4 * grp + 4; ++wq)
+                            for (int i = 0; i < 8; ++i) sum[i] += (double)h[((size_t)b * 8 + wq) * 8 + i];
+                    double tot = 0;
+                    for (int i = 0; i < 8; ++i) tot += sum[i];
+                    fprintf(fp, "  warps %d-%d: total %.0f cycles/warp;", 4 * grp, 4 * grp + 3, tot / (4.0 * gridForProf));
+                    for (int i = 0; i < 8; ++i)
+                        if (names[i][0] != '-') fprintf(fp, " %s %.1f%%", names[i], 100.0 * sum[i] / tot);
+                    fprintf(fp, "\n");
+                }
+                fclose(fp);
+            }
+        }
         *launches += 1;
         *flops = d->launchFlops;
     }
@@ -1147,10 +1333,10 @@ int fact_plan_build(FactPlanData **out, int N, int no, int P, int F, const int *
     d.nOt = (d.no + d.bn() - 1) / d.bn();
     f->mDoubles = (size_t)d.nComp * RT * S * ldo;
     int rc = QCDMET_OK;
-    if ((rc = upload(&d.d_compSites, d.compSites)) || (rc = upload(&d.d_compP, d.compP)) ||
-        (rc = upload(&d.d_compEnt, d.compEnt)) || (rc = upload(&d.d_tileRow, d.tileRow)) ||
-        (rc = upload(&d.d_tilePartner, d.tilePartner)) || (rc = upload(&d.d_tileSelf, d.tileSelf)) ||
-        (rc = upload(&d.d_tileQ, d.tileQ)) || (rc = upload(&f->d_elU, f->elU)) ||
+    pack_item_tables(d);
+    if ((rc = query_sms(d)) || (rc = upload(&d.d_compSites, d.compSites)) || (rc = upload(&d.d_tileRow, d.tileRow)) ||
+        (rc = upload(&d.d_tileTab, d.tileTab)) || (rc = upload(&d.d_compTab, d.compTab)) ||
+        (rc = upload(&f->d_elU, f->elU)) ||
         (rc = contract_plan_build(&f->contract, F, rowStart))) {
         fact_plan_free(f);
         return rc;
@@ -1179,8 +1365,7 @@ void fact_plan_free(FactPlanData *f)
 {
     if (!f) return;
     DmmaPlanData &d = f->sched;
-    cudaFree(d.d_compSites); cudaFree(d.d_compP); cudaFree(d.d_compEnt); cudaFree(d.d_tileRow);
-    cudaFree(d.d_tilePartner); cudaFree(d.d_tileSelf); cudaFree(d.d_tileQ); cudaFree(d.d_work);
+    cudaFree(d.d_compSites); cudaFree(d.d_tileRow); cudaFree(d.d_tileTab); cudaFree(d.d_compTab); cudaFree(d.d_work);
     cudaFree(d.d_Wt); cudaFree(d.d_PVt); cudaFree(d.d_CVt);
     cudaFree(f->d_elU); cudaFree(f->d_M);
     cudaGetLastError();
@@ -1225,12 +1410,13 @@ int launch_jacobian_factorised(FactPlanData *f, const JacView &v, long long nnzI
         memset(&a, 0, sizeof(a));
         a.nKc = d->nKc; a.nOt = d->nOt;
         a.Wt = d->d_Wt; a.PVt = d->d_PVt; a.CVt = d->d_CVt;
-        a.work = d->d_work;
-        a.compSites = d->d_compSites; a.compP = d->d_compP; a.compEnt = d->d_compEnt;
-        a.tileRow = d->d_tileRow; a.tilePartner = d->d_tilePartner; a.tileSelf = d->d_tileSelf; a.tileQ = d->d_tileQ;
+        a.work = d->d_work; a.nWork = (int)d->work.size();
+        a.tileTab = d->d_tileTab; a.compTab = d->d_compTab;
         a.Mout = f->d_M; a.mRows = v.S; a.ldm = v.ldo;
+        a.prof = nullptr;
         a.nDest = 0;
-        const unsigned grid = (unsigned)d->work.size();
+        a.lead = 0;                         // panel mode has no epilogue to hide
+        const unsigned grid = (unsigned)std::min<size_t>(d->work.size(), (size_t)d->numSMs);
         int rc = QCDMET_E_STATE;
         // per device (function attributes live in the context of the current device): set on every launch
 #define QC_LAUNCH_PANEL(NJV)                                                                                  \

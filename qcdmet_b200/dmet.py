@@ -58,6 +58,8 @@ class dmet:
             assert self.fitImpBath is False
             assert self.SCmethod in ('BFGS', 'NONE')
         self.solver = solver
+        self.bath_on_gpu = False          # doexact: baths of all fragments from one device call (helper.constructbaths)
+        self._bath_cache = None
         self.solver_threads = 1            # > 1: the embedded problems of one doexact pass are solved in a thread pool
         self.gpu_residual = True      # residual blocks from the device eigensolve shared with the Jacobian
         self.fit_on_gpu = False       # LSTSQ: Levenberg-Marquardt with the normal equations solved on the device
@@ -155,7 +157,19 @@ class dmet:
         SURVEY.md 8); the solver is any callable with the signature of src/chemps2.py:27 (default: the
         dense-FCI stand-in qcdmet_b200.fci_solver.solve).  The DET / CASCI / incomplete-tiling branches
         (src/dmet.py:259-337) need pyscf and are not restated."""
-        OneRDM = self.helper.construct1RDM_loc(self.doSCF, self.umat)
+        maxiter = 1 if self.TransInv else len(self.impClust)
+        device_baths = None
+        if self.bath_on_gpu:
+            # one eigensolve (shared with the residual / Jacobian at this umat) and one batched bath call per umat;
+            # the Newton iteration on the chemical potential re-enters doexact with the same umat
+            key = np.asarray(self.umat).tobytes()
+            if self._bath_cache is None or self._bath_cache[0] != key:
+                req = None if self.BATH_ORBS is None else [self.BATH_ORBS[c] for c in range(maxiter)]
+                self._bath_cache = (key, self.helper.constructbaths(self.umat, self.impClust[:maxiter], req,
+                                                                    cache_key=self._umat_key(self.square2flat(self.umat))))
+            OneRDM, device_baths = self._bath_cache[1]
+        else:
+            OneRDM = self.helper.construct1RDM_loc(self.doSCF, self.umat)
         self.energy = 0.0
         self.imp_1RDM = []
         self.dmetOrbs = []
@@ -163,26 +177,40 @@ class dmet:
         if solver is None:
             from . import fci_solver
             solver = fci_solver.solve
-        maxiter = 1 if self.TransInv else len(self.impClust)
         remainingOrbs = np.ones([len(self.impClust[0])], dtype=float)
         problems = []
         for counter in range(maxiter):
             impurityOrbs = np.abs(self.impClust[counter])
             numImpOrbs = int(np.sum(impurityOrbs))
             numBathOrbs = numImpOrbs if self.BATH_ORBS is None else self.BATH_ORBS[counter]
-            numBathOrbs, loc2dmet, core1RDM_dmet = self.helper.constructbath(OneRDM, impurityOrbs, numBathOrbs)
             core_cutoff = 0.01 if self.BATH_ORBS is None else 0.5
-            for cnt in range(len(core1RDM_dmet)):
-                if core1RDM_dmet[cnt] < core_cutoff:
-                    core1RDM_dmet[cnt] = 0.0
-                elif core1RDM_dmet[cnt] > 2.0 - core_cutoff:
-                    core1RDM_dmet[cnt] = 2.0
-                else:
+            if device_baths is not None:
+                # loc2dmet[:, :imp + bath] and the core density without the pure-environment orbitals: for an
+                # idempotent D/2, D_env,env = sum_bath occ_k b_k b_k^T + (core 1-RDM)
+                numBathOrbs, loc2dmet, cand_occ = device_baths[counter]
+                left = cand_occ[numBathOrbs:]
+                if np.any((left > core_cutoff) & (left < 2.0 - core_cutoff)):
                     raise AssertionError("Bad DMET bath orbital selection: bath orbital with occupation "
-                                         f"{core1RDM_dmet[cnt]} would go into the environment")
+                                         f"{left} would go into the environment")
+                env = np.flatnonzero(impurityOrbs == 0)
+                bath = loc2dmet[:, numImpOrbs:]
+                core1RDM_loc = np.zeros_like(OneRDM)
+                core1RDM_loc[np.ix_(env, env)] = (OneRDM - (bath * cand_occ[:numBathOrbs]) @ bath.T)[np.ix_(env, env)]
+                core_electrons = float(np.trace(core1RDM_loc))
+            else:
+                numBathOrbs, loc2dmet, core1RDM_dmet = self.helper.constructbath(OneRDM, impurityOrbs, numBathOrbs)
+                for cnt in range(len(core1RDM_dmet)):
+                    if core1RDM_dmet[cnt] < core_cutoff:
+                        core1RDM_dmet[cnt] = 0.0
+                    elif core1RDM_dmet[cnt] > 2.0 - core_cutoff:
+                        core1RDM_dmet[cnt] = 2.0
+                    else:
+                        raise AssertionError("Bad DMET bath orbital selection: bath orbital with occupation "
+                                             f"{core1RDM_dmet[cnt]} would go into the environment")
+                core1RDM_loc = np.dot(np.dot(loc2dmet, np.diag(core1RDM_dmet)), loc2dmet.T)
+                core_electrons = float(np.sum(core1RDM_dmet))
             Norb_in_imp = numImpOrbs + numBathOrbs
-            Nelec_in_imp = int(round(self.ints.Nelec - np.sum(core1RDM_dmet)))
-            core1RDM_loc = np.dot(np.dot(loc2dmet, np.diag(core1RDM_dmet)), loc2dmet.T)
+            Nelec_in_imp = int(round(self.ints.Nelec - core_electrons))
             self.dmetOrbs.append(loc2dmet[:, :Norb_in_imp])
             assert Norb_in_imp <= self.Norb
             dmetOEI = self.ints.dmet_oei(loc2dmet, Norb_in_imp)

@@ -104,6 +104,35 @@ class qcdmethelper:
         assert np.linalg.norm(loc2dmet.T @ loc2dmet - np.eye(ntot)) < 1e-12
         return (numBathOrbs, loc2dmet, coreOccupations)
 
+    def constructbaths(self, umat_loc, impurityOrbsList, numBathOrbsList=None, threshold=1e-13, cache_key=None,
+                       want_one_rdm=True):
+        """Baths of ALL fragments in one device call, from the orbitals of Fock + umat -- the
+        same eigensolve the residual and the Jacobian at this umat use.  Replaces the loop over
+        constructbath(construct1RDM_loc(doSCF, umat), impurityOrbs, numBathOrbs) of src/dmet.py:194-204, whose
+        numpy eigh of the (N - m) x (N - m) environment block per fragment becomes one m x m eigenproblem per
+        fragment and one DGEMM (kernels_bath.cu).
+
+        Returns (OneRDM or None, [(numBathOrbs, loc2dmet_active, bathOccupations), ...]) with
+        loc2dmet_active = loc2dmet[:, :numImpOrbs + numBathOrbs] of the reference (impurity | bath columns; the
+        pure-environment columns are never formed) and bathOccupations the environment occupations of ALL
+        m candidates in rank order (closest to 1 first, src/qcdmethelper.py:139-140)."""
+        imps = [np.flatnonzero(np.abs(np.asarray(v).reshape(-1)).astype(int)) for v in impurityOrbsList]
+        imp_start = np.concatenate([[0], np.cumsum([i.size for i in imps])]).astype(np.int32)
+        imp_idx = (np.concatenate(imps) if imps else np.zeros(0)).astype(np.int32)
+        # any plan of this helper has the orbitals: use (and create if needed) the impurity-row plan
+        plan = self._plan_with_orbitals(umat_loc, imp_start, None, imp_idx, None, cache_key)
+        req = None if numBathOrbsList is None else np.asarray(numBathOrbsList, dtype=np.int32)
+        num_bath, occ, bath = plan.construct_baths(imp_start, imp_idx, req, threshold)
+        n = self.locints.Norbs
+        out = []
+        for f, imp in enumerate(imps):
+            nb = int(num_bath[f])
+            active = np.zeros((n, imp.size + nb))
+            active[imp, np.arange(imp.size)] = 1.0
+            active[:, imp.size:] = bath[imp_start[f]:imp_start[f] + nb].T
+            out.append((nb, active, occ[imp_start[f]:imp_start[f + 1]].copy()))
+        return (plan.one_rdm() if want_one_rdm else None), out
+
     def _oei(self, doSCF, umat_loc, NOrotation):
         if doSCF:
             raise NotImplementedError("doSCF=True is outside the response hot path (src/dmet.py:44)")
@@ -164,7 +193,8 @@ class qcdmethelper:
             # cheap identity of (Fock + umat): e.g. the bytes of the flat parameter vector (dmet passes it), so
             # that large problems neither compare nor copy an N x N matrix per call
             key = ("key", cache_key, NOrotation is not None)
-            if getattr(plan, "_oei_cache", None) == key:
+            cached = getattr(plan, "_oei_cache", None)
+            if isinstance(cached, tuple) and cached == key:
                 return plan
             oei = self._oei(False, umat_loc, NOrotation)
         else:
