@@ -218,6 +218,14 @@ int qcdmet_plan_construct_baths(qcdmet_plan *plan, int Nfrag, const int *impStar
  * Replaces the MINPACK lmder iteration behind scipy.optimize.leastsq (src/dmet.py:631) for large fits.
  * QCDMET_E_SOLVER if the damped matrix is not positive definite (raise lambda). */
 int qcdmet_plan_lm_step(qcdmet_plan *plan, const double *resid, double lambda, double *step, double *info);
+/* How qcdmet_plan_lm_step solves the damped problem.  QCDMET_LM_NORMAL (default): equilibrated normal equations,
+ * Cholesky; J^T J is formed once per Jacobian (sharded over the devices of a multi-device plan) and a retry with
+ * another lambda costs one Cholesky.  QCDMET_LM_QR: Householder QR (cuSOLVER geqrf/ormqr) of the augmented matrix
+ * [J; sqrt(lambda) D] -- what MINPACK's lmpar factorises -- for fits whose cond(J)^2 exceeds double precision;
+ * needs (Q + P) P doubles of scratch and one QR per lambda. */
+#define QCDMET_LM_NORMAL 0
+#define QCDMET_LM_QR 1
+int qcdmet_plan_set_lm_method(qcdmet_plan *plan, int method);
 
 /* grad = 2 J^T resid from the device-resident Jacobian (the BFGS gradient of src/dmet.py:381-388);
  * resid: Q doubles (host), grad: ncols doubles (host). */

@@ -16,6 +16,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("QCDMET_B200_LIB", os.path.join(_HERE, "libqcdmet_b200.so"))
 
 KERNEL_AUTO, KERNEL_GENERAL, KERNEL_DMMA, KERNEL_DMMA_NOSYM, KERNEL_FACTORISED = 0, 1, 2, 3, 4
+LM_NORMAL, LM_QR = 0, 1
 
 c_int_p = ctypes.POINTER(ctypes.c_int)
 c_double_p = ctypes.POINTER(ctypes.c_double)
@@ -64,6 +65,7 @@ SIGNATURES = {
                                                    ctypes.c_void_p]),
     "qcdmet_plan_lm_step": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_double, ctypes.c_void_p,
                                            ctypes.c_void_p]),
+    "qcdmet_plan_set_lm_method": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "qcdmet_plan_gradient": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "qcdmet_plan_num_residuals": (ctypes.c_longlong, [ctypes.c_void_p]),
     "qcdmet_plan_kernel_used": (ctypes.c_int, [ctypes.c_void_p]),
@@ -398,6 +400,10 @@ class Plan:
         info = np.zeros(2, dtype=np.float64)
         check(self.lib.qcdmet_plan_lm_step(self.handle, _ptr(resid), float(lam), _ptr(step), _ptr(info)))
         return step, float(info[0]), float(info[1])
+
+    def set_lm_method(self, method):
+        """LM_NORMAL (equilibrated normal equations + Cholesky) or LM_QR (QR of [J; sqrt(lambda) D])."""
+        check(self.lib.qcdmet_plan_set_lm_method(self.handle, int(method)))
 
     def gradient(self, resid):
         """2 J^T resid from the device-resident Jacobian."""

@@ -2,6 +2,7 @@
 // compat rhf_response.
 #include "common.cuh"
 #include <cstdarg>
+#include <cmath>
 #include <algorithm>
 #include <chrono>
 #include <numeric>
@@ -76,6 +77,10 @@ struct qcdmet_plan {
     size_t Apart_capacity = 0;
     int potrf_lwork = 0;
     bool normal_valid = false;          // d_A = J^T J of the Jacobian in memory
+    int lm_method = QCDMET_LM_NORMAL;
+    double *d_aug = nullptr, *d_tau = nullptr, *d_qrwork = nullptr, *d_cn = nullptr, *d_qrb = nullptr;   // QR route: [J; sqrt(lambda) D], tau, workspace, column norms
+    size_t aug_capacity = 0;
+    int qr_lwork = 0;
     bool jac_in_memory = false;         // d_J holds a complete Jacobian (possibly of earlier orbitals)
     bool peers_on = false;
     PeerSet peers;
@@ -909,6 +914,7 @@ void plan_destroy_single(qcdmet_plan *p)
     cudaFree(p->d_CoT); cudaFree(p->d_CvT); cudaFree(p->d_PO); cudaFree(p->d_PV); cudaFree(p->d_W);
     cudaFree(p->d_A); cudaFree(p->d_Awork); cudaFree(p->d_g); cudaFree(p->d_r); cudaFree(p->d_potrf);
     cudaFree(p->d_Apart); cudaFree(p->d_ck); cudaFree(p->d_flush);
+    cudaFree(p->d_aug); cudaFree(p->d_tau); cudaFree(p->d_qrwork); cudaFree(p->d_cn); cudaFree(p->d_qrb);
     cudaFree(p->d_J_own); cudaFree(p->d_D); cudaFree(p->d_work); cudaFree(p->d_info);
     if (p->ev0) cudaEventDestroy(p->ev0);
     if (p->ev1) cudaEventDestroy(p->ev1);
@@ -1151,6 +1157,44 @@ __global__ void lm_scale_kernel(double *__restrict__ x, const double *__restrict
     if (i < n) x[i] = sign * x[i] * d[i];
 }
 
+// ---- QR route of the Levenberg-Marquardt step (no normal equations: cond(J), not cond(J)^2) ----
+// squared column norms of J (one CTA per column, fixed reduction order)
+__global__ void lm_colnorm_kernel(const double *__restrict__ J, long long Q, double *__restrict__ cn)
+{
+    __shared__ double red[32];
+    const double *col = J + (size_t)Q * blockIdx.x;
+    double s = 0.0;
+    for (long long q = threadIdx.x; q < Q; q += blockDim.x) s += col[q] * col[q];
+    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        double t = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.0;
+        for (int off = 16; off > 0; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
+        if (threadIdx.x == 0) cn[blockIdx.x] = t;
+    }
+}
+// Aug = [J; sqrt(lambda) diag(sqrt(max(cn, floor)))], (Q + n) x n, leading dimension Q + n; rhs = [-r; 0]
+__global__ void lm_augment_kernel(const double *__restrict__ J, long long Q, int n, const double *__restrict__ cn,
+                                  double lambda, double floor_, double *__restrict__ Aug)
+{
+    const long long ld = Q + n;
+    const size_t total = (size_t)ld * n;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const long long r = (long long)(i % ld);
+        const int c = (int)(i / ld);
+        double v;
+        if (r < Q) v = J[(size_t)Q * c + r];
+        else v = (r - Q == c) ? sqrt(lambda * fmax(cn[c], floor_)) : 0.0;
+        Aug[i] = v;
+    }
+}
+__global__ void lm_rhs_kernel(const double *__restrict__ r, long long Q, int n, double *__restrict__ b)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < Q + n) b[i] = i < Q ? -r[i] : 0.0;
+}
+
 namespace {
 
 // A = J^T J (upper triangle) on the leader.  Single device: one DSYRK.  Group with a replicated Jacobian (fused
@@ -1223,23 +1267,81 @@ extern "C" int qcdmet_plan_lm_step(qcdmet_plan *p, const double *resid, double l
     const int n = p->colEnd - p->colBegin;
     const long long Q = p->Q;
     QC_CHECK(n > 0 && Q > 0 && Q < (1LL << 31), QCDMET_E_ARG, "empty or oversized least-squares problem");
-    if (!p->d_A) {
-        QC_TRY(dev_alloc(&p->d_A, (size_t)p->P * p->P));
-        QC_TRY(dev_alloc(&p->d_Awork, (size_t)p->P * p->P));
-    }
     if (!p->d_g) QC_TRY(dev_alloc(&p->d_g, (size_t)2 * p->P));
     if (!p->d_r) QC_TRY(dev_alloc(&p->d_r, (size_t)std::max<long long>(Q, p->P)));
     cublasSetStream(p->blas, p->stream);
     cusolverDnSetStream(p->solver, p->stream);
     const double one = 1.0, zero = 0.0;
     const double *J = jac_slice(p);
+    QC_CUDA(cudaMemcpyAsync(p->d_r, resid, sizeof(double) * (size_t)Q, cudaMemcpyHostToDevice, p->stream));
+    cublasStatus_t cs = cublasDgemv(p->blas, CUBLAS_OP_T, (int)Q, n, &one, J, (int)Q, p->d_r, 1, &zero, p->d_g, 1);
+    QC_CHECK(cs == CUBLAS_STATUS_SUCCESS, QCDMET_E_CUDA, "cublasDgemv failed: %d", (int)cs);
+    if (p->lm_method == QCDMET_LM_QR) {
+        // min | [J; sqrt(lambda) D] step + [r; 0] |  by Householder QR of the augmented matrix (what MINPACK's lmpar
+        // solves): step = -R^-1 (Q^T [r; 0])(1:n).  D^2 = diag(J^T J) (floored), the same scaling as the normal route.
+        const long long ld = Q + n;
+        QC_CHECK(ld < (1LL << 31), QCDMET_E_ARG, "augmented matrix has %lld rows (>= 2^31)", ld);
+        const size_t need = (size_t)ld * n;
+        if (need > p->aug_capacity) {
+            cudaFree(p->d_aug);
+            p->d_aug = nullptr;
+            p->aug_capacity = 0;
+            QC_TRY(dev_alloc(&p->d_aug, need));
+            p->aug_capacity = need;
+        }
+        if (!p->d_tau) QC_TRY(dev_alloc(&p->d_tau, (size_t)p->P));
+        if (!p->d_cn) QC_TRY(dev_alloc(&p->d_cn, (size_t)p->P));
+        if (!p->d_qrb) QC_TRY(dev_alloc(&p->d_qrb, (size_t)(Q + p->P)));    // right-hand side [-r; 0], then the step
+        double *d_b = p->d_qrb;
+        lm_colnorm_kernel<<<n, 256, 0, p->stream>>>(J, Q, p->d_cn);
+        lm_augment_kernel<<<2048, 256, 0, p->stream>>>(J, Q, n, p->d_cn, lambda, 1e-12, p->d_aug);
+        lm_rhs_kernel<<<(unsigned)((ld + 255) / 256), 256, 0, p->stream>>>(p->d_r, Q, n, d_b);
+        QC_CUDA(cudaGetLastError());
+        int lw1 = 0, lw2 = 0;
+        cusolverStatus_t qs = cusolverDnDgeqrf_bufferSize(p->solver, (int)ld, n, p->d_aug, (int)ld, &lw1);
+        QC_CHECK(qs == CUSOLVER_STATUS_SUCCESS, QCDMET_E_SOLVER, "cusolverDnDgeqrf_bufferSize failed: %d", (int)qs);
+        qs = cusolverDnDormqr_bufferSize(p->solver, CUBLAS_SIDE_LEFT, CUBLAS_OP_T, (int)ld, 1, n, p->d_aug, (int)ld, p->d_tau,
+                                         d_b, (int)ld, &lw2);
+        QC_CHECK(qs == CUSOLVER_STATUS_SUCCESS, QCDMET_E_SOLVER, "cusolverDnDormqr_bufferSize failed: %d", (int)qs);
+        const int lw = std::max(lw1, lw2);
+        if (lw > p->qr_lwork) {
+            cudaFree(p->d_qrwork);
+            p->d_qrwork = nullptr;
+            p->qr_lwork = 0;
+            QC_TRY(dev_alloc(&p->d_qrwork, (size_t)lw));
+            p->qr_lwork = lw;
+        }
+        qs = cusolverDnDgeqrf(p->solver, (int)ld, n, p->d_aug, (int)ld, p->d_tau, p->d_qrwork, p->qr_lwork, p->d_info);
+        QC_CHECK(qs == CUSOLVER_STATUS_SUCCESS, QCDMET_E_SOLVER, "cusolverDnDgeqrf failed: %d", (int)qs);
+        qs = cusolverDnDormqr(p->solver, CUBLAS_SIDE_LEFT, CUBLAS_OP_T, (int)ld, 1, n, p->d_aug, (int)ld, p->d_tau, d_b, (int)ld,
+                              p->d_qrwork, p->qr_lwork, p->d_info);
+        QC_CHECK(qs == CUSOLVER_STATUS_SUCCESS, QCDMET_E_SOLVER, "cusolverDnDormqr failed: %d", (int)qs);
+        cs = cublasDtrsv(p->blas, CUBLAS_FILL_MODE_UPPER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, n, p->d_aug, (int)ld, d_b, 1);
+        QC_CHECK(cs == CUBLAS_STATUS_SUCCESS, QCDMET_E_CUDA, "cublasDtrsv failed: %d", (int)cs);
+        QC_CUDA(cudaMemcpyAsync(step, d_b, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, p->stream));
+        if (info) {
+            int imax = 0;
+            cublasIdamax(p->blas, n, p->d_g, 1, &imax);
+            double gmax = 0.0, gdots = 0.0;
+            QC_CUDA(cudaMemcpyAsync(&gmax, p->d_g + (imax - 1), sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+            cublasDdot(p->blas, n, p->d_g, 1, d_b, 1, &gdots);
+            QC_CUDA(cudaStreamSynchronize(p->stream));
+            info[0] = fabs(gmax);
+            info[1] = gdots;
+        }
+        QC_CUDA(cudaStreamSynchronize(p->stream));
+        for (int i = 0; i < n; ++i)
+            QC_CHECK(std::isfinite(step[i]), QCDMET_E_SOLVER, "QR step is not finite (rank-deficient J with lambda = 0?): raise lambda");
+        return QCDMET_OK;
+    }
+    if (!p->d_A) {
+        QC_TRY(dev_alloc(&p->d_A, (size_t)p->P * p->P));
+        QC_TRY(dev_alloc(&p->d_Awork, (size_t)p->P * p->P));
+    }
     if (!p->normal_valid) {
         QC_TRY(normal_matrix(p, n, Q));
         p->normal_valid = true;
     }
-    QC_CUDA(cudaMemcpyAsync(p->d_r, resid, sizeof(double) * (size_t)Q, cudaMemcpyHostToDevice, p->stream));
-    cublasStatus_t cs = cublasDgemv(p->blas, CUBLAS_OP_T, (int)Q, n, &one, J, (int)Q, p->d_r, 1, &zero, p->d_g, 1);
-    QC_CHECK(cs == CUBLAS_STATUS_SUCCESS, QCDMET_E_CUDA, "cublasDgemv failed: %d", (int)cs);
     // equilibrated damped normal matrix W = D (A + lambda diag A) D and scale vector D (second half of d_g)
     double *d_scale = p->d_g + p->P;
     lm_damp_scaled_kernel<<<1024, 256, 0, p->stream>>>(p->d_A, p->d_Awork, d_scale, n, lambda, 1e-12);
@@ -1283,6 +1385,14 @@ extern "C" int qcdmet_plan_lm_step(qcdmet_plan *p, const double *resid, double l
         info[1] = gdots;
     }
     QC_CUDA(cudaStreamSynchronize(p->stream));
+    return QCDMET_OK;
+}
+
+extern "C" int qcdmet_plan_set_lm_method(qcdmet_plan *p, int method)
+{
+    QC_CHECK(p != nullptr, QCDMET_E_ARG, "plan is NULL");
+    QC_CHECK(method == QCDMET_LM_NORMAL || method == QCDMET_LM_QR, QCDMET_E_ARG, "unknown LM method %d", method);
+    p->lm_method = method;
     return QCDMET_OK;
 }
 

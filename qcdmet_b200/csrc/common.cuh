@@ -124,11 +124,15 @@ struct ContractSchedule {               // host-built, see kernels_contract.cu
 struct ContractPlan {
     ContractSchedule sched;
     int *d_tileInfo = nullptr, *d_slotRow = nullptr, *d_strips = nullptr;
+    // resident variant (small occupied spaces): CTA table (tile, first column, columns) for the column count resCols
+    void *d_ctaTab = nullptr;
+    size_t ctaCapacity = 0;
+    int nCtas = 0, resCols = -1;
 };
 void contract_schedule_build(int F, const int *rowStart, ContractSchedule *out);
 int contract_plan_build(ContractPlan **out, int F, const int *rowStart);
 void contract_plan_free(ContractPlan *c);
-int launch_contract_panels(const ContractPlan *c, const JacView &v, const double *M, const int *elU,
+int launch_contract_panels(ContractPlan *c, const JacView &v, const double *M, const int *elU,
                            long long nnzInRange, bool nnzAtMost2, cudaStream_t st, int *launches, double *flops);
 
 // factorised path for large fragments (kernels_dmma.cu panel mode + kernels_contract.cu)

@@ -38,6 +38,7 @@ constexpr int CBUF = CSLOTS * CLD;     // doubles per staged array
 constexpr int CCB = 8;                 // columns per CTA
 constexpr int CSTG = 4;                // staging tasks in flight per thread (loads issued before they are used)
 constexpr int CMAXE = QCDMET_CONTRACT_MAX_NNZ;
+constexpr int RES_MAXCOLS = 256;       // columns per CTA of the resident variant (descriptor table in shared memory)
 constexpr int CSMEM = 2 * CBUF * 8 + CCB * CMAXE * 16 + CCB * 4 + CSLOTS * 4;
 // warp-specialised variant (contract_panels_ws_kernel): 4 staging warps + 8 DMMA warps, 2 stages
 constexpr int WS_STAGE_WARPS = 4;
@@ -166,7 +167,7 @@ void contract_schedule_build(int F, const int *rowStart, ContractSchedule *out)
 namespace {
 // One strip over the k-steps of a staged chunk: block b1 against N2 consecutive blocks b2.
 // D[b1,b2] += Y[b1] PO[b2]^T + PO[b1] Y[b2]^T; the two products of a pair are issued N2 DMMAs apart.
-template <int N2>
+template <int N2, int LD = CLD>
 __device__ __forceinline__ void strip_steps(double (&acc)[CMAXN2][2], const double *__restrict__ ya,
                                             const double *__restrict__ pa, const double *__restrict__ yb,
                                             const double *__restrict__ pb, int nk)
@@ -177,14 +178,33 @@ __device__ __forceinline__ void strip_steps(double (&acc)[CMAXN2][2], const doub
         double bP[N2], bY[N2];
 #pragma unroll
         for (int j = 0; j < N2; ++j) {
-            bP[j] = pb[j * CB8 * CLD + 4 * kk];
-            bY[j] = yb[j * CB8 * CLD + 4 * kk];
+            bP[j] = pb[j * CB8 * LD + 4 * kk];
+            bY[j] = yb[j * CB8 * LD + 4 * kk];
         }
 #pragma unroll
         for (int j = 0; j < N2; ++j) dmma884(acc[j][0], acc[j][1], aY, bP[j]);
 #pragma unroll
         for (int j = 0; j < N2; ++j) dmma884(acc[j][0], acc[j][1], aP, bY[j]);
     }
+}
+// One k-step (4 orbitals) of a strip: the resident kernel walks all strips of a warp inside one k loop, so that two
+// DMMAs on the same accumulator are a whole k-step of every strip apart (no dependent back-to-back issue for short strips).
+template <int N2, int LD>
+__device__ __forceinline__ void strip_kstep(double (&acc)[CMAXN2][2], const double *__restrict__ ya,
+                                            const double *__restrict__ pa, const double *__restrict__ yb,
+                                            const double *__restrict__ pb)
+{
+    const double aY = ya[0], aP = pa[0];
+    double bP[N2], bY[N2];
+#pragma unroll
+    for (int j = 0; j < N2; ++j) {
+        bP[j] = pb[j * CB8 * LD];
+        bY[j] = yb[j * CB8 * LD];
+    }
+#pragma unroll
+    for (int j = 0; j < N2; ++j) dmma884(acc[j][0], acc[j][1], aY, bP[j]);
+#pragma unroll
+    for (int j = 0; j < N2; ++j) dmma884(acc[j][0], acc[j][1], aP, bY[j]);
 }
 }  // namespace
 
@@ -342,6 +362,190 @@ contract_panels_kernel(const JacView v, const double *__restrict__ M, const int 
                 acc[s][j][0] = acc[s][j][1] = 0.0;
             }
         }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Resident variant for small occupied spaces (ldo <= 64: the polyyne- and sn2-like fits) and DMET lists
+// (<= 2 elements per perturbation).  contract_panels_kernel re-stages three panel chunks (M of both elements, PO)
+// from L2 for every column; here a CTA owns a tile for a long run of consecutive columns and keeps in shared
+// memory, over the WHOLE occupied range: the PO rows of the tile (loaded once per CTA) and the panel of the
+// column's first element (consecutive columns (r,r), (r,r+1), ... share the row site r: loaded once per run).
+// Only the second element's panel is streamed -- prefetched into registers while the DMMA strips of the previous
+// column run -- so the L2 -> SM traffic per column drops from 3 panel tiles to 1 + 1/(run length) + 1/(columns per
+// CTA).  One CTA per SM (3 x 128 x (ldo + 4) doubles of shared memory), CTAs sized by the host so that every
+// CTA has the same number of block-pair DMMAs.
+// ------------------------------------------------------------------------------------------
+template <int LDO>
+__global__ void __launch_bounds__(CNT, 1)
+contract_resident_kernel(const JacView v, const double *__restrict__ M, const int *__restrict__ elU,
+                         const int4 *__restrict__ tileInfo, const int *__restrict__ slotRowG,
+                         const int *__restrict__ stripsG, const int4 *__restrict__ ctaTab)
+{
+    constexpr int RLD = LDO + 4;                   // row stride: 4 (mod 16) doubles, as CLD
+    constexpr int RBUF = CSLOTS * RLD;
+    constexpr int QP = LDO / 2;                    // orbital pairs per row
+    constexpr int NIT = CSLOTS * QP / CNT;         // (slot, orbital pair) items per thread: 4 / 8 / 12 / 16
+    static_assert(CSLOTS * QP % CNT == 0, "items divide evenly");
+    extern __shared__ __align__(16) unsigned char csm[];
+    double *Ys = reinterpret_cast<double *>(csm);          // Y_p of the tile's rows, whole occupied range
+    double *Ps = Ys + RBUF;                                // PO of the same rows
+    double *Mr = Ps + RBUF;                                // panel of the first element's row site
+    double *coS = Mr + RBUF;                               // [2 buffers][2 elements][LDO] rows of C_o that scale the panels
+    long long *dPan = reinterpret_cast<long long *>(coS + 4 * LDO);   // [RES_MAXCOLS][2] panel offsets of the elements, -1 = none
+    int *dCol = reinterpret_cast<int *>(dPan + 2 * RES_MAXCOLS);      // [RES_MAXCOLS][2] sites whose C_o rows scale them
+    int *srow = dCol + 2 * RES_MAXCOLS;                    // [CSLOTS]
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int4 ct = ctaTab[blockIdx.x];              // tile, first local column, number of columns
+    const int4 ti = tileInfo[ct.x];                  // slotBegin, nSlots, first strip-table entry, nStrips
+    const int pl0 = ct.y, ncb = ct.z;
+
+    if (tid < CSLOTS) srow[tid] = tid < ti.y ? slotRowG[ti.x + tid] : -1;
+    for (int i = tid; i < 3 * RBUF / 2; i += CNT) *reinterpret_cast<double2 *>(Ys + 2 * i) = make_double2(0.0, 0.0);
+    // column descriptions: panels of the (<= 2) elements and the C_o rows that scale them
+    for (int cb = tid; cb < ncb; cb += CNT) {
+        const int p = v.colBegin + pl0 + cb;
+        const int eb = v.h1start[p], n = v.h1start[p + 1] - eb;
+        dPan[2 * cb] = n > 0 ? (long long)elU[eb] * v.S * v.ldo : -1;
+        dCol[2 * cb] = n > 0 ? v.h1col[eb] : 0;
+        dPan[2 * cb + 1] = n > 1 ? (long long)elU[eb + 1] * v.S * v.ldo : -1;
+        dCol[2 * cb + 1] = n > 1 ? v.h1col[eb + 1] : 0;
+    }
+    int sw[CMAXS];
+#pragma unroll
+    for (int s = 0; s < CMAXS; ++s) sw[s] = stripsG[ti.z + warp * CMAXS + s];
+    double acc[CMAXS][CMAXN2][2];
+#pragma unroll
+    for (int s = 0; s < CMAXS; ++s)
+#pragma unroll
+        for (int j = 0; j < CMAXN2; ++j) acc[s][j][0] = acc[s][j][1] = 0.0;
+    __syncthreads();
+
+    // this thread's items: (slot, orbital pair), consecutive threads on consecutive addresses of a panel row
+    int goff[NIT], soff[NIT];
+#pragma unroll
+    for (int k = 0; k < NIT; ++k) {
+        const int i = tid + CNT * k, slot = i / QP, q = i % QP;
+        const int row = srow[slot];
+        goff[k] = row >= 0 ? row * v.ldo + 2 * q : -1;         // S ldo < 2^31 (checked at plan creation)
+        soff[k] = slot * RLD + 2 * q;
+    }
+#pragma unroll
+    for (int k = 0; k < NIT; ++k)
+        if (goff[k] >= 0) *reinterpret_cast<double2 *>(Ps + soff[k]) = ld2(v.PO + goff[k]);
+
+    const int g4 = lane >> 2, t4 = lane & 3;
+    int offA[CMAXS], offB[CMAXS];
+#pragma unroll
+    for (int s = 0; s < CMAXS; ++s) {
+        offA[s] = ((sw[s] & 0xFF) * CB8 + g4) * RLD + t4;
+        offB[s] = (((sw[s] >> 8) & 0xFF) * CB8 + g4) * RLD + t4;
+    }
+    const int nk = (min(LDO, v.no) + 3) / 4;
+
+    // where this warp's strips store: fragment geometry is fixed for the CTA
+    int stRs[CMAXS], stRf[CMAXS], stRa[CMAXS];
+    long long stQ[CMAXS];
+#pragma unroll
+    for (int s = 0; s < CMAXS; ++s) {
+        stRs[s] = stRf[s] = 0; stRa[s] = -1; stQ[s] = 0;
+        if (sw[s] < 0) continue;
+        const int b1 = sw[s] & 0xFF;
+        const int f = v.rowFrag[srow[b1 * CB8]];                  // the first row of a block always exists
+        stRs[s] = v.rowStart[f];
+        stRf[s] = v.rowStart[f + 1] - stRs[s];
+        stRa[s] = srow[b1 * CB8 + g4];
+        stQ[s] = v.qoff[f];
+    }
+    long long resident = -1;                         // panel offset held in Mr
+    long long pA = dPan[0], pB = dPan[1];
+    double2 mreg[NIT];                               // streamed panel (second element) of the current column
+#pragma unroll
+    for (int k = 0; k < NIT; ++k) mreg[k] = (pB >= 0 && goff[k] >= 0) ? ld2(M + pB + goff[k]) : make_double2(0.0, 0.0);
+    if (tid < LDO) {
+        coS[tid] = pA >= 0 ? v.CoT[(size_t)dCol[0] * v.ldo + tid] : 0.0;
+        coS[LDO + tid] = pB >= 0 ? v.CoT[(size_t)dCol[1] * v.ldo + tid] : 0.0;
+    }
+
+    for (int cb = 0; cb < ncb; ++cb) {
+        const int buf = cb & 1;
+        // (A) the first element's panel: reload only when the row site changes
+        if (pA >= 0 && pA != resident) {
+#pragma unroll
+            for (int k = 0; k < NIT; ++k)
+                if (goff[k] >= 0) *reinterpret_cast<double2 *>(Mr + soff[k]) = ld2(M + pA + goff[k]);
+            resident = pA;
+        }
+        __syncthreads();                             // coS[buf] visible; every warp is done with the previous Ys
+        // (B) Y = M_a * Co[c_a] + M_b * Co[c_b] for this thread's own items
+#pragma unroll
+        for (int k = 0; k < NIT; ++k) {
+            if (goff[k] < 0) continue;
+            const int q2 = soff[k] % RLD;            // 2 q
+            const double2 a = ld2(coS + (2 * buf) * LDO + q2), b = ld2(coS + (2 * buf + 1) * LDO + q2);
+            const double2 mr = ld2(Mr + soff[k]);
+            double2 y;
+            y.x = fma(mreg[k].x, b.x, mr.x * a.x);
+            y.y = fma(mreg[k].y, b.y, mr.y * a.y);
+            *reinterpret_cast<double2 *>(Ys + soff[k]) = y;
+        }
+        __syncthreads();                             // Ys complete
+        // (C) next column: streamed panel into registers, C_o rows into the other buffer -- in flight during (D)
+        long long nA = -1, nB = -1;
+        if (cb + 1 < ncb) {
+            nA = dPan[2 * cb + 2]; nB = dPan[2 * cb + 3];
+#pragma unroll
+            for (int k = 0; k < NIT; ++k)
+                mreg[k] = (nB >= 0 && goff[k] >= 0) ? ld2(M + nB + goff[k]) : make_double2(0.0, 0.0);
+            if (tid < LDO) {
+                coS[(2 * (buf ^ 1)) * LDO + tid] = nA >= 0 ? v.CoT[(size_t)dCol[2 * cb + 2] * v.ldo + tid] : 0.0;
+                coS[(2 * (buf ^ 1) + 1) * LDO + tid] = nB >= 0 ? v.CoT[(size_t)dCol[2 * cb + 3] * v.ldo + tid] : 0.0;
+            }
+        }
+        // (D) the strips of this warp over the whole occupied range, interleaved k-step by k-step
+#pragma unroll 2
+        for (int kk = 0; kk < nk; ++kk) {
+#pragma unroll
+            for (int s = 0; s < CMAXS; ++s) {
+                if (sw[s] < 0) continue;             // warp-uniform
+                const double *ya = Ys + offA[s] + 4 * kk, *pa = Ps + offA[s] + 4 * kk;
+                const double *yb = Ys + offB[s] + 4 * kk, *pb = Ps + offB[s] + 4 * kk;
+                switch (sw[s] >> 16) {               // warp-uniform
+                case 4: strip_kstep<4, RLD>(acc[s], ya, pa, yb, pb); break;
+                case 3: strip_kstep<3, RLD>(acc[s], ya, pa, yb, pb); break;
+                case 2: strip_kstep<2, RLD>(acc[s], ya, pa, yb, pb); break;
+                default: strip_kstep<1, RLD>(acc[s], ya, pa, yb, pb); break;
+                }
+            }
+        }
+        // (E) J[a,b] and J[b,a] from the same register, then restart the sums
+        double *Jc = v.J + (size_t)v.Q * (pl0 + cb);
+#pragma unroll
+        for (int s = 0; s < CMAXS; ++s) {
+            if (sw[s] < 0) continue;
+            const int b1 = sw[s] & 0xFF, b2 = (sw[s] >> 8) & 0xFF, n2 = sw[s] >> 16;
+            const int rs = stRs[s], rf = stRf[s], ra = stRa[s];
+            double *Jp = Jc + stQ[s];
+#pragma unroll
+            for (int j = 0; j < CMAXN2; ++j) {
+                if (j < n2) {
+                    const bool diag = (b2 + j == b1);
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int rb = srow[(b2 + j) * CB8 + 2 * t4 + e];
+                        if (ra >= 0 && rb >= 0 && !(diag && 2 * t4 + e < g4)) {
+                            const long long al = ra - rs, bl = rb - rs;
+                            const double val = 2.0 * acc[s][j][e];
+                            Jp[al + rf * bl] = val;
+                            Jp[bl + rf * al] = val;
+                        }
+                    }
+                }
+                acc[s][j][0] = acc[s][j][1] = 0.0;
+            }
+        }
+        pA = nA; pB = nB;
     }
 }
 
@@ -559,12 +763,72 @@ int contract_plan_build(ContractPlan **out, int F, const int *rowStart)
 void contract_plan_free(ContractPlan *c)
 {
     if (!c) return;
-    cudaFree(c->d_tileInfo); cudaFree(c->d_slotRow); cudaFree(c->d_strips);
+    cudaFree(c->d_tileInfo); cudaFree(c->d_slotRow); cudaFree(c->d_strips); cudaFree(c->d_ctaTab);
     cudaGetLastError();
     delete c;
 }
 
-int launch_contract_panels(const ContractPlan *c, const JacView &v, const double *M, const int *elU,
+namespace {
+// CTAs of the resident variant: every tile gets a number of CTAs proportional to its block-pair count (its DMMA
+// work per column), each CTA a run of consecutive columns; about 3 CTAs per SM so that the hardware scheduler evens
+// out what is left.  Returns the table (tile, first local column, columns, 0).
+std::vector<int4> resident_cta_table(const ContractSchedule &s, int ncols, int numSMs)
+{
+    // time of a CTA per column: the DMMA phase lasts as long as the busiest warp's strips (block pairs), plus a
+    // constant for staging Y, the two CTA-wide barriers and the stores (about 3 block pairs' worth)
+    std::vector<double> cost(s.nTiles, 0.0);
+    double total = 0.0;
+    for (int t = 0; t < s.nTiles; ++t) {
+        const int first = s.tileInfo[4 * t + 2];
+        int worst = 0;
+        for (int w = 0; w < CWARPS; ++w) {
+            int load = 0;
+            for (int k = 0; k < CMAXS; ++k) {
+                const int st = s.strips[first + w * CMAXS + k];
+                if (st >= 0) load += st >> 16;
+            }
+            worst = std::max(worst, load);
+        }
+        cost[t] = worst + 3.0;
+        total += cost[t];
+    }
+    // CTAs per tile: largest-remainder split of exactly `waves` x numSMs CTAs (no straggler wave)
+    const int waves = 3;
+    long long want = (long long)waves * numSMs;
+    want = std::max<long long>(want, (long long)s.nTiles * ((ncols + RES_MAXCOLS - 1) / RES_MAXCOLS));
+    std::vector<long long> n(s.nTiles, 0);
+    std::vector<std::pair<double, int>> rem;
+    long long given = 0;
+    for (int t = 0; t < s.nTiles; ++t) {
+        const double share = want * cost[t] / std::max(total, 1e-30);
+        n[t] = std::max<long long>(1, (long long)share);
+        given += n[t];
+        rem.push_back({share - (double)(long long)share, t});
+    }
+    std::sort(rem.begin(), rem.end(), [](const std::pair<double, int> &a, const std::pair<double, int> &b) {
+        return a.first > b.first || (a.first == b.first && a.second < b.second);
+    });
+    for (size_t k = 0; given < want && k < rem.size(); ++k, ++given) ++n[rem[k].second];
+    std::vector<int4> tab;
+    for (int t = 0; t < s.nTiles; ++t) {
+        n[t] = std::min<long long>(n[t], ncols);
+        n[t] = std::max<long long>(n[t], (ncols + RES_MAXCOLS - 1) / RES_MAXCOLS);
+        for (long long k = 0; k < n[t]; ++k) {
+            const int c0 = (int)((long long)ncols * k / n[t]), c1 = (int)((long long)ncols * (k + 1) / n[t]);
+            if (c1 > c0) tab.push_back(make_int4(t, c0, c1 - c0, 0));
+        }
+    }
+    return tab;
+}
+
+template <int LDO>
+constexpr int resident_smem()
+{
+    return 3 * CSLOTS * (LDO + 4) * 8 + 4 * LDO * 8 + RES_MAXCOLS * (2 * 8 + 2 * 4) + CSLOTS * 4;
+}
+}  // namespace
+
+int launch_contract_panels(ContractPlan *c, const JacView &v, const double *M, const int *elU,
                            long long nnzInRange, bool nnzAtMost2, cudaStream_t st, int *launches, double *flops)
 {
     *launches = 0;
@@ -572,12 +836,55 @@ int launch_contract_panels(const ContractPlan *c, const JacView &v, const double
     const int ncols = v.colEnd - v.colBegin;
     const ContractSchedule &s = c->sched;
     if (ncols <= 0 || s.nTiles == 0) return QCDMET_OK;
+    // executed: 2 DMMA.8x8x4 (2 x 512 flop) per block pair and k-step of 4 orbitals (padding of ragged
+    // blocks and of no to a multiple of 4 included); Y build 2 flop per element, slot and orbital
+    *flops = (double)ncols * (double)s.blockPairs * 1024.0 * ((v.no + 3) / 4) +
+             2.0 * (double)nnzInRange * (double)s.validSlots * v.no;
+    const char *wsEnv = getenv("QCDMET_B200_CONTRACT_WS");
+    const bool ws = wsEnv && wsEnv[0] == '1';
+    const char *resEnv = getenv("QCDMET_B200_CONTRACT_RESIDENT");          // "0": keep the chunked kernel (tests, tuning)
+    if (nnzAtMost2 && v.ldo <= 64 && !ws && !(resEnv && resEnv[0] == '0')) {
+        // ---- resident variant: the whole occupied range of a tile stays in shared memory
+        if (c->resCols != ncols || !c->d_ctaTab) {
+            int dev = 0, sms = 0;
+            QC_CUDA(cudaGetDevice(&dev));
+            QC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+            const std::vector<int4> tab = resident_cta_table(s, ncols, sms);
+            if (tab.size() > c->ctaCapacity) {
+                cudaFree(c->d_ctaTab);
+                c->d_ctaTab = nullptr;
+                c->ctaCapacity = 0;
+                if (cudaMalloc((void **)&c->d_ctaTab, tab.size() * sizeof(int4)) != cudaSuccess) {
+                    cudaGetLastError();
+                    set_error("cudaMalloc of the contraction CTA table failed");
+                    return QCDMET_E_ALLOC;
+                }
+                c->ctaCapacity = tab.size();
+            }
+            QC_CUDA(cudaMemcpyAsync(c->d_ctaTab, tab.data(), tab.size() * sizeof(int4), cudaMemcpyHostToDevice, st));
+            QC_CUDA(cudaStreamSynchronize(st));          // tab is a local: the copy must have read it
+            c->nCtas = (int)tab.size();
+            c->resCols = ncols;
+        }
+        const int4 *ctaTab = reinterpret_cast<const int4 *>(c->d_ctaTab);
+        const int4 *tinfo = reinterpret_cast<const int4 *>(c->d_tileInfo);
+#define QC_LAUNCH_RESIDENT(LDOV)                                                                              \
+        if (v.ldo == LDOV) {                                                                                  \
+            QC_CUDA(cudaFuncSetAttribute(contract_resident_kernel<LDOV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                         resident_smem<LDOV>()));                                             \
+            contract_resident_kernel<LDOV><<<c->nCtas, CNT, resident_smem<LDOV>(), st>>>(                     \
+                v, M, elU, tinfo, c->d_slotRow, c->d_strips, ctaTab);                                         \
+        }
+        QC_LAUNCH_RESIDENT(16) QC_LAUNCH_RESIDENT(32) QC_LAUNCH_RESIDENT(48) QC_LAUNCH_RESIDENT(64)
+#undef QC_LAUNCH_RESIDENT
+        QC_CUDA(cudaGetLastError());
+        *launches += 1;
+        return QCDMET_OK;
+    }
     // per device (function attributes live in the context of the current device): set on every launch
     QC_CUDA(cudaFuncSetAttribute(contract_panels_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CSMEM));
     QC_CUDA(cudaFuncSetAttribute(contract_panels_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CSMEM));
     // warp-specialised variant (see the kernel's comment): only on request
-    const char *wsEnv = getenv("QCDMET_B200_CONTRACT_WS");
-    const bool ws = wsEnv && wsEnv[0] == '1';
     if (ws) {
         QC_CUDA(cudaFuncSetAttribute(contract_panels_ws_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM));
         QC_CUDA(cudaFuncSetAttribute(contract_panels_ws_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM));
@@ -606,10 +913,6 @@ int launch_contract_panels(const ContractPlan *c, const JacView &v, const double
         QC_CUDA(cudaGetLastError());
         *launches += 1;
     }
-    // executed: 2 DMMA.8x8x4 (2 x 512 flop) per block pair and k-step of 4 orbitals (padding of ragged
-    // blocks and of no to a multiple of 4 included); Y build 2 flop per element, slot and orbital
-    *flops = (double)ncols * (double)s.blockPairs * 1024.0 * ((v.no + 3) / 4) +
-             2.0 * (double)nnzInRange * (double)s.validSlots * v.no;
     return QCDMET_OK;
 }
 

@@ -94,7 +94,7 @@ struct Cfg {
     static constexpr uint32_t EPI_BYTES = (POS_DOUBLES + COS_DOUBLES) * 8;
     static constexpr int NSTRIDE = RT * RF + 2;         // running-sum row stride (conflict-free 16 B slots)
     static constexpr int NS_DOUBLES = 2 * 128 * NSTRIDE;   // running sums of one item: [column half][site slot][row slot][NSTRIDE]
-    // barriers: full/empty per stage, epilogue operands full/empty, item tables full/empty, running sums done/free, lead
+    // barriers: full/empty per stage, epilogue operands full/empty, item tables full/empty, running sums done/free
     static constexpr int BAR_BYTES = (((2 * MAX_STAGES + 2 + 2 * TABS + 4 + 1) * 8 + 15) / 16) * 16;
     static constexpr int AUX_BYTES = BAR_BYTES + TABS * ITEM_TAB_BYTES;
     static constexpr int FIXED1 = (POS_DOUBLES + COS_DOUBLES + NS_DOUBLES) * 8 + AUX_BYTES;
@@ -121,7 +121,8 @@ struct Cfg {
 struct DmmaArgs {
     int nKc, nOt;
     int nWork;                          // work items of this launch; CTA b executes items b, b + gridDim.x, ...
-    int lead;                           // stages warps 0-3 run ahead of warps 4-7 (0 = start together), < ring depth
+    int nP, nTP;                        // upper bounds of used perturbation slots per component / per tile (assembly loops)
+    int maxE;                           // elements per perturbation (<= MAXE)
     int colBegin, colEnd;
     int sym;                            // symmetric mode: also store the mirrored patch
     long long Q;
@@ -322,7 +323,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) jac_dmma_kernel(const DmmaArgs g)
     const uint32_t barBase = smem_u32(bars);
     const uint32_t epiFull = barBase + 8 * (2 * STAGES), epiEmpty = epiFull + 8;
     const uint32_t tabFull0 = epiEmpty + 8, tabEmpty0 = tabFull0 + 8 * TABS;
-    const uint32_t nsDone0 = tabEmpty0 + 8 * TABS, nsFree0 = nsDone0 + 8 * 2, leadBar = nsFree0 + 8 * 2;
+    const uint32_t nsDone0 = tabEmpty0 + 8 * TABS, nsFree0 = nsDone0 + 8 * 2;
 
     // ---- set-up: barriers
     if (tid == 0) {
@@ -334,7 +335,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) jac_dmma_kernel(const DmmaArgs g)
         mbar_init(epiEmpty, 8);
         for (int t = 0; t < TABS; ++t) { mbar_init(tabFull0 + 8 * t, 1); mbar_init(tabEmpty0 + 8 * t, 8); }
         for (int b = 0; b < 2; ++b) { mbar_init(nsDone0 + 8 * b, 8); mbar_init(nsFree0 + 8 * b, 8); }
-        mbar_init(leadBar, 4);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -403,30 +403,31 @@ __global__ void __launch_bounds__(NTHREADS, 1) jac_dmma_kernel(const DmmaArgs g)
         const int *cp = reinterpret_cast<const int *>(ctab + CT_CP);
         const unsigned char *cent = ctab + CT_CENT;
         const double *Ns0 = Ns + nbj * NS_DOUBLES, *Ns1 = Ns0 + 128 * NSTRIDE;
-        // patch 1: rows of the tile x perturbations of the component
-        for (int idx = tid; idx < MAXP * AT * RF; idx += NCONS) {
+        // patch 1: rows of the tile x perturbations of the component.  Branch-free: elements a perturbation does not
+        // have enter with weight 0 (every running sum is finite), only the store is predicated.
+        const int maxE = g.maxE;
+        for (int idx = tid; idx < g.nP * AT * RF; idx += NCONS) {
             const int pl = idx / (AT * RF), rem = idx % (AT * RF);
             const int a_slot = rem / RF, jj = rem % RF;
             const int p = cp[pl];
-            if (p < g.colBegin || p >= g.colEnd) continue;
             const int self = selfi[a_slot];
             const int a_loc = self & 15, rf = self >> 4;
-            if (trow[a_slot] < 0 || jj >= rf) continue;
-            const int b_slot = partner[a_slot * RF + jj];
+            const int b_slot = partner[a_slot * RF + jj] & (AT - 1);       // "none" (AT) only where nothing is stored
+            const int o1 = a_slot * NSTRIDE + jj, o2 = b_slot * NSTRIDE + a_loc;
             double gab = 0.0, gba = 0.0;
-#pragma unroll
-            for (int e = 0; e < MAXE; ++e) {
+            for (int e = 0; e < maxE; ++e) {
                 const unsigned char ent = cent[pl * MAXE + e];
-                if (ent == 0xFF) continue;
-                const int rs = ent & 15, cs = ent >> 4;
-                const int i1 = (rs * AT + a_slot) * NSTRIDE + cs * RF + jj;
-                const int i2 = (rs * AT + b_slot) * NSTRIDE + cs * RF + a_loc;
-                gab += Ns0[i1] + Ns1[i1];
-                gba += Ns0[i2] + Ns1[i2];
+                const double wgt = ent == 0xFF ? 0.0 : 1.0;
+                const int rs = ent & 3, cs = (ent >> 4) & 3;
+                const int base = rs * AT * NSTRIDE + cs * RF;
+                gab = fma(wgt, Ns0[base + o1] + Ns1[base + o1], gab);
+                gba = fma(wgt, Ns0[base + o2] + Ns1[base + o2], gba);
             }
-            const size_t off = (size_t)g.Q * (p - g.colBegin) + qrow[a_slot] + (long long)rf * jj;
-            const double val = 2.0 * (gab + gba);
-            for (int dst = 0; dst < g.nDest; ++dst) g.J[dst][off] = val;
+            if (p >= g.colBegin && p < g.colEnd && trow[a_slot] >= 0 && jj < rf) {
+                const size_t off = (size_t)g.Q * (p - g.colBegin) + qrow[a_slot] + (long long)rf * jj;
+                const double val = 2.0 * (gab + gba);
+                for (int dst = 0; dst < g.nDest; ++dst) g.J[dst][off] = val;
+            }
         }
         // patch 2 (symmetric mode, off-diagonal block pairs): rows of the component's own fragment x
         // perturbations of the blocks in the tile, from M_a[r,o] = M_r[a,o]:
@@ -436,28 +437,26 @@ __global__ void __launch_bounds__(NTHREADS, 1) jac_dmma_kernel(const DmmaArgs g)
             const unsigned char *loc = ctab + CT_LOC;
             const int *tp = reinterpret_cast<const int *>(tab + TT_TP);
             const unsigned char *te = tab + TT_TE;
-            for (int idx = tid; idx < TP * RT * RT; idx += NCONS) {
+            for (int idx = tid; idx < g.nTP * RT * RT; idx += NCONS) {
                 const int pp = idx / (RT * RT), rem = idx % (RT * RT);
                 const int cs = rem / RT, rs = rem % RT;          // site slots of the component: row r, column c
                 const int p = tp[pp];
-                if (p < g.colBegin || p >= g.colEnd) continue;
                 const int lr = loc[rs], lc = loc[cs];
-                if (lr == 0xFF || lc == 0xFF) continue;
                 const int rf = lr >> 4;
+                const int o1 = rs * AT * NSTRIDE + cs * RF, o2 = cs * AT * NSTRIDE + rs * RF;
                 double grc = 0.0, gcr = 0.0;
-#pragma unroll
-                for (int e = 0; e < MAXE; ++e) {
+                for (int e = 0; e < maxE; ++e) {
                     const unsigned char ent = te[pp * MAXE + e];
-                    if (ent == 0xFF) continue;
-                    const int a_slot = ent & 31, jj = ent >> 5;
-                    const int i1 = (rs * AT + a_slot) * NSTRIDE + cs * RF + jj;
-                    const int i2 = (cs * AT + a_slot) * NSTRIDE + rs * RF + jj;
-                    grc += Ns0[i1] + Ns1[i1];
-                    gcr += Ns0[i2] + Ns1[i2];
+                    const double wgt = ent == 0xFF ? 0.0 : 1.0;
+                    const int base = (ent & 31) * NSTRIDE + ((ent >> 5) & 3);
+                    grc = fma(wgt, Ns0[base + o1] + Ns1[base + o1], grc);
+                    gcr = fma(wgt, Ns0[base + o2] + Ns1[base + o2], gcr);
                 }
-                const size_t off = (size_t)g.Q * (p - g.colBegin) + q0 + (lr & 15) + (long long)rf * (lc & 15);
-                const double val = 2.0 * (grc + gcr);
-                for (int dst = 0; dst < g.nDest; ++dst) g.J[dst][off] = val;
+                if (p >= g.colBegin && p < g.colEnd && lr != 0xFF && lc != 0xFF) {
+                    const size_t off = (size_t)g.Q * (p - g.colBegin) + q0 + (lr & 15) + (long long)rf * (lc & 15);
+                    const double val = 2.0 * (grc + gcr);
+                    for (int dst = 0; dst < g.nDest; ++dst) g.J[dst][off] = val;
+                }
             }
         }
         __syncwarp();
@@ -466,12 +465,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) jac_dmma_kernel(const DmmaArgs g)
             mbar_arrive(tabEmpty0 + 8 * tbj);        // ... nor its tables
         }
     };
-
-    // Stagger the two consumer warps of every SM sub-partition (warps w and w + 4): warps 4-7 start g.lead stages
-    // after warps 0-3 and keep that distance (the ring is deep enough), so one warp of the pair is in the DMMA main
-    // loop while the other one runs its latency-bound epilogue.  Paid once per CTA: the kernel is persistent.
-    int toLead = (warp < 4 && g.lead > 0) ? g.lead : -1;    // stages until warps 0-3 release warps 4-7
-    if (warp >= 4 && g.lead > 0) mbar_wait(leadBar, 0);
 
     long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     long long tPrev = PROF ? clock64() : 0;
@@ -519,7 +512,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) jac_dmma_kernel(const DmmaArgs g)
                 __syncwarp();
                 if (lane == 0) mbar_arrive(barBase + 8 * (STAGES + rs));
                 if (++rs == STAGES) { rs = 0; rph ^= 1; }
-                if (toLead > 0 && --toLead == 0 && lane == 0) mbar_arrive(leadBar);
                 lap(1);
             }
 
@@ -619,7 +611,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) jac_dmma_kernel(const DmmaArgs g)
         if (NSBUF == 1) { assemble(k, wk.y); lap(4); }
         prevTile = wk.y;
     }
-    if (toLead > 0 && lane == 0) mbar_arrive(leadBar);       // fewer stages than the lead: release warps 4-7 now
     if constexpr (!PANEL)
         if (NSBUF == 2 && k > 0) { assemble(k - 1, prevTile); lap(4); }
     if constexpr (PROF)
@@ -664,6 +655,7 @@ struct DmmaPlanData {
     int *d_compSites = nullptr, *d_tileRow = nullptr;
     unsigned char *d_tileTab = nullptr, *d_compTab = nullptr;
     int numSMs = 0;                     // persistent grid: one CTA per SM of the plan's device
+    int nP = 0, nTP = 0, maxE = 0;      // used perturbation slots per component / per tile (max), elements per perturbation (max)
     int2 *d_work = nullptr;
     size_t workCapacity = 0;
     double *d_Wt = nullptr, *d_PVt = nullptr, *d_CVt = nullptr, *d_POt = nullptr, *d_COt = nullptr;
@@ -829,6 +821,8 @@ Schedule build_schedule(int N, int no, int Porig, int F, const int *h1start0, co
     }
     d.nKc = (d.nv + KC - 1) / KC;
     d.nOt = (d.no + d.bn() - 1) / d.bn();
+    for (int c = 0; c < d.nComp; ++c) d.nP = std::max(d.nP, np[c]);
+    for (int p = 0; p < P; ++p) d.maxE = std::max(d.maxE, h1start[p + 1] - h1start[p]);
 
     // symmetric mode: impurity-only rows, and the row sites of every non-empty fragment are exactly the
     // sites of one component (and vice versa).  Then PV/PO rows are C_v/C_o site rows and
@@ -871,6 +865,7 @@ Schedule build_schedule(int N, int no, int Porig, int F, const int *h1start0, co
                 const int f = compFrag[c], t = fragTile[f];
                 if (ntp[t] >= TP) { sym = false; break; }
                 const int pp = ntp[t]++;
+                d.nTP = std::max(d.nTP, ntp[t]);
                 d.tileP[(size_t)t * TP + pp] = p;
                 for (int k = h1start[p]; k < h1start[p + 1]; ++k) {
                     int al = -1, bl = -1;
@@ -934,15 +929,6 @@ int query_sms(DmmaPlanData &d)
     QC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     d.numSMs = sms > 0 ? sms : 1;
     return QCDMET_OK;
-}
-
-// Stages by which warps 0-3 lead warps 4-7: about (epilogue time) / (time one warp alone needs for a stage, 64 NJ
-// cycles of the DMMA pipe), at most ring depth - 1.  $QCDMET_B200_LEAD overrides (tuning; 0 = start together).
-int consumer_lead(int stages, int nj)
-{
-    int lead = nj >= 8 ? 3 : nj >= 6 ? 4 : 6;
-    if (const char *env = getenv("QCDMET_B200_LEAD")) lead = atoi(env);
-    return std::max(0, std::min(lead, stages - 1));
 }
 
 template <typename T>
@@ -1138,6 +1124,7 @@ int launch_jacobian_dmma(DmmaPlanData *d, const JacView &v, cudaStream_t st, int
         a.Wt = d->d_Wt; a.PVt = d->d_PVt; a.CVt = d->d_CVt; a.POt = d->d_POt; a.COt = d->d_COt;
         a.work = d->d_work; a.nWork = (int)d->work.size();
         a.tileTab = d->d_tileTab; a.compTab = d->d_compTab;
+        a.nP = d->nP; a.nTP = d->nTP; a.maxE = d->maxE;
         a.Mout = nullptr; a.mRows = 0; a.ldm = 0;
         a.nDest = z.nDest;
         for (int r = 0; r < QCDMET_MAX_PEERS; ++r) a.J[r] = z.J[r];
@@ -1162,7 +1149,6 @@ int launch_jacobian_dmma(DmmaPlanData *d, const JacView &v, cudaStream_t st, int
                                              K::SMEM_BYTES));                                                 \
                 d->attrSet = true;                                                                            \
             }                                                                                                 \
-            a.lead = consumer_lead(K::STAGES, NJV);                                                           \
             if (profPath && RFV == 4 && NJV >= 6) {                                                           \
                 QC_CUDA(cudaFuncSetAttribute(jac_dmma_kernel<Cfg<4, (NJV >= 6 ? NJV : 6)>, false, true>,      \
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM_BYTES));    \
@@ -1184,7 +1170,7 @@ int launch_jacobian_dmma(DmmaPlanData *d, const JacView &v, cudaStream_t st, int
             cudaFree(a.prof);
             if (FILE *fp = fopen(profPath, "a")) {
                 static const char *names[8] = {"wait_full", "stage_body", "wait_epi", "epilogue", "assembly", "-", "-", "loop_overhead"};
-                fprintf(fp, "items %zu ctas %u nKc %d nOt %d nj %d lead %d\n", d->work.size(), gridForProf, d->nKc, d->nOt, d->nj, a.lead);
+                fprintf(fp, "items %zu ctas %u nKc %d nOt %d nj %d\n", d->work.size(), gridForProf, d->nKc, d->nOt, d->nj);
                 for (int grp = 0; grp < 2; ++grp) {
                     double sum[8] = {0};
                     for (unsigned b = 0; b < gridForProf; ++b)
@@ -1415,7 +1401,6 @@ int launch_jacobian_factorised(FactPlanData *f, const JacView &v, long long nnzI
         a.Mout = f->d_M; a.mRows = v.S; a.ldm = v.ldo;
         a.prof = nullptr;
         a.nDest = 0;
-        a.lead = 0;                         // panel mode has no epilogue to hide
         const unsigned grid = (unsigned)std::min<size_t>(d->work.size(), (size_t)d->numSMs);
         int rc = QCDMET_E_STATE;
         // per device (function attributes live in the context of the current device): set on every launch

@@ -62,7 +62,8 @@ class dmet:
         self._bath_cache = None
         self.solver_threads = 1            # > 1: the embedded problems of one doexact pass are solved in a thread pool
         self.gpu_residual = True      # residual blocks from the device eigensolve shared with the Jacobian
-        self.fit_on_gpu = False       # LSTSQ: Levenberg-Marquardt with the normal equations solved on the device
+        self.fit_on_gpu = False       # LSTSQ: Levenberg-Marquardt with every O(Q P^2) step on the device
+        self.lm_method = 0            # _lib.LM_NORMAL (normal equations + Cholesky) or _lib.LM_QR (QR of [J; sqrt(lambda) D])
 
         self.print_u = True
         self.print_rdm = True
@@ -499,6 +500,7 @@ class dmet:
             plan = self.helper.response_jacobian_device(self.flat2square(x), row_start, rows=rows, row_idx=row_idx,
                                                         NOrotation=self.NOrotation, cache_key=self._umat_key(x))
             self.time_grad += time.time() - start_grad
+            plan.set_lm_method(self.lm_method)
             self.lm_iterations += 1
             accepted = False
             for _ in range(40):

@@ -166,3 +166,72 @@ def test_lm_step_matches_numpy_normal_equations():
     step2, *_ = plan.lm_step(r, 1.0)
     assert np.array_equal(step2, step)
     plan.close()
+
+
+@pytest.mark.gpu
+def test_lm_step_qr_route_matches_lstsq_and_survives_ill_conditioning():
+    """QCDMET_LM_QR factorises [J; sqrt(lambda) D] (cuSOLVER geqrf), as MINPACK's lmpar does, instead of forming J^T J.
+    Same step as the normal-equation route on a well-conditioned fit; on a Jacobian whose columns are scaled over 12
+    decades (cond(J)^2 far beyond double precision) the step still matches a QR-based host solve."""
+    from qcdmet_b200 import _lib, workloads as wl
+    from oracle import response_oracle as ro
+    w = wl.sweep(64)
+    e, c = ro.eigh_sorted(w.h0)
+    plan = _lib.Plan(w.norb, w.num_pairs, w.h1start, w.h1row, w.h1col, w.row_start, w.rows, w.row_idx)
+    plan.set_orbitals(c, e)
+    plan.compute()
+    jac = plan.jacobian()
+    rng = np.random.default_rng(4)
+    r = rng.standard_normal(w.nresid)
+
+    def host_step(j, lam):
+        d = np.sqrt(np.maximum(np.sum(j * j, axis=0), 1e-12))
+        aug = np.vstack([j, np.sqrt(lam) * np.diag(d)])
+        rhs = np.concatenate([-r, np.zeros(j.shape[1])])
+        return np.linalg.lstsq(aug, rhs, rcond=None)[0]
+
+    for lam in (1e-3, 1.0):
+        plan.set_lm_method(_lib.LM_NORMAL)
+        s_normal, gmax_n, _ = plan.lm_step(r, lam)
+        plan.set_lm_method(_lib.LM_QR)
+        s_qr, gmax_q, gdots = plan.lm_step(r, lam)
+        ref = host_step(jac, lam)
+        scale = max(1.0, np.abs(ref).max())
+        assert np.abs(s_qr - ref).max() <= 1e-9 * scale
+        assert np.abs(s_qr - s_normal).max() <= 1e-7 * scale
+        assert abs(gmax_q - gmax_n) <= 1e-12 * gmax_n
+        assert abs(gdots - (jac.T @ r) @ ref) <= 1e-7 * abs((jac.T @ r) @ ref)
+    plan.close()
+
+
+@pytest.mark.gpu
+def test_gpu_lm_reaches_the_minpack_fit_on_a_square_lattice():
+    """f-3 on the configs[1] kind of fit (2-D Hubbard, 2 x 2 impurities, non-TI, impurity-only rows; 16 x 16 lattice:
+    P = 640 parameters, Q = 1024 residuals): device Levenberg-Marquardt, both routes, against MINPACK."""
+    from scipy import optimize
+    from qcdmet_b200 import _lib, workloads as wl
+    l = 16
+    n = l * l
+    # staggered on-site potential: a gapped mean field, so that no level crosses the Fermi energy along the fit (on the
+    # bare lattice the residual is discontinuous there and every optimiser's path depends on where it first steps)
+    stagger = np.array([0.4 if (k % 4) in (0, 3) else -0.4 for k in range(n)])
+    ints = lh.localintegrals_hubbard(wl.hubbard2d_hopping(l, l) + np.diag(stagger), 4.0, n)
+    d = dmet_mod.dmet(ints, chain_clusters(n, 4), False, method='ED', SCmethod='LSTSQ', fitImpBath=False)
+    # synthetic impurity 1-RDMs: the mean-field blocks with the nearest-neighbour coherences reduced (what the
+    # correlated solver does), so that the fit has a non-trivial, well-defined minimiser
+    mf = ints.origDMloc
+    d.imp_1RDM = []
+    for f in range(n // 4):
+        blk = mf[4 * f:4 * f + 4, 4 * f:4 * f + 4].copy()
+        blk[~np.eye(4, dtype=bool)] *= 0.8
+        d.imp_1RDM.append(blk)
+    x0 = np.zeros(d.helper.Nterms)
+    ref = optimize.leastsq(d.rdm_differences, x0, Dfun=d.rdm_differences_derivative, factor=0.1,
+                           ftol=1e-15, xtol=1e-15, gtol=0.0)[0]
+    gauge = lambda u: u - np.eye(n) * np.average(np.diag(u))
+    for method in (_lib.LM_NORMAL, _lib.LM_QR):
+        d.lm_method = method
+        got = d.leastsq_gpu(x0)
+        assert abs(d.costfunction(got) - d.costfunction(ref)) <= 1e-11
+        assert np.abs(gauge(d.flat2square(got)) - gauge(d.flat2square(ref))).max() <= 1e-6
+        assert d.lm_iterations >= 2

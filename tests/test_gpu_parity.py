@@ -486,6 +486,33 @@ def test_experimental_ws_contraction_is_bit_identical(shape, monkeypatch):
     assert np.array_equal(got, ref)
 
 
+@pytest.mark.parametrize("shape", ["sn2", "polyyne", "frag100", "small_no", "column_shard"])
+def test_resident_contraction_is_bit_identical_to_chunked(shape, monkeypatch):
+    """Occupied spaces of <= 64 orbitals with <= 2 elements per perturbation run contract_resident_kernel (PO of
+    the tile and the panel of the first element's row site stay in shared memory, the second panel is streamed
+    through registers); QCDMET_B200_CONTRACT_RESIDENT=0 selects the chunked kernel.  Same schedule, same
+    operation order per accumulator: bit-identical Jacobians."""
+    w = {"sn2": lambda: wl.make_workload("sn2s", 321, 58, [52] + [24] * 10 + [29], nterms=900, seed=20240 + 321),
+         "polyyne": wl.polyyne_like,
+         "frag100": lambda: wl.make_workload("big", 150, 60, [100, 30, 9], nterms=700),
+         "small_no": lambda: wl.make_workload("few", 90, 11, [17, 40, 9, 24], nterms=333),
+         "column_shard": lambda: wl.make_workload("sn2c", 200, 40, [52, 24, 29, 24, 24, 47], nterms=500)}[shape]()
+    e, c = ro.eigh_sorted(w.h0)
+    cols = (123, 407) if shape == "column_shard" else None
+    monkeypatch.setenv("QCDMET_B200_CONTRACT_RESIDENT", "0")
+    ref, *_ = run_plan(w, FACT, from_orbitals=(c, e), cols=cols)
+    monkeypatch.delenv("QCDMET_B200_CONTRACT_RESIDENT")
+    got, *_ = run_plan(w, FACT, from_orbitals=(c, e), cols=cols)
+    assert np.array_equal(got, ref)
+    lo, hi = cols if cols else (0, w.nterms)
+    sample = np.unique(np.linspace(lo, hi - 1, 12).astype(int))
+    lens = w.h1start[sample + 1] - w.h1start[sample]
+    hs = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    take = np.concatenate([np.arange(w.h1start[p], w.h1start[p + 1]) for p in sample])
+    orc = ro.jacobian_from_orbitals(c, e, w.num_pairs, hs, w.h1row[take], w.h1col[take], w.row_start, w.rows, w.row_idx)
+    assert np.abs(got[:, sample - lo] - orc).max() <= TOL
+
+
 def test_invariants_large():
     """Size-independent properties at a size the CPU oracle does not reach in seconds."""
     w = wl.sweep(1000, nterms=600)
