@@ -122,14 +122,18 @@ struct ContractSchedule {               // host-built, see kernels_contract.cu
     std::vector<int> strips;            // [nTiles][8 warps][3] b1 | b2 << 8 | n2 << 16 (tile-local blocks), -1 = none
 };
 struct ContractPlan {
-    ContractSchedule sched;
+    ContractSchedule sched;             // tiles of <= 16 blocks (chunked kernel)
     int *d_tileInfo = nullptr, *d_slotRow = nullptr, *d_strips = nullptr;
+    ContractSchedule sched8;            // tiles of <= 8 blocks (resident kernel)
+    int *d_tileInfo8 = nullptr, *d_slotRow8 = nullptr, *d_strips8 = nullptr;
     // resident variant (small occupied spaces): CTA table (tile, first column, columns) for the column count resCols
     void *d_ctaTab = nullptr;
     size_t ctaCapacity = 0;
     int nCtas = 0, resCols = -1;
+    bool res64 = false;                 // the table was built for the 64-slot variant
+    int maxFragBlocks = 0;              // 8-row blocks of the largest fragment
 };
-void contract_schedule_build(int F, const int *rowStart, ContractSchedule *out);
+void contract_schedule_build(int F, const int *rowStart, ContractSchedule *out, int maxBlocks = 0);   // 0: 16 blocks per tile
 int contract_plan_build(ContractPlan **out, int F, const int *rowStart);
 void contract_plan_free(ContractPlan *c);
 int launch_contract_panels(ContractPlan *c, const JacView &v, const double *M, const int *elU,

@@ -38,7 +38,8 @@ constexpr int CBUF = CSLOTS * CLD;     // doubles per staged array
 constexpr int CCB = 8;                 // columns per CTA
 constexpr int CSTG = 4;                // staging tasks in flight per thread (loads issued before they are used)
 constexpr int CMAXE = QCDMET_CONTRACT_MAX_NNZ;
-constexpr int RES_MAXCOLS = 256;       // columns per CTA of the resident variant (descriptor table in shared memory)
+constexpr int RES_MAXCOLS = 128;       // columns per CTA of the resident variant (descriptor table in shared memory)
+constexpr int RMAXB = 8;               // blocks per tile of the 64-slot resident variant (two CTAs per SM)
 constexpr int CSMEM = 2 * CBUF * 8 + CCB * CMAXE * 16 + CCB * 4 + CSLOTS * 4;
 // warp-specialised variant (contract_panels_ws_kernel): 4 staging warps + 8 DMMA warps, 2 stages
 constexpr int WS_STAGE_WARPS = 4;
@@ -78,8 +79,10 @@ __device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double
 // ------------------------------------------------------------------------------------------
 // host: schedule
 // ------------------------------------------------------------------------------------------
-void contract_schedule_build(int F, const int *rowStart, ContractSchedule *out)
+void contract_schedule_build(int F, const int *rowStart, ContractSchedule *out, int maxBlocks)
 {
+    if (maxBlocks <= 0) maxBlocks = CMAXB;
+    const int slice = maxBlocks / 2;
     ContractSchedule &s = *out;
     s.tileInfo.clear(); s.slotRow.clear(); s.strips.clear();
     s.nTiles = 0; s.validSlots = 0; s.blockPairs = 0;
@@ -130,21 +133,21 @@ void contract_schedule_build(int F, const int *rowStart, ContractSchedule *out)
         if (rf <= 0) continue;
         const int nb = (rf + CB8 - 1) / CB8;
         std::vector<Strip> mine;
-        if (nb <= CMAXB) add_strips(0, nb, 0, nb, true, &mine);
-        if (nb <= CMAXB && (int)mine.size() <= CWARPS * CMAXS) {
+        if (nb <= maxBlocks) add_strips(0, nb, 0, nb, true, &mine);
+        if (nb <= maxBlocks && (int)mine.size() <= CWARPS * CMAXS) {
             // whole fragment in one tile, packed with its neighbours
-            if (blocks + nb > CMAXB || cur.size() + mine.size() > (size_t)(CWARPS * CMAXS)) flush();
+            if (blocks + nb > maxBlocks || cur.size() + mine.size() > (size_t)(CWARPS * CMAXS)) flush();
             for (const Strip &st : mine) cur.push_back({st.b1 + blocks, st.b2 + blocks, st.n2});
             push_blocks(rs, rf, 0, nb);
             blocks += nb;
         } else {
-            // large fragment: one tile per pair of 8-block slices (si <= sj)
+            // large fragment: one tile per pair of slices of maxBlocks / 2 blocks (si <= sj)
             flush();
-            const int ns = (nb + CSLICE - 1) / CSLICE;
+            const int ns = (nb + slice - 1) / slice;
             for (int si = 0; si < ns; ++si)
                 for (int sj = si; sj < ns; ++sj) {
-                    const int bi0 = si * CSLICE, bin = std::min(CSLICE, nb - bi0);
-                    const int bj0 = sj * CSLICE, bjn = std::min(CSLICE, nb - bj0);
+                    const int bi0 = si * slice, bin = std::min(slice, nb - bi0);
+                    const int bj0 = sj * slice, bjn = std::min(slice, nb - bj0);
                     push_blocks(rs, rf, bi0, bin);
                     if (sj == si) {
                         add_strips(0, bin, 0, bin, true, &cur);
@@ -167,11 +170,18 @@ void contract_schedule_build(int F, const int *rowStart, ContractSchedule *out)
 namespace {
 // One strip over the k-steps of a staged chunk: block b1 against N2 consecutive blocks b2.
 // D[b1,b2] += Y[b1] PO[b2]^T + PO[b1] Y[b2]^T; the two products of a pair are issued N2 DMMAs apart.
-template <int N2, int LD = CLD>
+template <int N2, int LD = CLD, bool SPLIT = false>
 __device__ __forceinline__ void strip_steps(double (&acc)[CMAXN2][2], const double *__restrict__ ya,
                                             const double *__restrict__ pa, const double *__restrict__ yb,
                                             const double *__restrict__ pb, int nk)
 {
+    // SPLIT: the two products of a pair accumulate in separate registers (two independent DMMA chains per pair
+    // instead of one: a strip of one pair no longer issues dependent DMMAs back to back) and are added at the end
+    double c2[SPLIT ? N2 : 1][2];
+    if constexpr (SPLIT) {
+#pragma unroll
+        for (int j = 0; j < N2; ++j) c2[j][0] = c2[j][1] = 0.0;
+    }
 #pragma unroll 2
     for (int kk = 0; kk < nk; ++kk) {
         const double aY = ya[4 * kk], aP = pa[4 * kk];
@@ -184,27 +194,15 @@ __device__ __forceinline__ void strip_steps(double (&acc)[CMAXN2][2], const doub
 #pragma unroll
         for (int j = 0; j < N2; ++j) dmma884(acc[j][0], acc[j][1], aY, bP[j]);
 #pragma unroll
-        for (int j = 0; j < N2; ++j) dmma884(acc[j][0], acc[j][1], aP, bY[j]);
+        for (int j = 0; j < N2; ++j) {
+            if constexpr (SPLIT) dmma884(c2[j][0], c2[j][1], aP, bY[j]);
+            else dmma884(acc[j][0], acc[j][1], aP, bY[j]);
+        }
     }
-}
-// One k-step (4 orbitals) of a strip: the resident kernel walks all strips of a warp inside one k loop, so that two
-// DMMAs on the same accumulator are a whole k-step of every strip apart (no dependent back-to-back issue for short strips).
-template <int N2, int LD>
-__device__ __forceinline__ void strip_kstep(double (&acc)[CMAXN2][2], const double *__restrict__ ya,
-                                            const double *__restrict__ pa, const double *__restrict__ yb,
-                                            const double *__restrict__ pb)
-{
-    const double aY = ya[0], aP = pa[0];
-    double bP[N2], bY[N2];
+    if constexpr (SPLIT) {
 #pragma unroll
-    for (int j = 0; j < N2; ++j) {
-        bP[j] = pb[j * CB8 * LD];
-        bY[j] = yb[j * CB8 * LD];
+        for (int j = 0; j < N2; ++j) { acc[j][0] += c2[j][0]; acc[j][1] += c2[j][1]; }
     }
-#pragma unroll
-    for (int j = 0; j < N2; ++j) dmma884(acc[j][0], acc[j][1], aY, bP[j]);
-#pragma unroll
-    for (int j = 0; j < N2; ++j) dmma884(acc[j][0], acc[j][1], aP, bY[j]);
 }
 }  // namespace
 
@@ -373,20 +371,21 @@ contract_panels_kernel(const JacView v, const double *__restrict__ M, const int 
 // column's first element (consecutive columns (r,r), (r,r+1), ... share the row site r: loaded once per run).
 // Only the second element's panel is streamed -- prefetched into registers while the DMMA strips of the previous
 // column run -- so the L2 -> SM traffic per column drops from 3 panel tiles to 1 + 1/(run length) + 1/(columns per
-// CTA).  One CTA per SM (3 x 128 x (ldo + 4) doubles of shared memory), CTAs sized by the host so that every
-// CTA has the same number of block-pair DMMAs.
+// CTA).  CTAs are sized by the host so that every
+// CTA has the same number of block-pair DMMAs.  Tiles of 64 row slots (8 blocks): 3 x 64 x (ldo + 4) doubles, so two
+// CTAs share an SM and one runs its DMMA strips while the other stages Y or stores.
 // ------------------------------------------------------------------------------------------
-template <int LDO>
-__global__ void __launch_bounds__(CNT, 1)
+template <int LDO, int RSLOTS>
+__global__ void __launch_bounds__(CNT, RSLOTS <= 64 ? 2 : 1)
 contract_resident_kernel(const JacView v, const double *__restrict__ M, const int *__restrict__ elU,
                          const int4 *__restrict__ tileInfo, const int *__restrict__ slotRowG,
                          const int *__restrict__ stripsG, const int4 *__restrict__ ctaTab)
 {
     constexpr int RLD = LDO + 4;                   // row stride: 4 (mod 16) doubles, as CLD
-    constexpr int RBUF = CSLOTS * RLD;
+    constexpr int RBUF = RSLOTS * RLD;
     constexpr int QP = LDO / 2;                    // orbital pairs per row
-    constexpr int NIT = CSLOTS * QP / CNT;         // (slot, orbital pair) items per thread: 4 / 8 / 12 / 16
-    static_assert(CSLOTS * QP % CNT == 0, "items divide evenly");
+    constexpr int NIT = RSLOTS * QP / CNT;         // (slot, orbital pair) items per thread: 4 / 8 / 12 / 16
+    static_assert(RSLOTS * QP % CNT == 0, "items divide evenly");
     extern __shared__ __align__(16) unsigned char csm[];
     double *Ys = reinterpret_cast<double *>(csm);          // Y_p of the tile's rows, whole occupied range
     double *Ps = Ys + RBUF;                                // PO of the same rows
@@ -394,14 +393,14 @@ contract_resident_kernel(const JacView v, const double *__restrict__ M, const in
     double *coS = Mr + RBUF;                               // [2 buffers][2 elements][LDO] rows of C_o that scale the panels
     long long *dPan = reinterpret_cast<long long *>(coS + 4 * LDO);   // [RES_MAXCOLS][2] panel offsets of the elements, -1 = none
     int *dCol = reinterpret_cast<int *>(dPan + 2 * RES_MAXCOLS);      // [RES_MAXCOLS][2] sites whose C_o rows scale them
-    int *srow = dCol + 2 * RES_MAXCOLS;                    // [CSLOTS]
+    int *srow = dCol + 2 * RES_MAXCOLS;                    // [RSLOTS]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int4 ct = ctaTab[blockIdx.x];              // tile, first local column, number of columns
     const int4 ti = tileInfo[ct.x];                  // slotBegin, nSlots, first strip-table entry, nStrips
     const int pl0 = ct.y, ncb = ct.z;
 
-    if (tid < CSLOTS) srow[tid] = tid < ti.y ? slotRowG[ti.x + tid] : -1;
+    if (tid < RSLOTS) srow[tid] = tid < ti.y ? slotRowG[ti.x + tid] : -1;
     for (int i = tid; i < 3 * RBUF / 2; i += CNT) *reinterpret_cast<double2 *>(Ys + 2 * i) = make_double2(0.0, 0.0);
     // column descriptions: panels of the (<= 2) elements and the C_o rows that scale them
     for (int cb = tid; cb < ncb; cb += CNT) {
@@ -478,10 +477,9 @@ contract_resident_kernel(const JacView v, const double *__restrict__ M, const in
             resident = pA;
         }
         __syncthreads();                             // coS[buf] visible; every warp is done with the previous Ys
-        // (B) Y = M_a * Co[c_a] + M_b * Co[c_b] for this thread's own items
+        // (B) Y = M_a * Co[c_a] + M_b * Co[c_b] for this thread's own items (padding slots: 0 = 0 a + 0 b, no branch)
 #pragma unroll
         for (int k = 0; k < NIT; ++k) {
-            if (goff[k] < 0) continue;
             const int q2 = soff[k] % RLD;            // 2 q
             const double2 a = ld2(coS + (2 * buf) * LDO + q2), b = ld2(coS + (2 * buf + 1) * LDO + q2);
             const double2 mr = ld2(Mr + soff[k]);
@@ -503,20 +501,16 @@ contract_resident_kernel(const JacView v, const double *__restrict__ M, const in
                 coS[(2 * (buf ^ 1) + 1) * LDO + tid] = nB >= 0 ? v.CoT[(size_t)dCol[2 * cb + 3] * v.ldo + tid] : 0.0;
             }
         }
-        // (D) the strips of this warp over the whole occupied range, interleaved k-step by k-step
-#pragma unroll 2
-        for (int kk = 0; kk < nk; ++kk) {
+        // (D) the strips of this warp over the whole occupied range
 #pragma unroll
-            for (int s = 0; s < CMAXS; ++s) {
-                if (sw[s] < 0) continue;             // warp-uniform
-                const double *ya = Ys + offA[s] + 4 * kk, *pa = Ps + offA[s] + 4 * kk;
-                const double *yb = Ys + offB[s] + 4 * kk, *pb = Ps + offB[s] + 4 * kk;
-                switch (sw[s] >> 16) {               // warp-uniform
-                case 4: strip_kstep<4, RLD>(acc[s], ya, pa, yb, pb); break;
-                case 3: strip_kstep<3, RLD>(acc[s], ya, pa, yb, pb); break;
-                case 2: strip_kstep<2, RLD>(acc[s], ya, pa, yb, pb); break;
-                default: strip_kstep<1, RLD>(acc[s], ya, pa, yb, pb); break;
-                }
+        for (int s = 0; s < CMAXS; ++s) {
+            if (sw[s] < 0) continue;                 // warp-uniform
+            const double *ya = Ys + offA[s], *pa = Ps + offA[s], *yb = Ys + offB[s], *pb = Ps + offB[s];
+            switch (sw[s] >> 16) {                   // warp-uniform
+            case 4: strip_steps<4, RLD, true>(acc[s], ya, pa, yb, pb, nk); break;
+            case 3: strip_steps<3, RLD, true>(acc[s], ya, pa, yb, pb, nk); break;
+            case 2: strip_steps<2, RLD, true>(acc[s], ya, pa, yb, pb, nk); break;
+            default: strip_steps<1, RLD, true>(acc[s], ya, pa, yb, pb, nk); break;
             }
         }
         // (E) J[a,b] and J[b,a] from the same register, then restart the sums
@@ -738,7 +732,28 @@ int contract_plan_build(ContractPlan **out, int F, const int *rowStart)
 {
     *out = nullptr;
     ContractPlan *c = new ContractPlan();
-    contract_schedule_build(F, rowStart, &c->sched);
+    for (int f = 0; f < F; ++f) c->maxFragBlocks = std::max(c->maxFragBlocks, (rowStart[f + 1] - rowStart[f] + CB8 - 1) / CB8);
+    contract_schedule_build(F, rowStart, &c->sched, CMAXB);
+    contract_schedule_build(F, rowStart, &c->sched8, RMAXB);
+    {
+        const ContractSchedule &r = c->sched8;
+        const size_t nt8 = std::max<size_t>(r.tileInfo.size(), 4), nsl8 = std::max<size_t>(r.slotRow.size(), 1),
+                     ni8 = std::max<size_t>(r.strips.size(), 1);
+        if (cudaMalloc((void **)&c->d_tileInfo8, nt8 * sizeof(int)) != cudaSuccess ||
+            cudaMalloc((void **)&c->d_slotRow8, nsl8 * sizeof(int)) != cudaSuccess ||
+            cudaMalloc((void **)&c->d_strips8, ni8 * sizeof(int)) != cudaSuccess) {
+            cudaGetLastError();
+            set_error("cudaMalloc of the contraction schedule failed");
+            contract_plan_free(c);
+            return QCDMET_E_ALLOC;
+        }
+        if (!r.tileInfo.empty())
+            QC_CUDA(cudaMemcpy(c->d_tileInfo8, r.tileInfo.data(), r.tileInfo.size() * sizeof(int), cudaMemcpyHostToDevice));
+        if (!r.slotRow.empty())
+            QC_CUDA(cudaMemcpy(c->d_slotRow8, r.slotRow.data(), r.slotRow.size() * sizeof(int), cudaMemcpyHostToDevice));
+        if (!r.strips.empty())
+            QC_CUDA(cudaMemcpy(c->d_strips8, r.strips.data(), r.strips.size() * sizeof(int), cudaMemcpyHostToDevice));
+    }
     const ContractSchedule &s = c->sched;
     const size_t nt = std::max<size_t>(s.tileInfo.size(), 4), nsl = std::max<size_t>(s.slotRow.size(), 1),
                  ni = std::max<size_t>(s.strips.size(), 1);
@@ -764,6 +779,7 @@ void contract_plan_free(ContractPlan *c)
 {
     if (!c) return;
     cudaFree(c->d_tileInfo); cudaFree(c->d_slotRow); cudaFree(c->d_strips); cudaFree(c->d_ctaTab);
+    cudaFree(c->d_tileInfo8); cudaFree(c->d_slotRow8); cudaFree(c->d_strips8);
     cudaGetLastError();
     delete c;
 }
@@ -772,7 +788,7 @@ namespace {
 // CTAs of the resident variant: every tile gets a number of CTAs proportional to its block-pair count (its DMMA
 // work per column), each CTA a run of consecutive columns; about 3 CTAs per SM so that the hardware scheduler evens
 // out what is left.  Returns the table (tile, first local column, columns, 0).
-std::vector<int4> resident_cta_table(const ContractSchedule &s, int ncols, int numSMs)
+std::vector<int4> resident_cta_table(const ContractSchedule &s, int ncols, int numSMs, int ctasPerSM)
 {
     // time of a CTA per column: the DMMA phase lasts as long as the busiest warp's strips (block pairs), plus a
     // constant for staging Y, the two CTA-wide barriers and the stores (about 3 block pairs' worth)
@@ -793,8 +809,8 @@ std::vector<int4> resident_cta_table(const ContractSchedule &s, int ncols, int n
         total += cost[t];
     }
     // CTAs per tile: largest-remainder split of exactly `waves` x numSMs CTAs (no straggler wave)
-    const int waves = 3;
-    long long want = (long long)waves * numSMs;
+    const int waves = 3;                          // per resident CTA slot
+    long long want = (long long)ctasPerSM * waves * numSMs;
     want = std::max<long long>(want, (long long)s.nTiles * ((ncols + RES_MAXCOLS - 1) / RES_MAXCOLS));
     std::vector<long long> n(s.nTiles, 0);
     std::vector<std::pair<double, int>> rem;
@@ -821,10 +837,10 @@ std::vector<int4> resident_cta_table(const ContractSchedule &s, int ncols, int n
     return tab;
 }
 
-template <int LDO>
+template <int LDO, int RSLOTS>
 constexpr int resident_smem()
 {
-    return 3 * CSLOTS * (LDO + 4) * 8 + 4 * LDO * 8 + RES_MAXCOLS * (2 * 8 + 2 * 4) + CSLOTS * 4;
+    return 3 * RSLOTS * (LDO + 4) * 8 + 4 * LDO * 8 + RES_MAXCOLS * (2 * 8 + 2 * 4) + RSLOTS * 4;
 }
 }  // namespace
 
@@ -845,11 +861,17 @@ int launch_contract_panels(ContractPlan *c, const JacView &v, const double *M, c
     const char *resEnv = getenv("QCDMET_B200_CONTRACT_RESIDENT");          // "0": keep the chunked kernel (tests, tuning)
     if (nnzAtMost2 && v.ldo <= 64 && !ws && !(resEnv && resEnv[0] == '0')) {
         // ---- resident variant: the whole occupied range of a tile stays in shared memory
-        if (c->resCols != ncols || !c->d_ctaTab) {
+        // tiles of 64 row slots with two CTAs per SM when the fragments are small (<= 2 blocks: the strips of a 64-slot
+        // tile then still fill the eight warps); tiles of 128 slots, one CTA per SM otherwise
+        const bool small = c->maxFragBlocks <= 2;
+        const char *slotsEnv = getenv("QCDMET_B200_CONTRACT_SLOTS");        // tuning: 64 | 128
+        const bool use64 = slotsEnv ? atoi(slotsEnv) == 64 : small;
+        const ContractSchedule &rs = use64 ? c->sched8 : c->sched;
+        if (c->resCols != ncols || c->res64 != use64 || !c->d_ctaTab) {
             int dev = 0, sms = 0;
             QC_CUDA(cudaGetDevice(&dev));
             QC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-            const std::vector<int4> tab = resident_cta_table(s, ncols, sms);
+            const std::vector<int4> tab = resident_cta_table(rs, ncols, sms, use64 ? 2 : 1);
             if (tab.size() > c->ctaCapacity) {
                 cudaFree(c->d_ctaTab);
                 c->d_ctaTab = nullptr;
@@ -865,17 +887,20 @@ int launch_contract_panels(ContractPlan *c, const JacView &v, const double *M, c
             QC_CUDA(cudaStreamSynchronize(st));          // tab is a local: the copy must have read it
             c->nCtas = (int)tab.size();
             c->resCols = ncols;
+            c->res64 = use64;
         }
         const int4 *ctaTab = reinterpret_cast<const int4 *>(c->d_ctaTab);
-        const int4 *tinfo = reinterpret_cast<const int4 *>(c->d_tileInfo);
-#define QC_LAUNCH_RESIDENT(LDOV)                                                                              \
-        if (v.ldo == LDOV) {                                                                                  \
-            QC_CUDA(cudaFuncSetAttribute(contract_resident_kernel<LDOV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                         resident_smem<LDOV>()));                                             \
-            contract_resident_kernel<LDOV><<<c->nCtas, CNT, resident_smem<LDOV>(), st>>>(                     \
-                v, M, elU, tinfo, c->d_slotRow, c->d_strips, ctaTab);                                         \
+        const int4 *tinfo = reinterpret_cast<const int4 *>(use64 ? c->d_tileInfo8 : c->d_tileInfo);
+        const int *slotRow = use64 ? c->d_slotRow8 : c->d_slotRow, *strips = use64 ? c->d_strips8 : c->d_strips;
+#define QC_LAUNCH_RESIDENT(LDOV, SLOTSV)                                                                      \
+        if (v.ldo == LDOV && (use64 ? 64 : 128) == SLOTSV) {                                                  \
+            QC_CUDA(cudaFuncSetAttribute(contract_resident_kernel<LDOV, SLOTSV>,                              \
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, resident_smem<LDOV, SLOTSV>())); \
+            contract_resident_kernel<LDOV, SLOTSV><<<c->nCtas, CNT, resident_smem<LDOV, SLOTSV>(), st>>>(     \
+                v, M, elU, tinfo, slotRow, strips, ctaTab);                                                   \
         }
-        QC_LAUNCH_RESIDENT(16) QC_LAUNCH_RESIDENT(32) QC_LAUNCH_RESIDENT(48) QC_LAUNCH_RESIDENT(64)
+        QC_LAUNCH_RESIDENT(16, 64) QC_LAUNCH_RESIDENT(32, 64) QC_LAUNCH_RESIDENT(48, 64) QC_LAUNCH_RESIDENT(64, 64)
+        QC_LAUNCH_RESIDENT(16, 128) QC_LAUNCH_RESIDENT(32, 128) QC_LAUNCH_RESIDENT(48, 128) QC_LAUNCH_RESIDENT(64, 128)
 #undef QC_LAUNCH_RESIDENT
         QC_CUDA(cudaGetLastError());
         *launches += 1;

@@ -403,59 +403,122 @@ __global__ void __launch_bounds__(NTHREADS, 1) jac_dmma_kernel(const DmmaArgs g)
         const int *cp = reinterpret_cast<const int *>(ctab + CT_CP);
         const unsigned char *cent = ctab + CT_CENT;
         const double *Ns0 = Ns + nbj * NS_DOUBLES, *Ns1 = Ns0 + 128 * NSTRIDE;
-        // patch 1: rows of the tile x perturbations of the component.  Branch-free: elements a perturbation does not
-        // have enter with weight 0 (every running sum is finite), only the store is predicated.
-        const int maxE = g.maxE;
-        for (int idx = tid; idx < g.nP * AT * RF; idx += NCONS) {
-            const int pl = idx / (AT * RF), rem = idx % (AT * RF);
-            const int a_slot = rem / RF, jj = rem % RF;
-            const int p = cp[pl];
-            const int self = selfi[a_slot];
-            const int a_loc = self & 15, rf = self >> 4;
-            const int b_slot = partner[a_slot * RF + jj] & (AT - 1);       // "none" (AT) only where nothing is stored
-            const int o1 = a_slot * NSTRIDE + jj, o2 = b_slot * NSTRIDE + a_loc;
-            double gab = 0.0, gba = 0.0;
-            for (int e = 0; e < maxE; ++e) {
-                const unsigned char ent = cent[pl * MAXE + e];
-                const double wgt = ent == 0xFF ? 0.0 : 1.0;
-                const int rs = ent & 3, cs = (ent >> 4) & 3;
-                const int base = rs * AT * NSTRIDE + cs * RF;
-                gab = fma(wgt, Ns0[base + o1] + Ns1[base + o1], gab);
-                gba = fma(wgt, Ns0[base + o2] + Ns1[base + o2], gba);
-            }
-            if (p >= g.colBegin && p < g.colEnd && trow[a_slot] >= 0 && jj < rf) {
+        // Two forms of the same arithmetic.  ptxas schedules the DMMA main loop of a variant differently depending on
+        // the code around it: measured on one B200 (profiles/r2_ab_fused_assembly.txt), the branchy form below keeps
+        // Cfg<4,6> 2.9 % faster (N = 576 and N = 4000), the branch-free form keeps Cfg<4,8> 1.8 % faster (N = 1000, 2000).
+        if constexpr (RF == 4 && NJ == 6) {
+            // patch 1: rows of the tile x perturbations of the component
+            for (int idx = tid; idx < MAXP * AT * RF; idx += NCONS) {
+                const int pl = idx / (AT * RF), rem = idx % (AT * RF);
+                const int a_slot = rem / RF, jj = rem % RF;
+                const int p = cp[pl];
+                if (p < g.colBegin || p >= g.colEnd) continue;
+                const int self = selfi[a_slot];
+                const int a_loc = self & 15, rf = self >> 4;
+                if (trow[a_slot] < 0 || jj >= rf) continue;
+                const int b_slot = partner[a_slot * RF + jj];
+                double gab = 0.0, gba = 0.0;
+    #pragma unroll
+                for (int e = 0; e < MAXE; ++e) {
+                    const unsigned char ent = cent[pl * MAXE + e];
+                    if (ent == 0xFF) continue;
+                    const int rs = ent & 15, cs = ent >> 4;
+                    const int i1 = (rs * AT + a_slot) * NSTRIDE + cs * RF + jj;
+                    const int i2 = (rs * AT + b_slot) * NSTRIDE + cs * RF + a_loc;
+                    gab += Ns0[i1] + Ns1[i1];
+                    gba += Ns0[i2] + Ns1[i2];
+                }
                 const size_t off = (size_t)g.Q * (p - g.colBegin) + qrow[a_slot] + (long long)rf * jj;
                 const double val = 2.0 * (gab + gba);
                 for (int dst = 0; dst < g.nDest; ++dst) g.J[dst][off] = val;
             }
-        }
-        // patch 2 (symmetric mode, off-diagonal block pairs): rows of the component's own fragment x
-        // perturbations of the blocks in the tile, from M_a[r,o] = M_r[a,o]:
-        //   G_p'[r,c] = sum_{(a,b') in p'} N_r[a; c, b']
-        if (g.sym && *reinterpret_cast<const int *>(ctab + CT_TILE) != tile) {
-            const long long q0 = *reinterpret_cast<const long long *>(ctab + CT_Q);
-            const unsigned char *loc = ctab + CT_LOC;
-            const int *tp = reinterpret_cast<const int *>(tab + TT_TP);
-            const unsigned char *te = tab + TT_TE;
-            for (int idx = tid; idx < g.nTP * RT * RT; idx += NCONS) {
-                const int pp = idx / (RT * RT), rem = idx % (RT * RT);
-                const int cs = rem / RT, rs = rem % RT;          // site slots of the component: row r, column c
-                const int p = tp[pp];
-                const int lr = loc[rs], lc = loc[cs];
-                const int rf = lr >> 4;
-                const int o1 = rs * AT * NSTRIDE + cs * RF, o2 = cs * AT * NSTRIDE + rs * RF;
-                double grc = 0.0, gcr = 0.0;
-                for (int e = 0; e < maxE; ++e) {
-                    const unsigned char ent = te[pp * MAXE + e];
-                    const double wgt = ent == 0xFF ? 0.0 : 1.0;
-                    const int base = (ent & 31) * NSTRIDE + ((ent >> 5) & 3);
-                    grc = fma(wgt, Ns0[base + o1] + Ns1[base + o1], grc);
-                    gcr = fma(wgt, Ns0[base + o2] + Ns1[base + o2], gcr);
-                }
-                if (p >= g.colBegin && p < g.colEnd && lr != 0xFF && lc != 0xFF) {
+            // patch 2 (symmetric mode, off-diagonal block pairs): rows of the component's own fragment x
+            // perturbations of the blocks in the tile, from M_a[r,o] = M_r[a,o]:
+            //   G_p'[r,c] = sum_{(a,b') in p'} N_r[a; c, b']
+            if (g.sym && *reinterpret_cast<const int *>(ctab + CT_TILE) != tile) {
+                const long long q0 = *reinterpret_cast<const long long *>(ctab + CT_Q);
+                const unsigned char *loc = ctab + CT_LOC;
+                const int *tp = reinterpret_cast<const int *>(tab + TT_TP);
+                const unsigned char *te = tab + TT_TE;
+                for (int idx = tid; idx < TP * RT * RT; idx += NCONS) {
+                    const int pp = idx / (RT * RT), rem = idx % (RT * RT);
+                    const int cs = rem / RT, rs = rem % RT;          // site slots of the component: row r, column c
+                    const int p = tp[pp];
+                    if (p < g.colBegin || p >= g.colEnd) continue;
+                    const int lr = loc[rs], lc = loc[cs];
+                    if (lr == 0xFF || lc == 0xFF) continue;
+                    const int rf = lr >> 4;
+                    double grc = 0.0, gcr = 0.0;
+    #pragma unroll
+                    for (int e = 0; e < MAXE; ++e) {
+                        const unsigned char ent = te[pp * MAXE + e];
+                        if (ent == 0xFF) continue;
+                        const int a_slot = ent & 31, jj = ent >> 5;
+                        const int i1 = (rs * AT + a_slot) * NSTRIDE + cs * RF + jj;
+                        const int i2 = (cs * AT + a_slot) * NSTRIDE + rs * RF + jj;
+                        grc += Ns0[i1] + Ns1[i1];
+                        gcr += Ns0[i2] + Ns1[i2];
+                    }
                     const size_t off = (size_t)g.Q * (p - g.colBegin) + q0 + (lr & 15) + (long long)rf * (lc & 15);
                     const double val = 2.0 * (grc + gcr);
                     for (int dst = 0; dst < g.nDest; ++dst) g.J[dst][off] = val;
+                }
+            }
+        } else {
+            // patch 1: rows of the tile x perturbations of the component.  Branch-free: elements a perturbation does not
+            // have enter with weight 0 (every running sum is finite), only the store is predicated.
+            const int maxE = g.maxE;
+            for (int idx = tid; idx < g.nP * AT * RF; idx += NCONS) {
+                const int pl = idx / (AT * RF), rem = idx % (AT * RF);
+                const int a_slot = rem / RF, jj = rem % RF;
+                const int p = cp[pl];
+                const int self = selfi[a_slot];
+                const int a_loc = self & 15, rf = self >> 4;
+                const int b_slot = partner[a_slot * RF + jj] & (AT - 1);       // "none" (AT) only where nothing is stored
+                const int o1 = a_slot * NSTRIDE + jj, o2 = b_slot * NSTRIDE + a_loc;
+                double gab = 0.0, gba = 0.0;
+                for (int e = 0; e < maxE; ++e) {
+                    const unsigned char ent = cent[pl * MAXE + e];
+                    const double wgt = ent == 0xFF ? 0.0 : 1.0;
+                    const int rs = ent & 3, cs = (ent >> 4) & 3;
+                    const int base = rs * AT * NSTRIDE + cs * RF;
+                    gab = fma(wgt, Ns0[base + o1] + Ns1[base + o1], gab);
+                    gba = fma(wgt, Ns0[base + o2] + Ns1[base + o2], gba);
+                }
+                if (p >= g.colBegin && p < g.colEnd && trow[a_slot] >= 0 && jj < rf) {
+                    const size_t off = (size_t)g.Q * (p - g.colBegin) + qrow[a_slot] + (long long)rf * jj;
+                    const double val = 2.0 * (gab + gba);
+                    for (int dst = 0; dst < g.nDest; ++dst) g.J[dst][off] = val;
+                }
+            }
+            // patch 2 (symmetric mode, off-diagonal block pairs): rows of the component's own fragment x
+            // perturbations of the blocks in the tile, from M_a[r,o] = M_r[a,o]:
+            //   G_p'[r,c] = sum_{(a,b') in p'} N_r[a; c, b']
+            if (g.sym && *reinterpret_cast<const int *>(ctab + CT_TILE) != tile) {
+                const long long q0 = *reinterpret_cast<const long long *>(ctab + CT_Q);
+                const unsigned char *loc = ctab + CT_LOC;
+                const int *tp = reinterpret_cast<const int *>(tab + TT_TP);
+                const unsigned char *te = tab + TT_TE;
+                for (int idx = tid; idx < g.nTP * RT * RT; idx += NCONS) {
+                    const int pp = idx / (RT * RT), rem = idx % (RT * RT);
+                    const int cs = rem / RT, rs = rem % RT;          // site slots of the component: row r, column c
+                    const int p = tp[pp];
+                    const int lr = loc[rs], lc = loc[cs];
+                    const int rf = lr >> 4;
+                    const int o1 = rs * AT * NSTRIDE + cs * RF, o2 = cs * AT * NSTRIDE + rs * RF;
+                    double grc = 0.0, gcr = 0.0;
+                    for (int e = 0; e < maxE; ++e) {
+                        const unsigned char ent = te[pp * MAXE + e];
+                        const double wgt = ent == 0xFF ? 0.0 : 1.0;
+                        const int base = (ent & 31) * NSTRIDE + ((ent >> 5) & 3);
+                        grc = fma(wgt, Ns0[base + o1] + Ns1[base + o1], grc);
+                        gcr = fma(wgt, Ns0[base + o2] + Ns1[base + o2], gcr);
+                    }
+                    if (p >= g.colBegin && p < g.colEnd && lr != 0xFF && lc != 0xFF) {
+                        const size_t off = (size_t)g.Q * (p - g.colBegin) + q0 + (lr & 15) + (long long)rf * (lc & 15);
+                        const double val = 2.0 * (grc + gcr);
+                        for (int dst = 0; dst < g.nDest; ++dst) g.J[dst][off] = val;
+                    }
                 }
             }
         }

@@ -487,11 +487,12 @@ def test_experimental_ws_contraction_is_bit_identical(shape, monkeypatch):
 
 
 @pytest.mark.parametrize("shape", ["sn2", "polyyne", "frag100", "small_no", "column_shard"])
-def test_resident_contraction_is_bit_identical_to_chunked(shape, monkeypatch):
+def test_resident_contraction_matches_chunked(shape, monkeypatch):
     """Occupied spaces of <= 64 orbitals with <= 2 elements per perturbation run contract_resident_kernel (PO of
     the tile and the panel of the first element's row site stay in shared memory, the second panel is streamed
-    through registers); QCDMET_B200_CONTRACT_RESIDENT=0 selects the chunked kernel.  Same schedule, same
-    operation order per accumulator: bit-identical Jacobians."""
+    through registers); QCDMET_B200_CONTRACT_RESIDENT=0 selects the chunked kernel.  Same schedule and stores; the
+    resident kernel keeps the two products of a block pair in separate accumulators (added at the end of a column),
+    so the results agree to rounding, blocks stay exactly symmetric and runs are bit-reproducible."""
     w = {"sn2": lambda: wl.make_workload("sn2s", 321, 58, [52] + [24] * 10 + [29], nterms=900, seed=20240 + 321),
          "polyyne": wl.polyyne_like,
          "frag100": lambda: wl.make_workload("big", 150, 60, [100, 30, 9], nterms=700),
@@ -503,7 +504,9 @@ def test_resident_contraction_is_bit_identical_to_chunked(shape, monkeypatch):
     ref, *_ = run_plan(w, FACT, from_orbitals=(c, e), cols=cols)
     monkeypatch.delenv("QCDMET_B200_CONTRACT_RESIDENT")
     got, *_ = run_plan(w, FACT, from_orbitals=(c, e), cols=cols)
-    assert np.array_equal(got, ref)
+    again, *_ = run_plan(w, FACT, from_orbitals=(c, e), cols=cols)
+    assert np.array_equal(got, again)                       # run-to-run bit-reproducible
+    assert np.abs(got - ref).max() <= 1e-13 * max(1.0, np.abs(ref).max())
     lo, hi = cols if cols else (0, w.nterms)
     sample = np.unique(np.linspace(lo, hi - 1, 12).astype(int))
     lens = w.h1start[sample + 1] - w.h1start[sample]
