@@ -40,6 +40,22 @@ void set_error(const char *fmt, ...);
 
 inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
+// Debug build (make debug -> libqcdmet_b200_dbg.so, -DQCDMET_BOUNDS_CHECK): every Jacobian / panel store and the
+// table-driven shared-memory indices of the kernels are range-checked on the device; a violation prints where and
+// traps (the next CUDA call returns an error).  compute-sanitizer is not available on the GPU pool.
+#ifdef QCDMET_BOUNDS_CHECK
+#define QC_DEV_ASSERT(cond)                                                                              \
+    do {                                                                                                 \
+        if (!(cond)) {                                                                                   \
+            printf("qcdmet bounds check failed: %s (%s:%d) block %d thread %d\n", #cond, __FILE__, __LINE__, \
+                   (int)blockIdx.x, (int)threadIdx.x);                                                   \
+            __trap();                                                                                    \
+        }                                                                                                \
+    } while (0)
+#else
+#define QC_DEV_ASSERT(cond) ((void)0)
+#endif
+
 // ---------------------------------------------------------------------------------------
 // Device-side view of everything the Jacobian kernels read.  Layout in HBM:
 //   CoT [N ][ldo]  CoT[i][o] = C[i, o]          (site-major, orbital contiguous, zero padded)

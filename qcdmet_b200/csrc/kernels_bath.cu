@@ -37,6 +37,7 @@ __global__ void __launch_bounds__(BATH_THREADS) bath_eigen_kernel(
     const int r0 = impStart[f], m = impStart[f + 1] - r0;
     if (m == 0) { if (threadIdx.x == 0) { numKept[f] = 0; sweepsOut[f] = 0; } return; }
     const int mp = (m + 1) & ~1, ld = mp + 1, npairs = mp / 2;
+    QC_DEV_ASSERT(m <= QCDMET_BATH_MAX_IMP);
     double *A = reinterpret_cast<double *>(bsm);
     double *V = A + mp * ld;
     double *cs = V + mp * ld;                        // [npairs][2]
@@ -74,6 +75,7 @@ __global__ void __launch_bounds__(BATH_THREADS) bath_eigen_kernel(
                 int p = tid == 0 ? mp - 1 : (step + tid) % (mp - 1);
                 int q = (step - tid + (mp - 1)) % (mp - 1);
                 if (p > q) { const int t = p; p = q; q = t; }
+                QC_DEV_ASSERT(p >= 0 && q < mp && p != q);
                 double c = 1.0, s = 0.0;
                 if (q < m) {
                     const double app = A[p * ld + p], aqq = A[q * ld + q], apq = A[p * ld + q];

@@ -352,6 +352,7 @@ contract_panels_kernel(const JacView v, const double *__restrict__ M, const int 
                         if (ra >= 0 && rb >= 0 && !(diag && 2 * t4 + e < g4)) {
                             const long long al = ra - rs, bl = rb - rs;
                             const double val = 2.0 * acc[s][j][e];
+                            QC_DEV_ASSERT(al >= 0 && bl >= 0 && al < rf && bl < rf);
                             Jp[al + rf * bl] = val;
                             Jp[bl + rf * al] = val;
                         }
@@ -531,6 +532,7 @@ contract_resident_kernel(const JacView v, const double *__restrict__ M, const in
                         if (ra >= 0 && rb >= 0 && !(diag && 2 * t4 + e < g4)) {
                             const long long al = ra - rs, bl = rb - rs;
                             const double val = 2.0 * acc[s][j][e];
+                            QC_DEV_ASSERT(al >= 0 && bl >= 0 && al < rf && bl < rf);
                             Jp[al + rf * bl] = val;
                             Jp[bl + rf * al] = val;
                         }
@@ -712,6 +714,7 @@ contract_panels_ws_kernel(const JacView v, const double *__restrict__ M, const i
                             if (ra >= 0 && rb >= 0 && !(diag && 2 * t4 + e < g4)) {
                                 const long long al = ra - rs, bl = rb - rs;
                                 const double val = 2.0 * acc[s][j][e];
+                                QC_DEV_ASSERT(al >= 0 && bl >= 0 && al < rf && bl < rf);
                                 Jp[al + rf * bl] = val;
                                 Jp[bl + rf * al] = val;
                             }

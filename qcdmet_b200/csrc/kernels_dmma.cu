@@ -126,6 +126,7 @@ struct DmmaArgs {
     int colBegin, colEnd;
     int sym;                            // symmetric mode: also store the mirrored patch
     long long Q;
+    long long jCap;                     // doubles in every destination buffer reachable from column colBegin (bounds checks)
     const double *Wt, *PVt, *CVt, *POt, *COt;
     const int2 *work;                   // (component, tile) per work item
     const unsigned char *tileTab;       // [nTiles][TILE_TAB_BYTES]
@@ -430,6 +431,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) jac_dmma_kernel(const DmmaArgs g)
                 }
                 const size_t off = (size_t)g.Q * (p - g.colBegin) + qrow[a_slot] + (long long)rf * jj;
                 const double val = 2.0 * (gab + gba);
+                QC_DEV_ASSERT(off < (size_t)g.jCap);
                 for (int dst = 0; dst < g.nDest; ++dst) g.J[dst][off] = val;
             }
             // patch 2 (symmetric mode, off-diagonal block pairs): rows of the component's own fragment x
@@ -461,6 +463,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) jac_dmma_kernel(const DmmaArgs g)
                     }
                     const size_t off = (size_t)g.Q * (p - g.colBegin) + q0 + (lr & 15) + (long long)rf * (lc & 15);
                     const double val = 2.0 * (grc + gcr);
+                    QC_DEV_ASSERT(off < (size_t)g.jCap);
                     for (int dst = 0; dst < g.nDest; ++dst) g.J[dst][off] = val;
                 }
             }
@@ -488,6 +491,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) jac_dmma_kernel(const DmmaArgs g)
                 if (p >= g.colBegin && p < g.colEnd && trow[a_slot] >= 0 && jj < rf) {
                     const size_t off = (size_t)g.Q * (p - g.colBegin) + qrow[a_slot] + (long long)rf * jj;
                     const double val = 2.0 * (gab + gba);
+                    QC_DEV_ASSERT(off < (size_t)g.jCap);
                     for (int dst = 0; dst < g.nDest; ++dst) g.J[dst][off] = val;
                 }
             }
@@ -517,6 +521,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) jac_dmma_kernel(const DmmaArgs g)
                     if (p >= g.colBegin && p < g.colEnd && lr != 0xFF && lc != 0xFF) {
                         const size_t off = (size_t)g.Q * (p - g.colBegin) + q0 + (lr & 15) + (long long)rf * (lc & 15);
                         const double val = 2.0 * (grc + gcr);
+                        QC_DEV_ASSERT(off < (size_t)g.jCap);
                         for (int dst = 0; dst < g.nDest; ++dst) g.J[dst][off] = val;
                     }
                 }
@@ -591,7 +596,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) jac_dmma_kernel(const DmmaArgs g)
                     for (int nj = 0; nj < NJ; ++nj) {
                         const int o = ot * BN + warp_n * (BN / 2) + nj * 8 + t4 * 2;
                         if (o < g.ldm)
-                            *reinterpret_cast<double2 *>(mbase + (size_t)row * g.ldm + o) =
+                            QC_DEV_ASSERT(row < g.mRows && o + 1 < g.ldm + 1);
+                        *reinterpret_cast<double2 *>(mbase + (size_t)row * g.ldm + o) =
                                 make_double2(acc[mi][nj][0], acc[mi][nj][1]);
                     }
                 }
@@ -1184,6 +1190,7 @@ int launch_jacobian_dmma(DmmaPlanData *d, const JacView &v, cudaStream_t st, int
         DmmaArgs a;
         a.nKc = d->nKc; a.nOt = d->nOt;
         a.colBegin = cb; a.colEnd = ce; a.sym = d->launchSym ? 1 : 0; a.Q = v.Q;
+        a.jCap = (long long)v.Q * (ce - cb);
         a.Wt = d->d_Wt; a.PVt = d->d_PVt; a.CVt = d->d_CVt; a.POt = d->d_POt; a.COt = d->d_COt;
         a.work = d->d_work; a.nWork = (int)d->work.size();
         a.tileTab = d->d_tileTab; a.compTab = d->d_compTab;
