@@ -211,6 +211,20 @@ int qcdmet_plan_get_one_rdm(qcdmet_plan *plan, double *one_rdm);
 int qcdmet_plan_construct_baths(qcdmet_plan *plan, int Nfrag, const int *impStart, const int *impIdx,
                                 const int *numBathReq, double threshold, int *numBath, double *occ, double *bath);
 
+/* Baths AND embedded Hamiltonians of all fragments for an on-site (Hubbard) interaction U sum_x n_x,up n_x,down, in one
+ * call: what the reference's DMET iteration does per fragment with constructbath + localintegrals_hubbard.dmet_oei /
+ * dmet_fock / dmet_tei (src/dmet.py:194-214, src/localintegrals_hubbard.py:88-116; dmet_tei is an O(n^4 N) Python loop).
+ *   hopping[Norb*Norb]: the one-electron matrix (symmetric); impStart/impIdx/numBathReq/threshold/numBath/occ/bath as in
+ *   qcdmet_plan_construct_baths (bath may be NULL).
+ *   Fragment f has cap_f = m_f + min(numBathReq_f, m_f) embedded-orbital slots (impurity orbitals first, then bath orbitals);
+ *   slots of bath orbitals that were not kept are zero.  Blocks are packed fragment after fragment, row-major:
+ *   oei, fock: cap_f^2 doubles each (c^T h c; c^T (h + U/2 diag(core 1-RDM)) c = loc_rhf_fock_bis of the core density);
+ *   tei (or NULL; cap_f <= 16): cap_f^4 doubles, tei[i,j,k,l] = U sum_x c_xi c_xj c_xk c_xl;
+ *   coreElectrons (or NULL): trace of the core 1-RDM per fragment (Nelec_in_imp = Nelec - round(that), src/dmet.py:207). */
+int qcdmet_plan_embed_hubbard(qcdmet_plan *plan, const double *hopping, double U, int Nfrag, const int *impStart,
+                              const int *impIdx, const int *numBathReq, double threshold, int *numBath, double *occ,
+                              double *bath, double *oei, double *fock, double *tei, double *coreElectrons);
+
 /* Levenberg-Marquardt step from the Jacobian resident on the device (no 8 Q P byte D2H):
  *   (J^T J + lambda diag(J^T J)) step = -J^T resid        resid: Q doubles (host), step: ncols doubles (host)
  * cuBLAS DSYRK/DGEMV + cuSOLVER potrf/potrs; J^T J is kept until the next compute, so retries with a

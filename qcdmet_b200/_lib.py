@@ -65,6 +65,9 @@ SIGNATURES = {
                                                    ctypes.c_void_p]),
     "qcdmet_plan_lm_step": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_double, ctypes.c_void_p,
                                            ctypes.c_void_p]),
+    "qcdmet_plan_embed_hubbard": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_double, ctypes.c_int, ctypes.c_void_p,
+                                                 ctypes.c_void_p, ctypes.c_void_p, ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p,
+                                                 ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "qcdmet_plan_set_lm_method": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "qcdmet_plan_gradient": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "qcdmet_plan_num_residuals": (ctypes.c_longlong, [ctypes.c_void_p]),
@@ -437,6 +440,38 @@ class Plan:
         check(self.lib.qcdmet_plan_construct_baths(self.handle, nfrag, _ptr(imp_start), _ptr(imp_idx), _ptr(req),
                                                    float(threshold), _ptr(num_bath), _ptr(occ), _ptr(bath)))
         return num_bath, occ, bath
+
+    def embed_hubbard(self, hopping, hubbard_u, imp_start, imp_idx, num_bath_req=None, threshold=1e-13, want_tei=True,
+                      want_bath=True):
+        """Baths and embedded Hubbard Hamiltonians of all fragments (qcdmet_plan_embed_hubbard).  Returns a dict with
+        num_bath [F], occ [S], bath [S, Norb] or None, core_electrons [F] and per-fragment lists oei / fock (n x n) and
+        tei (n x n x n x n or None), n = impurity + kept bath orbitals."""
+        imp_start, imp_idx = as_i32(imp_start), as_i32(imp_idx)
+        nfrag = imp_start.size - 1
+        m = np.diff(imp_start)
+        req = m.copy() if num_bath_req is None else np.minimum(np.asarray(num_bath_req, dtype=np.int64), m)
+        cap = (m + req).astype(np.int64)
+        off2 = np.concatenate([[0], np.cumsum(cap ** 2)])
+        off4 = np.concatenate([[0], np.cumsum(cap ** 4)])
+        total = int(imp_start[-1])
+        num_bath = np.zeros(nfrag, dtype=np.int32)
+        occ = np.zeros(total, dtype=np.float64)
+        bath = np.zeros((total, self.norb), dtype=np.float64) if want_bath else None
+        oei = np.zeros(int(off2[-1]), dtype=np.float64)
+        fock = np.zeros(int(off2[-1]), dtype=np.float64)
+        tei = np.zeros(int(off4[-1]), dtype=np.float64) if want_tei else None
+        core = np.zeros(nfrag, dtype=np.float64)
+        h = as_f64(hopping)
+        check(self.lib.qcdmet_plan_embed_hubbard(self.handle, _ptr(h), float(hubbard_u), nfrag, _ptr(imp_start), _ptr(imp_idx),
+                                                 _ptr(as_i32(num_bath_req)), float(threshold), _ptr(num_bath), _ptr(occ),
+                                                 _ptr(bath), _ptr(oei), _ptr(fock), _ptr(tei), _ptr(core)))
+        out = {"num_bath": num_bath, "occ": occ, "bath": bath, "core_electrons": core, "oei": [], "fock": [], "tei": []}
+        for f in range(nfrag):
+            c, n = int(cap[f]), int(m[f] + num_bath[f])
+            out["oei"].append(oei[off2[f]:off2[f + 1]].reshape(c, c)[:n, :n].copy())
+            out["fock"].append(fock[off2[f]:off2[f + 1]].reshape(c, c)[:n, :n].copy())
+            out["tei"].append(None if tei is None else tei[off4[f]:off4[f + 1]].reshape(c, c, c, c)[:n, :n, :n, :n].copy())
+        return out
 
     def eigenvalues(self):
         out = np.empty(self.norb, dtype=np.float64)

@@ -1683,6 +1683,95 @@ int qcdmet_plan_construct_baths(qcdmet_plan *p, int Nfrag, const int *impStart, 
     return QCDMET_OK;
 }
 
+/* Baths AND embedded Hamiltonians of Nfrag impurities for an on-site (Hubbard) interaction, in one call
+ * (src/localintegrals_hubbard.py:88-116 dmet_oei / dmet_fock / dmet_tei).  See kernels_bath.cu. */
+int qcdmet_plan_embed_hubbard(qcdmet_plan *p, const double *hopping, double U, int Nfrag, const int *impStart, const int *impIdx,
+                              const int *numBathReq, double threshold, int *numBath, double *occ, double *bath,
+                              double *oei, double *fock, double *tei, double *coreElectrons)
+{
+    QC_CHECK(p != nullptr && hopping != nullptr && numBath != nullptr && oei != nullptr && fock != nullptr, QCDMET_E_ARG,
+             "plan, hopping, numBath, oei or fock is NULL");
+    QC_CHECK(p->have_orbitals, QCDMET_E_STATE, "plan has no orbitals: call set_h0/set_orbitals first");
+    QC_CHECK(Nfrag >= 0 && (Nfrag == 0 || (impStart != nullptr && impStart[0] == 0)), QCDMET_E_ARG, "impStart[0] must be 0");
+    if (Nfrag == 0) return QCDMET_OK;
+    int maxM = 0, nbMax = 0;
+    std::vector<int> cap(Nfrag);
+    std::vector<long long> off2(Nfrag), off4(Nfrag);
+    long long tot2 = 0, tot4 = 0;
+    for (int f = 0; f < Nfrag; ++f) {
+        const int m = impStart[f + 1] - impStart[f];
+        QC_CHECK(m >= 0 && m <= QCDMET_BATH_MAX_IMP, QCDMET_E_ARG, "fragment %d has %d impurity orbitals (0 .. %d)", f, m,
+                 QCDMET_BATH_MAX_IMP);
+        const int req = numBathReq ? numBathReq[f] : m;
+        QC_CHECK(req >= 0, QCDMET_E_ARG, "numBathReq[%d] is negative", f);
+        maxM = std::max(maxM, m);
+        nbMax = std::max(nbMax, std::min(req, m));
+        cap[f] = m + std::min(req, m);
+        QC_CHECK(!tei || cap[f] <= QCDMET_EMBED_MAX_TEI_ORBS, QCDMET_E_ARG,
+                 "two-electron block requested for fragment %d with %d embedded orbitals (at most %d): pass tei = NULL", f, cap[f],
+                 QCDMET_EMBED_MAX_TEI_ORBS);
+        off2[f] = tot2;
+        off4[f] = tei ? tot4 : -1;
+        tot2 += (long long)cap[f] * cap[f];
+        tot4 += (long long)cap[f] * cap[f] * cap[f] * cap[f];
+    }
+    const int S = impStart[Nfrag];
+    QC_CHECK(S > 0 && impIdx != nullptr, QCDMET_E_ARG, "no impurity orbitals");
+    std::vector<int> rowFrag(S);
+    for (int f = 0; f < Nfrag; ++f)
+        for (int a = impStart[f]; a < impStart[f + 1]; ++a) {
+            QC_CHECK(impIdx[a] >= 0 && impIdx[a] < p->N, QCDMET_E_ARG, "impIdx[%d] = %d out of range", a, impIdx[a]);
+            for (int b = impStart[f]; b < a; ++b)
+                QC_CHECK(impIdx[b] != impIdx[a], QCDMET_E_ARG, "orbital %d listed twice in fragment %d", impIdx[a], f);
+            rowFrag[a] = f;
+        }
+    DeviceGuard guard(p->device);
+    const int N = p->N;
+    int *d_impStart = nullptr, *d_impIdx = nullptr, *d_rowFrag = nullptr, *d_req = nullptr, *d_kept = nullptr, *d_sweeps = nullptr,
+        *d_cap = nullptr;
+    long long *d_off2 = nullptr, *d_off4 = nullptr;
+    double *d_Y = nullptr, *d_occ = nullptr, *d_B = nullptr, *d_H = nullptr, *d_HB = nullptr, *d_dd = nullptr, *d_oei = nullptr,
+           *d_fock = nullptr, *d_tei = nullptr, *d_ct = nullptr;
+    int rc = QCDMET_OK;
+    std::vector<int> sweeps(Nfrag, 0);
+    do {
+        if ((rc = dev_alloc_copy(&d_impStart, impStart, (size_t)Nfrag + 1)) || (rc = dev_alloc_copy(&d_impIdx, impIdx, (size_t)S)) ||
+            (rc = dev_alloc_copy(&d_rowFrag, rowFrag.data(), (size_t)S)) || (rc = dev_alloc_copy(&d_cap, cap.data(), (size_t)Nfrag)) ||
+            (rc = dev_alloc_copy(&d_off2, off2.data(), (size_t)Nfrag)) || (rc = dev_alloc_copy(&d_off4, off4.data(), (size_t)Nfrag))) break;
+        if (numBathReq && (rc = dev_alloc_copy(&d_req, numBathReq, (size_t)Nfrag))) break;
+        if ((rc = dev_alloc(&d_kept, (size_t)Nfrag)) || (rc = dev_alloc(&d_sweeps, (size_t)Nfrag)) ||
+            (rc = dev_alloc(&d_Y, (size_t)S * p->ldo)) || (rc = dev_alloc(&d_occ, (size_t)S)) || (rc = dev_alloc(&d_B, (size_t)S * N)) ||
+            (rc = dev_alloc_copy(&d_H, hopping, (size_t)N * N)) || (rc = dev_alloc(&d_HB, (size_t)S * N)) ||
+            (rc = dev_alloc(&d_dd, (size_t)N)) || (rc = dev_alloc(&d_oei, (size_t)tot2)) || (rc = dev_alloc(&d_fock, (size_t)tot2)) ||
+            (rc = dev_alloc(&d_ct, (size_t)Nfrag))) break;
+        if (tei && (rc = dev_alloc(&d_tei, (size_t)tot4))) break;
+        if ((rc = launch_construct_baths(p->blas, p->d_CoT, p->ldo, N, p->no, Nfrag, S, maxM, d_impStart, d_impIdx, d_rowFrag, d_req,
+                                         threshold, d_Y, d_occ, d_kept, d_sweeps, d_B, p->stream))) break;
+        if ((rc = launch_embed_hubbard(p->blas, p->d_CoT, p->ldo, N, p->no, Nfrag, S, d_H, U, d_impStart, d_impIdx, d_kept, d_cap, d_off2,
+                                       d_off4, nbMax, d_B, d_occ, d_HB, d_dd, d_oei, d_fock, d_tei, d_ct, p->stream))) break;
+        bool ok = cudaMemcpyAsync(numBath, d_kept, sizeof(int) * (size_t)Nfrag, cudaMemcpyDeviceToHost, p->stream) == cudaSuccess &&
+                  cudaMemcpyAsync(sweeps.data(), d_sweeps, sizeof(int) * (size_t)Nfrag, cudaMemcpyDeviceToHost, p->stream) == cudaSuccess &&
+                  cudaMemcpyAsync(oei, d_oei, sizeof(double) * (size_t)tot2, cudaMemcpyDeviceToHost, p->stream) == cudaSuccess &&
+                  cudaMemcpyAsync(fock, d_fock, sizeof(double) * (size_t)tot2, cudaMemcpyDeviceToHost, p->stream) == cudaSuccess;
+        if (ok && occ) ok = cudaMemcpyAsync(occ, d_occ, sizeof(double) * (size_t)S, cudaMemcpyDeviceToHost, p->stream) == cudaSuccess;
+        if (ok && bath) ok = cudaMemcpyAsync(bath, d_B, sizeof(double) * (size_t)S * N, cudaMemcpyDeviceToHost, p->stream) == cudaSuccess;
+        if (ok && tei) ok = cudaMemcpyAsync(tei, d_tei, sizeof(double) * (size_t)tot4, cudaMemcpyDeviceToHost, p->stream) == cudaSuccess;
+        if (ok && coreElectrons)
+            ok = cudaMemcpyAsync(coreElectrons, d_ct, sizeof(double) * (size_t)Nfrag, cudaMemcpyDeviceToHost, p->stream) == cudaSuccess;
+        if (!ok || cudaStreamSynchronize(p->stream) != cudaSuccess) {
+            set_error("embedding failed: %s", cudaGetErrorString(cudaGetLastError()));
+            rc = QCDMET_E_CUDA;
+        }
+    } while (0);
+    cudaFree(d_impStart); cudaFree(d_impIdx); cudaFree(d_rowFrag); cudaFree(d_req); cudaFree(d_kept); cudaFree(d_sweeps); cudaFree(d_cap);
+    cudaFree(d_off2); cudaFree(d_off4); cudaFree(d_Y); cudaFree(d_occ); cudaFree(d_B); cudaFree(d_H); cudaFree(d_HB); cudaFree(d_dd);
+    cudaFree(d_oei); cudaFree(d_fock); cudaFree(d_tei); cudaFree(d_ct);
+    QC_TRY(rc);
+    for (int f = 0; f < Nfrag; ++f)
+        QC_CHECK(sweeps[f] < 60, QCDMET_E_SOLVER, "Jacobi iteration of fragment %d did not converge in 60 sweeps", f);
+    return QCDMET_OK;
+}
+
 long long qcdmet_plan_num_residuals(qcdmet_plan *p) { return p ? p->Q : -1; }
 int qcdmet_plan_kernel_used(qcdmet_plan *p) { return p ? p->kernel_used : -1; }
 int qcdmet_plan_launches(qcdmet_plan *p)

@@ -102,6 +102,12 @@ int launch_construct_baths(cublasHandle_t blas, const double *CoT, int ldo, int 
                            double threshold, double *d_Y, double *d_occ, int *d_numKept, int *d_sweeps, double *d_B,
                            cudaStream_t st);
 
+#define QCDMET_EMBED_MAX_TEI_ORBS 16     // embedded orbitals per fragment up to which the two-electron block is returned
+int launch_embed_hubbard(cublasHandle_t blas, const double *CoT, int ldo, int N, int no, int F, int S, const double *d_H, double U,
+                         const int *d_impStart, const int *d_impIdx, const int *d_numKept, const int *d_cap,
+                         const long long *d_off2, const long long *d_off4, int nbMax, const double *d_B, const double *d_occ, double *d_HB,
+                         double *d_ddiag, double *d_oei, double *d_fock, double *d_tei, double *d_coreTrace, cudaStream_t st);
+
 // Destinations of the fused all-gather: every rank of a node maps every rank's full Jacobian buffer;
 // the DMMA kernel stores each element it produces into all of them (NVLink peer stores).
 #define QCDMET_MAX_PEERS 8

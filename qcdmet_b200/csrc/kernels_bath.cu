@@ -65,6 +65,9 @@ __global__ void __launch_bounds__(BATH_THREADS) bath_eigen_kernel(
     __syncthreads();
 
     // ---- parallel cyclic Jacobi: mp - 1 steps per sweep, npairs disjoint rotations per step
+    const double tol = 4.0 * 2.220446049250313e-16 * sqrt((double)m);
+    double scale = 0.0;
+    for (int i = 0; i < m; ++i) scale = fmax(scale, fabs(A[i * ld + i]));
     int sweeps = 0;
     for (; sweeps < BATH_MAX_SWEEPS; ++sweeps) {
         if (tid == 0) *flag = 0;
@@ -79,7 +82,10 @@ __global__ void __launch_bounds__(BATH_THREADS) bath_eigen_kernel(
                 double c = 1.0, s = 0.0;
                 if (q < m) {
                     const double app = A[p * ld + p], aqq = A[q * ld + q], apq = A[p * ld + q];
-                    if (fabs(apq) > 1e-16 * sqrt(fabs(app) * fabs(aqq)) && fabs(apq) > 1e-290) {
+                    // rotate until |a_pq| <= tol max_i a_ii: absolute accuracy of a few ulps of the largest eigenvalue
+                    // (<= 1 for a projector block).  A criterion relative to sqrt(a_pp a_qq) never ends in the null space
+                    // of P_II (more impurity orbitals than occupied orbitals), where all three are rounding noise.
+                    if (fabs(apq) > tol * scale) {
                         const double theta = (aqq - app) / (2.0 * apq);
                         const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
                         c = 1.0 / sqrt(t * t + 1.0);
@@ -227,6 +233,175 @@ int launch_construct_baths(cublasHandle_t blas, const double *CoT, int ldo, int 
     cublasStatus_t cs = cublasDgemm(blas, CUBLAS_OP_T, CUBLAS_OP_N, N, S, no, &one, CoT, ldo, d_Y, ldo, &zero, d_B, N);
     QC_CHECK(cs == CUBLAS_STATUS_SUCCESS, QCDMET_E_CUDA, "cublasDgemm (bath orbitals) failed: %d", (int)cs);
     bath_normalise_kernel<<<S, 256, 0, st>>>(d_B, N, d_impStart, d_impIdx, d_rowFrag, d_numKept);
+    QC_CUDA(cudaGetLastError());
+    return QCDMET_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------
+// Embedded Hamiltonians of all fragments for an on-site (Hubbard) interaction, from the device baths
+// (src/localintegrals_hubbard.py:88-116: dmet_oei, dmet_fock with loc_rhf_fock_bis(core 1-RDM), dmet_tei, whose
+// O(n^4 N) Python loop per fragment is the second per-iteration wall after the bath eigh).  With c = [unit vectors of
+// the impurity orbitals | bath orbitals] (bath orbitals vanish on the impurity):
+//   oei  = c^T h c                     imp-imp: h[i,j];  imp-bath: (B h)[k, i];  bath-bath: B (h B^T)
+//   fock = oei + (U/2) c^T diag(core) c, core[x] = D[x,x] - sum_k occ_k B[k,x]^2 on the environment, 0 on the impurity:
+//          only the bath-bath block changes
+//   tei[a,b,c,d] = U sum_x c_xa c_xb c_xc c_xd: U on the impurity diagonal, U sum_x B_k B_l B_p B_q on the bath block,
+//          zero wherever impurity and bath indices mix
+// HB = B h comes from one library DGEMM for all fragments; this kernel does the per-fragment reductions.
+// ------------------------------------------------------------------------------------------
+namespace {
+
+constexpr int EMB_THREADS = 256;
+constexpr int EMB_XCH = 128;            // lattice orbitals per staged chunk
+constexpr int EMB_MAXB = 8;             // bath orbitals per fragment for which the two-electron block is built
+
+__global__ void rdm_diag_kernel(const double *__restrict__ CoT, int ldo, int no, int N, double *__restrict__ ddiag)
+{
+    const int x = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32, lane = threadIdx.x & 31;
+    if (x >= N) return;
+    const double *row = CoT + (size_t)x * ldo;
+    double s = 0.0;
+    for (int o = lane; o < no; o += 32) s += row[o] * row[o];
+    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    if (lane == 0) ddiag[x] = 2.0 * s;
+}
+
+// one CTA per fragment; outputs are packed per fragment with capacity ncap = m + (requested bath orbitals)
+__global__ void __launch_bounds__(EMB_THREADS) embed_hubbard_kernel(
+    const double *__restrict__ H /* N x N symmetric */, const double *__restrict__ B /* [S][N] */,
+    const double *__restrict__ HB /* [S][N] = B h */, const double *__restrict__ ddiag, const double *__restrict__ occ,
+    int N, double U, const int *__restrict__ impStart, const int *__restrict__ impIdx, const int *__restrict__ numKept,
+    const int *__restrict__ cap /* [F] */, const long long *__restrict__ off2 /* [F] */, const long long *__restrict__ off4 /* [F], -1 = no tei */,
+    int nbMax, double *__restrict__ oei, double *__restrict__ fock, double *__restrict__ tei, double *__restrict__ coreTrace)
+{
+    extern __shared__ __align__(16) unsigned char esm[];  // bath rows of the chunk and their images under h: [nbMax][XCH + 1] each
+    __shared__ double sCore[EMB_XCH];
+    __shared__ double red[EMB_THREADS / 32];
+    typedef double Row[EMB_XCH + 1];
+    Row *sB = reinterpret_cast<Row *>(esm);
+    Row *sHB = sB + nbMax;
+    const int f = blockIdx.x, tid = threadIdx.x;
+    const int r0 = impStart[f], m = impStart[f + 1] - r0, nb = numKept[f], n = cap[f];
+    QC_DEV_ASSERT(nb <= nbMax && m + nb <= n);
+    double *o1 = oei + off2[f], *f1 = fock + off2[f];
+    for (int i = tid; i < n * n; i += EMB_THREADS) { o1[i] = 0.0; f1[i] = 0.0; }
+    const bool wantTei = off4[f] >= 0;
+    double *t4 = wantTei ? tei + off4[f] : nullptr;
+    if (wantTei)
+        for (long long i = tid; i < (long long)n * n * n * n; i += EMB_THREADS) t4[i] = 0.0;
+    __syncthreads();
+    // impurity-impurity and impurity-bath blocks (row-major n x n)
+    for (int idx = tid; idx < m * m; idx += EMB_THREADS) {
+        const int a = idx / m, b = idx % m;
+        const double v = H[(size_t)impIdx[r0 + a] * N + impIdx[r0 + b]];
+        o1[a * n + b] = v; f1[a * n + b] = v;
+    }
+    for (int idx = tid; idx < m * nb; idx += EMB_THREADS) {
+        const int a = idx / nb, k = idx % nb;
+        const double v = HB[(size_t)(r0 + k) * N + impIdx[r0 + a]];
+        o1[a * n + (m + k)] = v; o1[(m + k) * n + a] = v;
+        f1[a * n + (m + k)] = v; f1[(m + k) * n + a] = v;
+    }
+    if (wantTei)
+        for (int a = tid; a < m; a += EMB_THREADS) t4[(((long long)a * n + a) * n + a) * n + a] = U;
+    // bath-bath blocks: reductions over the lattice in chunks
+    const int nbb = nb * nb;
+    const int per2 = (nbb + EMB_THREADS - 1) / EMB_THREADS;           // (k, l) pairs per thread: 1 for nb <= 16
+    const long long n4 = wantTei ? (long long)nbb * nbb : 0;
+    const int per4 = (int)((n4 + EMB_THREADS - 1) / EMB_THREADS);     // <= 16 for nb <= 8
+    double accO[16], accF[16], accT[16];
+    for (int i = 0; i < 16; ++i) accO[i] = accF[i] = accT[i] = 0.0;
+    double ctr = 0.0;
+    for (int x0 = 0; x0 < N; x0 += EMB_XCH) {
+        const int nx = min(EMB_XCH, N - x0);
+        for (int idx = tid; idx < nb * EMB_XCH; idx += EMB_THREADS) {
+            const int k = idx / EMB_XCH, xx = idx % EMB_XCH;
+            sB[k][xx] = xx < nx ? B[(size_t)(r0 + k) * N + x0 + xx] : 0.0;
+            sHB[k][xx] = xx < nx ? HB[(size_t)(r0 + k) * N + x0 + xx] : 0.0;
+        }
+        __syncthreads();
+        // core occupation of the chunk's orbitals: D[x,x] - sum_k occ_k B[k,x]^2 (bath rows are zero on the impurity, where
+        // the core density vanishes: mask those orbitals explicitly)
+        for (int xx = tid; xx < EMB_XCH; xx += EMB_THREADS) {
+            double c = 0.0;
+            if (xx < nx) {
+                c = ddiag[x0 + xx];
+                for (int k = 0; k < nb; ++k) c -= occ[r0 + k] * sB[k][xx] * sB[k][xx];
+                for (int a = 0; a < m; ++a)
+                    if (impIdx[r0 + a] == x0 + xx) c = 0.0;
+            }
+            sCore[xx] = c;
+            ctr += c;
+        }
+        __syncthreads();
+        for (int q = 0; q < per2 && q < 16; ++q) {
+            const int pr = tid + q * EMB_THREADS;
+            if (pr >= nbb) break;
+            const int k = pr / nb, l = pr % nb;
+            double so = 0.0, sf = 0.0;
+            for (int xx = 0; xx < EMB_XCH; ++xx) {
+                so = fma(sB[k][xx], sHB[l][xx], so);
+                sf = fma(sB[k][xx] * sB[l][xx], sCore[xx], sf);
+            }
+            accO[q] += so; accF[q] += sf;
+        }
+        for (int q = 0; q < per4 && q < 16; ++q) {
+            const long long id = tid + (long long)q * EMB_THREADS;
+            if (id >= n4) break;
+            const int kl = (int)(id / nbb), pq = (int)(id % nbb);
+            const int k = kl / nb, l = kl % nb, p = pq / nb, qq = pq % nb;
+            double st = 0.0;
+            for (int xx = 0; xx < EMB_XCH; ++xx) st = fma(sB[k][xx] * sB[l][xx], sB[p][xx] * sB[qq][xx], st);
+            accT[q] += st;
+        }
+        __syncthreads();
+    }
+    for (int q = 0; q < per2 && q < 16; ++q) {
+        const int pr = tid + q * EMB_THREADS;
+        if (pr >= nbb) break;
+        const int k = pr / nb, l = pr % nb;
+        o1[(m + k) * n + (m + l)] = accO[q];
+        f1[(m + k) * n + (m + l)] = accO[q] + 0.5 * U * accF[q];
+    }
+    for (int q = 0; q < per4 && q < 16; ++q) {
+        const long long id = tid + (long long)q * EMB_THREADS;
+        if (id >= n4) break;
+        const int kl = (int)(id / nbb), pq = (int)(id % nbb);
+        const int k = kl / nb, l = kl % nb, p = pq / nb, qq = pq % nb;
+        t4[((((long long)(m + k)) * n + (m + l)) * n + (m + p)) * n + (m + qq)] = U * accT[q];
+    }
+    // trace of the core 1-RDM (electrons outside the embedded problem)
+    for (int off = 16; off > 0; off >>= 1) ctr += __shfl_xor_sync(0xffffffffu, ctr, off);
+    if ((tid & 31) == 0) red[tid >> 5] = ctr;
+    __syncthreads();
+    if (tid == 0) {
+        double t = 0.0;
+        for (int w = 0; w < EMB_THREADS / 32; ++w) t += red[w];
+        coreTrace[f] = t;
+    }
+}
+
+}  // namespace
+
+// d_B, d_occ, d_numKept: outputs of launch_construct_baths (device).  d_H: hopping matrix on the device.  d_HB: scratch [S][N].
+int launch_embed_hubbard(cublasHandle_t blas, const double *CoT, int ldo, int N, int no, int F, int S, const double *d_H, double U,
+                         const int *d_impStart, const int *d_impIdx, const int *d_numKept, const int *d_cap,
+                         const long long *d_off2, const long long *d_off4, int nbMax, const double *d_B, const double *d_occ, double *d_HB,
+                         double *d_ddiag, double *d_oei, double *d_fock, double *d_tei, double *d_coreTrace, cudaStream_t st)
+{
+    if (F == 0 || S == 0) return QCDMET_OK;
+    rdm_diag_kernel<<<(N + 7) / 8, 256, 0, st>>>(CoT, ldo, no, N, d_ddiag);
+    QC_CUDA(cudaGetLastError());
+    // HB (row-major [S][N]) = B h:  column-major  HB_cm (N x S) = h (N x N, symmetric) B_cm (N x S)
+    const double one = 1.0, zero = 0.0;
+    cublasSetStream(blas, st);
+    cublasStatus_t cs = cublasDgemm(blas, CUBLAS_OP_N, CUBLAS_OP_N, N, S, N, &one, d_H, N, d_B, N, &zero, d_HB, N);
+    QC_CHECK(cs == CUBLAS_STATUS_SUCCESS, QCDMET_E_CUDA, "cublasDgemm (h times bath orbitals) failed: %d", (int)cs);
+    const size_t smem = (size_t)2 * std::max(nbMax, 1) * (EMB_XCH + 1) * sizeof(double);
+    QC_CUDA(cudaFuncSetAttribute(embed_hubbard_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    embed_hubbard_kernel<<<F, EMB_THREADS, smem, st>>>(d_H, d_B, d_HB, d_ddiag, d_occ, N, U, d_impStart, d_impIdx, d_numKept, d_cap,
+                                                      d_off2, d_off4, nbMax, d_oei, d_fock, d_tei, d_coreTrace);
     QC_CUDA(cudaGetLastError());
     return QCDMET_OK;
 }

@@ -595,10 +595,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) jac_dmma_kernel(const DmmaArgs g)
 #pragma unroll
                     for (int nj = 0; nj < NJ; ++nj) {
                         const int o = ot * BN + warp_n * (BN / 2) + nj * 8 + t4 * 2;
-                        if (o < g.ldm)
-                            QC_DEV_ASSERT(row < g.mRows && o + 1 < g.ldm + 1);
-                        *reinterpret_cast<double2 *>(mbase + (size_t)row * g.ldm + o) =
+                        if (o < g.ldm) {
+                            QC_DEV_ASSERT(row < g.mRows);
+                            *reinterpret_cast<double2 *>(mbase + (size_t)row * g.ldm + o) =
                                 make_double2(acc[mi][nj][0], acc[mi][nj][1]);
+                        }
                     }
                 }
                 continue;

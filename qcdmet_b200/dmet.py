@@ -59,6 +59,7 @@ class dmet:
             assert self.SCmethod in ('BFGS', 'NONE')
         self.solver = solver
         self.bath_on_gpu = False          # doexact: baths of all fragments from one device call (helper.constructbaths)
+        self.embed_on_gpu = False         # ... and, for on-site (Hubbard) integrals, the embedded Hamiltonians too
         self._bath_cache = None
         self.solver_threads = 1            # > 1: the embedded problems of one doexact pass are solved in a thread pool
         self.gpu_residual = True      # residual blocks from the device eigensolve shared with the Jacobian
@@ -159,8 +160,17 @@ class dmet:
         dense-FCI stand-in qcdmet_b200.fci_solver.solve).  The DET / CASCI / incomplete-tiling branches
         (src/dmet.py:259-337) need pyscf and are not restated."""
         maxiter = 1 if self.TransInv else len(self.impClust)
-        device_baths = None
-        if self.bath_on_gpu:
+        device_baths = device_emb = None
+        if self.embed_on_gpu:
+            # baths + embedded one- and two-electron integrals of every fragment from one device call
+            assert hasattr(self.ints, "HubbardU"), "embed_on_gpu needs an on-site (Hubbard) integral provider"
+            key = np.asarray(self.umat).tobytes()
+            if self._bath_cache is None or self._bath_cache[0] != key:
+                req = None if self.BATH_ORBS is None else [self.BATH_ORBS[c] for c in range(maxiter)]
+                self._bath_cache = (key, self.helper.embed_hubbard(self.umat, self.impClust[:maxiter], req,
+                                                                   cache_key=self._umat_key(self.square2flat(self.umat))))
+            device_emb = self._bath_cache[1]
+        elif self.bath_on_gpu:
             # one eigensolve (shared with the residual / Jacobian at this umat) and one batched bath call per umat;
             # the Newton iteration on the chemical potential re-enters doexact with the same umat
             key = np.asarray(self.umat).tobytes()
@@ -169,7 +179,7 @@ class dmet:
                 self._bath_cache = (key, self.helper.constructbaths(self.umat, self.impClust[:maxiter], req,
                                                                     cache_key=self._umat_key(self.square2flat(self.umat))))
             OneRDM, device_baths = self._bath_cache[1]
-        else:
+        elif not self.embed_on_gpu:
             OneRDM = self.helper.construct1RDM_loc(self.doSCF, self.umat)
         self.energy = 0.0
         self.imp_1RDM = []
@@ -185,6 +195,20 @@ class dmet:
             numImpOrbs = int(np.sum(impurityOrbs))
             numBathOrbs = numImpOrbs if self.BATH_ORBS is None else self.BATH_ORBS[counter]
             core_cutoff = 0.01 if self.BATH_ORBS is None else 0.5
+            if device_emb is not None:
+                numBathOrbs = int(device_emb["num_bath"][counter])
+                r0, r1 = device_emb["imp_start"][counter], device_emb["imp_start"][counter + 1]
+                left = device_emb["occ"][r0 + numBathOrbs:r1]
+                if np.any((left > core_cutoff) & (left < 2.0 - core_cutoff)):
+                    raise AssertionError("Bad DMET bath orbital selection: bath orbital with occupation "
+                                         f"{left} would go into the environment")
+                Norb_in_imp = numImpOrbs + numBathOrbs
+                self.dmetOrbs.append(device_emb["active"][counter])
+                Nelec_in_imp = int(round(self.ints.Nelec - device_emb["core_electrons"][counter]))
+                problems.append((0.0, device_emb["oei"][counter], device_emb["fock"][counter], device_emb["tei"][counter],
+                                 Norb_in_imp, Nelec_in_imp, numImpOrbs, chempot_imp))
+                remainingOrbs -= impurityOrbs
+                continue
             if device_baths is not None:
                 # loc2dmet[:, :imp + bath] and the core density without the pure-environment orbitals: for an
                 # idempotent D/2, D_env,env = sum_bath occ_k b_k b_k^T + (core 1-RDM)

@@ -133,6 +133,28 @@ class qcdmethelper:
             out.append((nb, active, occ[imp_start[f]:imp_start[f + 1]].copy()))
         return (plan.one_rdm() if want_one_rdm else None), out
 
+    def embed_hubbard(self, umat_loc, impurityOrbsList, numBathOrbsList=None, threshold=1e-13, cache_key=None):
+        """constructbaths + the embedded Hamiltonians of every fragment in one device call, for integral providers
+        with an on-site interaction (localintegrals_hubbard: attributes activeOEI, HubbardU).  Replaces, per
+        fragment, constructbath and dmet_oei / dmet_fock / dmet_tei (src/localintegrals_hubbard.py:88-116).
+        Returns the dict of _lib.Plan.embed_hubbard plus 'active': loc2dmet[:, :n] per fragment."""
+        imps = [np.flatnonzero(np.abs(np.asarray(v).reshape(-1)).astype(int)) for v in impurityOrbsList]
+        imp_start = np.concatenate([[0], np.cumsum([i.size for i in imps])]).astype(np.int32)
+        imp_idx = np.concatenate(imps).astype(np.int32)
+        plan = self._plan_with_orbitals(umat_loc, imp_start, None, imp_idx, None, cache_key)
+        req = None if numBathOrbsList is None else np.asarray(numBathOrbsList, dtype=np.int32)
+        out = plan.embed_hubbard(self.locints.activeOEI, self.locints.HubbardU, imp_start, imp_idx, req, threshold)
+        n = self.locints.Norbs
+        out["active"] = []
+        for f, imp in enumerate(imps):
+            nb = int(out["num_bath"][f])
+            active = np.zeros((n, imp.size + nb))
+            active[imp, np.arange(imp.size)] = 1.0
+            active[:, imp.size:] = out["bath"][imp_start[f]:imp_start[f] + nb].T
+            out["active"].append(active)
+        out["imp_start"] = imp_start
+        return out
+
     def _oei(self, doSCF, umat_loc, NOrotation):
         if doSCF:
             raise NotImplementedError("doSCF=True is outside the response hot path (src/dmet.py:44)")

@@ -45,6 +45,8 @@ def random_problem(n, num_pairs, sizes, seed):
     (97, 41, [13, 7, 8, 1, 3]),                 # odd sizes: padded Jacobi index
     (150, 60, [52, 24, 29]),                    # sn2-like unit sizes (examples/sn2.py:74)
     (64, 32, [4] * 16),                         # tiling of all orbitals
+    (60, 10, [20, 13, 4]),                      # more impurity orbitals than occupied orbitals: rank-deficient P_II
+    (60, 49, [20, 13, 4]),                      # ... than virtual orbitals: eigenvalues 1 of P_II
 ])
 def test_baths_match_host_constructbath(n, num_pairs, sizes):
     h0, imp_start, imp_idx = random_problem(n, num_pairs, sizes, seed=11 + n)
@@ -229,3 +231,55 @@ def test_fit_imp_bath_jacobian_from_device_baths():
         scale = np.outer(sg, sg).reshape(-1, order="F")          # residual (a, b) of the block, column-major
         assert np.abs(jac[off:off + nb * nb] * scale[:, None] - ref[off:off + nb * nb]).max() <= 1e-10
         off += nb * nb
+
+
+@pytest.mark.parametrize("l,u", [(8, 4.0), (24, 2.0)])
+def test_embedded_hubbard_hamiltonians_match_host_transforms(l, u):
+    """qcdmet_plan_embed_hubbard against localintegrals_hubbard.dmet_oei / dmet_fock / dmet_tei evaluated on the host
+    with the SAME (device) bath orbitals: every fragment of the l x l lattice, 2 x 2 impurities."""
+    n = l * l
+    hop = wl.hubbard2d_hopping(l, l)
+    ints = lh.localintegrals_hubbard(hop, u, n)
+    w = wl.hubbard24(l=l)
+    imp_start, imp_idx = w.row_start, w.row_idx
+    plan = plan_for(ints.loc_rhf_fock(), n // 2, imp_start, imp_idx)
+    plan.embed_hubbard(hop, u, imp_start[:2], imp_idx[:4])            # warm-up
+    t0 = time.perf_counter()
+    emb = plan.embed_hubbard(hop, u, imp_start, imp_idx)
+    t_dev = time.perf_counter() - t0
+    one = plan.one_rdm()
+    nfrag = len(imp_start) - 1
+    t_host = 0.0
+    for f in ([0, 7, nfrag - 1] if l > 8 else range(nfrag)):
+        idx = imp_idx[imp_start[f]:imp_start[f + 1]]
+        nb = int(emb["num_bath"][f])
+        bath = emb["bath"][imp_start[f]:imp_start[f] + nb].T
+        active = np.concatenate([np.eye(n)[:, idx], bath], axis=1)
+        occ = emb["occ"][imp_start[f]:imp_start[f] + nb]
+        env = np.setdiff1d(np.arange(n), idx)
+        core = np.zeros((n, n))
+        core[np.ix_(env, env)] = (one - (bath * occ) @ bath.T)[np.ix_(env, env)]
+        t0 = time.perf_counter()
+        oei, fock, tei = ints.dmet_oei(active, 4 + nb), ints.dmet_fock(active, 4 + nb, core), ints.dmet_tei(active, 4 + nb)
+        t_host += time.perf_counter() - t0
+        assert np.abs(emb["oei"][f] - oei).max() <= 1e-11
+        assert np.abs(emb["fock"][f] - fock).max() <= 1e-11
+        assert np.abs(emb["tei"][f] - tei).max() <= 1e-11
+        assert abs(emb["core_electrons"][f] - np.trace(core)) <= 1e-9
+        assert int(round(n - emb["core_electrons"][f])) == 8
+    print(f"\nembedding of {nfrag} fragments (N = {n}): device {t_dev * 1e3:.2f} ms for all (baths included); host transforms "
+          f"{t_host * 1e3:.1f} ms for the checked fragments alone")
+    plan.close()
+
+
+@pytest.mark.parametrize("case", ["chain12_U4_imp_only", "chain12_U4_TI_bath"])
+def test_dmet_loop_with_device_embedding(case):
+    """The whole loop with baths AND embedded integrals from the device: same converged energy and umat."""
+    ref = build(case, dmet_mod.dmet)
+    e_ref = ref.doselfconsistent()
+    dev = build(case, dmet_mod.dmet)
+    dev.embed_on_gpu = True
+    e_dev = dev.doselfconsistent()
+    assert dev.iterations == ref.iterations
+    assert abs(e_dev - e_ref) <= 1e-8
+    assert np.abs(dev.umat - ref.umat).max() <= 1e-7
