@@ -2,7 +2,7 @@
 # round-2 full check on one GPU: smoke, whole GPU suite, bench lines of every shape, ncu launch list + captures
 set -u
 mkdir -p gpurun_out
-TAG=${TAG:-r2n}
+TAG=${TAG:-r2t}
 timeout 180 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${TAG}_smoke.log 2>&1
 echo "smoke rc=$?"; tail -3 gpurun_out/${TAG}_smoke.log
 timeout 1500 python -m pytest tests -m gpu -q --tb=short --durations=12 > gpurun_out/${TAG}_pytest.log 2>&1
@@ -31,7 +31,7 @@ timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/$
 echo "reference arm rc=$?"; cut -c1-400 gpurun_out/${TAG}_bench_reference_N4000.json
 # ncu: launch list of the default bench command, then full captures of the dominant kernels
 # (cuSOLVER's syevd alone is > 400 launches and belongs to the set-up: list this library's kernels)
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:qcdmet --csv --log-file gpurun_out/${TAG}_launches_N4000.csv \
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k 'regex:jac_dmma|build_|split_transpose|gather_rows|dblocks|checksum|contract_|sum_subcolumns|zero_columns|bath_|embed_|rdm_diag' --csv --log-file gpurun_out/${TAG}_launches_N4000.csv \
   python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e --no-parity > gpurun_out/${TAG}_ncu_list.log 2>&1
 echo "ncu list rc=$?"
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:jac_dmma -s 1 -c 1 -f -o gpurun_out/${TAG}_prof_dmma_N4000 \
@@ -45,5 +45,3 @@ for wl in sn2 polyyne; do
     python bench.py --workload $wl --steps 2 --warmup 3 --no-cpu-baseline --no-e2e --no-parity > gpurun_out/${TAG}_ncu_contract_$wl.log 2>&1
   echo "ncu contract $wl rc=$?"
 done
-timeout 150 compute-sanitizer --tool memcheck python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${TAG}_sanitizer.log 2>&1
-echo "compute-sanitizer rc=$?"; tail -5 gpurun_out/${TAG}_sanitizer.log
