@@ -507,6 +507,13 @@ def test_resident_contraction_matches_chunked(shape, monkeypatch):
     again, *_ = run_plan(w, FACT, from_orbitals=(c, e), cols=cols)
     assert np.array_equal(got, again)                       # run-to-run bit-reproducible
     assert np.abs(got - ref).max() <= 1e-13 * max(1.0, np.abs(ref).max())
+    # both tile sizes of the resident kernel (64 row slots x 2 CTAs per SM / 128 slots) run the same arithmetic per
+    # accumulator: bit-identical to each other
+    for slots in ("64", "128"):
+        monkeypatch.setenv("QCDMET_B200_CONTRACT_SLOTS", slots)
+        other, *_ = run_plan(w, FACT, from_orbitals=(c, e), cols=cols)
+        assert np.array_equal(other, got), slots
+    monkeypatch.delenv("QCDMET_B200_CONTRACT_SLOTS")
     lo, hi = cols if cols else (0, w.nterms)
     sample = np.unique(np.linspace(lo, hi - 1, 12).astype(int))
     lens = w.h1start[sample + 1] - w.h1start[sample]
