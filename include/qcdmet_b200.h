@@ -250,6 +250,10 @@ long long qcdmet_plan_num_residuals(qcdmet_plan *plan);    /* Q                 
 int  qcdmet_plan_kernel_used(qcdmet_plan *plan);           /* QCDMET_KERNEL_GENERAL, _DMMA or _FACTORISED */
 int  qcdmet_plan_launches(qcdmet_plan *plan);              /* kernels launched by the last compute */
 int  qcdmet_plan_symmetric_used(qcdmet_plan *plan);        /* 1 if the last compute used the mirrored-patch mode */
+/* 1 if the last fused launch balanced the SMs at column-tile granularity (an item cut by a range boundary is finished by
+ * the CTA holding its first tiles, in tile order: results are bit-identical to the unsplit launch); $QCDMET_B200_SPLIT=0|1
+ * forces it off / on (tuning, tests). */
+int  qcdmet_plan_split_used(qcdmet_plan *plan);
 double qcdmet_plan_flops(qcdmet_plan *plan);               /* FP64 flops executed by the last compute */
 /* Device time of the dominant kernel of the last compute (CUDA events recorded on the plan
  * stream around that launch; synchronises the stream).  ms < 0 if nothing was computed. */

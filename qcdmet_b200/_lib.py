@@ -74,6 +74,7 @@ SIGNATURES = {
     "qcdmet_plan_kernel_used": (ctypes.c_int, [ctypes.c_void_p]),
     "qcdmet_plan_launches": (ctypes.c_int, [ctypes.c_void_p]),
     "qcdmet_plan_symmetric_used": (ctypes.c_int, [ctypes.c_void_p]),
+    "qcdmet_plan_split_used": (ctypes.c_int, [ctypes.c_void_p]),
     "qcdmet_plan_flops": (ctypes.c_double, [ctypes.c_void_p]),
     "qcdmet_plan_kernel_time_ms": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     "qcdmet_schedule_info": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
@@ -493,6 +494,10 @@ class Plan:
     @property
     def symmetric_used(self):
         return bool(self.lib.qcdmet_plan_symmetric_used(self.handle))
+
+    @property
+    def split_used(self):
+        return bool(self.lib.qcdmet_plan_split_used(self.handle))
 
     @property
     def launches(self):

@@ -1782,6 +1782,10 @@ int qcdmet_plan_launches(qcdmet_plan *p)
     return n;
 }
 int qcdmet_plan_symmetric_used(qcdmet_plan *p) { return p ? (p->symmetric_used ? 1 : 0) : -1; }
+int qcdmet_plan_split_used(qcdmet_plan *p)
+{
+    return p ? ((p->kernel_used == QCDMET_KERNEL_DMMA && dmma_last_launch_split(p->dmma)) ? 1 : 0) : -1;
+}
 double qcdmet_plan_flops(qcdmet_plan *p) { return p ? p->flops : -1.0; }
 const char *qcdmet_plan_info(qcdmet_plan *p) { return p ? p->info.c_str() : ""; }
 

@@ -128,6 +128,7 @@ int launch_jacobian_dmma(DmmaPlanData *d, const JacView &v, cudaStream_t st, int
                          double *flops, cudaEvent_t ev0, cudaEvent_t ev1, bool allowSym,
                          const PeerSet *peers);
 bool dmma_last_launch_symmetric(const DmmaPlanData *d);
+bool dmma_last_launch_split(const DmmaPlanData *d);      // tile-granular balancing (SPLIT kernel) was used
 bool dmma_plan_expanded(const DmmaPlanData *d);   // the list was split into per-cell sub-perturbations (TI)
 void dmma_schedule_info(int N, int no, int P, int F, const int *h1start, const int *h1row, const int *h1col,
                         const int *rowStart, const int *rowIdx, int *info, std::string *why);

@@ -135,6 +135,10 @@ struct DmmaArgs {
     double *Mout;
     int mRows, ldm;
     long long *prof;                    // PROF builds: [gridDim.x][8 warps][8] cycle counters
+    // SPLIT builds: a CTA owns a contiguous range of (item, column tile) units; an item cut by a range boundary is finished
+    // by the CTA that holds its first tiles, which adds the other CTA's per-tile contributions (ws) in tile order
+    double *ws;                         // [gridDim.x][nOt - 1][NS_DOUBLES]
+    unsigned int *flags;                // [gridDim.x] consumer warps of range r that have written their share of ws[r]
     int nDest;                          // destinations of every Jacobian store (1, or the ranks of a node)
     double *J[QCDMET_MAX_PEERS];        // J[0..nDest): own buffer and peer-mapped buffers (NVLink P2P stores)
 };
@@ -304,9 +308,11 @@ __global__ void sum_subcolumns_kernel(const double *__restrict__ Jsub, const int
 // PANEL = true: no epilogue, the M panels go to HBM (factorised path for large fragments, end of this file)
 // PROF = true (tuning builds only, $QCDMET_B200_PROFILE): every consumer warp adds up the clock cycles it spends
 // waiting for stages / in the stage bodies / waiting for epilogue operands / in the epilogue / in the assembly.
-template <class C, bool PANEL = false, bool PROF = false>
+// SPLIT = true: tile-granular balancing for sizes where nWork is not a multiple of the SM count (see launch_jacobian_dmma).
+template <class C, bool PANEL = false, bool PROF = false, bool SPLIT = false>
 __global__ void __launch_bounds__(NTHREADS, 1) jac_dmma_kernel(const DmmaArgs g)
 {
+    static_assert(!(PANEL && SPLIT), "panel mode has no running sums to split");
     constexpr int RF = C::RF, NJ = C::NJ, BN = C::BN, PSTRIDE = C::PSTRIDE, NSTRIDE = C::NSTRIDE;
     constexpr int W_STAGE = C::W_STAGE, STAGE_DOUBLES = C::STAGE_DOUBLES;
     constexpr int POS_DOUBLES = C::POS_DOUBLES, COS_DOUBLES = C::COS_DOUBLES;
@@ -346,9 +352,26 @@ __global__ void __launch_bounds__(NTHREADS, 1) jac_dmma_kernel(const DmmaArgs g)
             const int epiAt = nKc > 3 ? nKc - 3 : 0;      // prefetch the epilogue operands near the end of a tile
             int rs = 0, rph = 0, T = 0, k = 0;           // ring slot and phase of the next stage
             int2 wkNext = blockIdx.x < nWork ? g.work[blockIdx.x] : make_int2(0, 0);
-            for (int w = blockIdx.x; w < nWork; w += gridDim.x, ++k) {
-                const int comp = wkNext.x, tile = wkNext.y;
-                if (w + (int)gridDim.x < nWork) wkNext = g.work[w + gridDim.x];
+            // SPLIT: units [u, uEnd) of range r = gridDim.x - 1 - blockIdx.x (a CTA only ever waits for a lower-numbered CTA)
+            long long u = 0, uEnd = 0;
+            if constexpr (SPLIT) {
+                const long long units = (long long)nWork * nOt, r = gridDim.x - 1 - blockIdx.x;
+                u = units * r / gridDim.x;
+                uEnd = units * (r + 1) / gridDim.x;
+            }
+            for (int w = blockIdx.x; SPLIT ? u < uEnd : w < nWork; w += gridDim.x, ++k) {
+                int comp, tile, ota = 0, otb = nOt;
+                if constexpr (SPLIT) {
+                    const int item = (int)(u / nOt);
+                    ota = (int)(u % nOt);
+                    otb = (int)min((long long)nOt, ota + (uEnd - u));
+                    u += otb - ota;
+                    const int2 wk = g.work[item];
+                    comp = wk.x; tile = wk.y;
+                } else {
+                    comp = wkNext.x; tile = wkNext.y;
+                    if (w + (int)gridDim.x < nWork) wkNext = g.work[w + gridDim.x];
+                }
                 // item tables
                 const int tb = k % TABS;
                 mbar_wait(tabEmpty0 + 8 * tb, ((k / TABS) & 1) ^ 1);
@@ -361,7 +384,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) jac_dmma_kernel(const DmmaArgs g)
                 const double *cvsrc = g.CVt + (size_t)comp * nKc * CV_STAGE;
                 const double *posrc = g.POt + (size_t)tile * nOt * POS_DOUBLES;
                 const double *cosrc = g.COt + (size_t)comp * nOt * COS_DOUBLES;
-                for (int ot = 0; ot < nOt; ++ot, ++T) {
+                for (int ot = ota; ot < otb; ++ot, ++T) {
                     const double *wsrc = g.Wt + (size_t)ot * nKc * W_STAGE;
                     for (int kc = 0; kc < nKc; ++kc) {
                         if (!PANEL && kc == epiAt) {
@@ -393,9 +416,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) jac_dmma_kernel(const DmmaArgs g)
     // Assemble G_p of work item j from its running sums, symmetrise, store the item's patches of J.  Every
     // consumer thread owns the same share of the index space whenever it gets here: no CTA-wide barrier, only
     // "all eight warps have added their last column tile" (nsDone).
-    auto assemble = [&](int j, int tile) {
-        const int tbj = j % TABS, nbj = j % NSBUF;
-        mbar_wait(nsDone0 + 8 * nbj, (j / NSBUF) & 1);
+    auto assemble = [&](int j, int jn, int tile) {       // j: part (item tables), jn: its running-sum use; equal unless SPLIT
+        const int tbj = j % TABS, nbj = jn % NSBUF;
+        mbar_wait(nsDone0 + 8 * nbj, (jn / NSBUF) & 1);
         const unsigned char *tab = tabs + tbj * ITEM_TAB_BYTES;
         const long long *qrow = reinterpret_cast<const long long *>(tab + TT_QROW);
         const int *trow = reinterpret_cast<const int *>(tab + TT_TROW);
@@ -541,12 +564,32 @@ __global__ void __launch_bounds__(NTHREADS, 1) jac_dmma_kernel(const DmmaArgs g)
     };
     double acc[4][NJ][2];
     int rs = 0, rph = 0, T = 0, k = 0, prevTile = 0;
-    for (int w = blockIdx.x; w < nWork; w += gridDim.x, ++k) {
-        const int2 wk = g.work[w];
-        const int tb = k % TABS, nb = k % NSBUF;
+    // SPLIT: kn counts the parts that use a running-sum buffer (all but the tail part a range may start with), kPrev /
+    // knPrev name the part whose assembly is pending; otherwise kn == k and the names fold away
+    int kn = 0, kPrev = -1, knPrev = -1;
+    long long u = 0, uEnd = 0;
+    const int range = SPLIT ? (int)gridDim.x - 1 - (int)blockIdx.x : 0;
+    if constexpr (SPLIT) {
+        const long long units = (long long)nWork * nOt;
+        u = units * range / gridDim.x;
+        uEnd = units * (range + 1) / gridDim.x;
+    }
+    for (int w = blockIdx.x; SPLIT ? u < uEnd : w < nWork; w += gridDim.x, ++k) {
+        int item = w, ota = 0, otb = nOt;
+        if constexpr (SPLIT) {
+            item = (int)(u / nOt);
+            ota = (int)(u % nOt);
+            otb = (int)min((long long)nOt, ota + (uEnd - u));
+            u += otb - ota;
+        }
+        const bool tail = SPLIT && ota > 0;                  // the item's first tiles belong to the previous range's CTA
+        const bool head = SPLIT && ota == 0 && otb < nOt;    // the item's last tiles come from the next range's CTA
+        if constexpr (!SPLIT) kn = k;
+        const int2 wk = g.work[item];
+        const int tb = k % TABS, nb = kn % NSBUF;
         const unsigned char *tab = tabs + tb * ITEM_TAB_BYTES;
         double *NsK = Ns + nb * NS_DOUBLES;
-        for (int ot = 0; ot < nOt; ++ot, ++T) {
+        for (int ot = ota; ot < otb; ++ot, ++T) {
 #pragma unroll
             for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
@@ -605,18 +648,28 @@ __global__ void __launch_bounds__(NTHREADS, 1) jac_dmma_kernel(const DmmaArgs g)
                 continue;
             }
             // ---- epilogue for this column tile (per warp, no CTA-wide barrier)
-            if (ot == 0) {
+            if (ot == ota) {
                 mbar_wait(tabFull0 + 8 * tb, (k / TABS) & 1);                  // tables of this item
-                mbar_wait(nsFree0 + 8 * nb, ((k / NSBUF) & 1) ^ 1);            // every warp has assembled the buffer's last item
+                if (!tail) mbar_wait(nsFree0 + 8 * nb, ((kn / NSBUF) & 1) ^ 1);   // every warp has assembled the buffer's last item
             }
             mbar_wait(epiFull, T & 1);
             lap(2);
             const unsigned char *partner = tab + TT_PARTNER;
+            // where this tile's contribution goes: the item's running sums, or (tail part of a split item) its own slot
+            // of the workspace, from which the CTA that holds the item's first tiles adds it in tile order
+            double *nsTarget = NsK;
+            bool startSums = ot == 0;
+            if constexpr (SPLIT) {
+                if (tail) {
+                    nsTarget = g.ws + ((size_t)range * (nOt - 1) + (ot - ota)) * NS_DOUBLES;
+                    startSums = true;
+                }
+            }
 #pragma unroll
             for (int mi = 0; mi < 4; ++mi) {
                 const int a_slot = mi * 8 + g4;
                 const double *pc = CoS + warp_n * (BN / 2) + t4 * 2;
-                double *nsrow = NsK + (warp_n * 128 + warp_m * AT + a_slot) * NSTRIDE + t4 * RF;
+                double *nsrow = nsTarget + (warp_n * 128 + warp_m * AT + a_slot) * NSTRIDE + t4 * RF;
 #pragma unroll
                 for (int jh = 0; jh < RF / 4; ++jh) {            // partners in groups of 4 (register budget)
                     const double *pb[4];
@@ -661,7 +714,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) jac_dmma_kernel(const DmmaArgs g)
                     }
                     double2 *dst = reinterpret_cast<double2 *>(nsrow + jh * 4);
                     double2 s01 = make_double2(0.0, 0.0), s23 = make_double2(0.0, 0.0);
-                    if (ot > 0) { s01 = dst[0]; s23 = dst[1]; }      // the first column tile of an item starts the sums
+                    if (!startSums) { s01 = dst[0]; s23 = dst[1]; }  // the first column tile of an item starts the sums
                     s01.x += keep[0]; s01.y += keep[1]; s23.x += keep[2]; s23.y += keep[3];
                     dst[0] = s01; dst[1] = s23;
                 }
@@ -669,20 +722,65 @@ __global__ void __launch_bounds__(NTHREADS, 1) jac_dmma_kernel(const DmmaArgs g)
             __syncwarp();
             if (lane == 0) mbar_arrive(epiEmpty);
             lap(3);
-            if (NSBUF == 2 && ot == 0 && k > 0) { assemble(k - 1, prevTile); lap(4); }   // acc is dead here: no register pressure
+            if constexpr (SPLIT) {
+                if (NSBUF == 2 && ot == ota && kPrev >= 0) { assemble(kPrev, knPrev, prevTile); kPrev = -1; lap(4); }
+            } else {
+                if (NSBUF == 2 && ot == 0 && k > 0) { assemble(k - 1, k - 1, prevTile); lap(4); }   // acc is dead here: no register pressure
+            }
         }
         if constexpr (PANEL) {
             __syncwarp();
             if (lane == 0) mbar_arrive(tabEmpty0 + 8 * tb);
             continue;
         }
+        if constexpr (SPLIT) {
+            if (tail) {
+                // this warp's share of the tile contributions is in the workspace: publish, release the item tables
+                __threadfence();
+                __syncwarp();
+                if (lane == 0) {
+                    atomicAdd(g.flags + range, 1u);
+                    mbar_arrive(tabEmpty0 + 8 * tb);
+                }
+                continue;
+            }
+            if (head) {
+                // add the tiles the next range's CTA computed (it starts with them: they are long done), in tile order --
+                // the same association as an unsplit item
+                if (lane == 0) {
+                    unsigned int seen = 0;
+                    do {
+                        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(g.flags + range + 1) : "memory");
+                        if (seen < 8u) __nanosleep(200);
+                    } while (seen < 8u);
+                }
+                __syncwarp();
+                const int base = (warp_n * 128 + warp_m * AT) * NSTRIDE;
+                for (int t = 0; t < nOt - otb; ++t) {
+                    const double *src = g.ws + ((size_t)(range + 1) * (nOt - 1) + t) * NS_DOUBLES + base;
+                    for (int i = lane; i < AT * NSTRIDE; i += 32)
+                        if (i % NSTRIDE < RT * RF) NsK[base + i] += __ldcg(src + i);
+                }
+            }
+        }
         __syncwarp();
         if (lane == 0) mbar_arrive(nsDone0 + 8 * nb);       // this warp has added its last column tile of item k
-        if (NSBUF == 1) { assemble(k, wk.y); lap(4); }
+        if constexpr (SPLIT) {
+            if (NSBUF == 1) { assemble(k, kn, wk.y); lap(4); }
+            else { kPrev = k; knPrev = kn; }
+            ++kn;
+        } else {
+            if (NSBUF == 1) { assemble(k, k, wk.y); lap(4); }
+        }
         prevTile = wk.y;
     }
-    if constexpr (!PANEL)
-        if (NSBUF == 2 && k > 0) { assemble(k - 1, prevTile); lap(4); }
+    if constexpr (!PANEL) {
+        if constexpr (SPLIT) {
+            if (NSBUF == 2 && kPrev >= 0) { assemble(kPrev, knPrev, prevTile); lap(4); }
+        } else {
+            if (NSBUF == 2 && k > 0) { assemble(k - 1, k - 1, prevTile); lap(4); }
+        }
+    }
     if constexpr (PROF)
         if (lane == 0 && g.prof)
             for (int i = 0; i < 8; ++i) g.prof[((size_t)blockIdx.x * 8 + warp) * 8 + i] = pc[i];
@@ -726,6 +824,10 @@ struct DmmaPlanData {
     unsigned char *d_tileTab = nullptr, *d_compTab = nullptr;
     int numSMs = 0;                     // persistent grid: one CTA per SM of the plan's device
     int nP = 0, nTP = 0, maxE = 0;      // used perturbation slots per component / per tile (max), elements per perturbation (max)
+    double *d_ws = nullptr;             // tile-granular split (SPLIT kernel): per-CTA workspace of tile contributions
+    size_t wsCapacity = 0;
+    unsigned int *d_flags = nullptr;    // [numSMs]
+    bool launchSplit = false;
     int2 *d_work = nullptr;
     size_t workCapacity = 0;
     double *d_Wt = nullptr, *d_PVt = nullptr, *d_CVt = nullptr, *d_POt = nullptr, *d_COt = nullptr;
@@ -1059,7 +1161,7 @@ void dmma_plan_free(DmmaPlanData *d)
     if (!d) return;
     cudaFree(d->d_compSites); cudaFree(d->d_tileRow); cudaFree(d->d_tileTab); cudaFree(d->d_compTab); cudaFree(d->d_work);
     cudaFree(d->d_Wt); cudaFree(d->d_PVt); cudaFree(d->d_CVt); cudaFree(d->d_POt); cudaFree(d->d_COt);
-    cudaFree(d->d_emptyCols); cudaFree(d->d_subStart); cudaFree(d->d_Jsub);
+    cudaFree(d->d_emptyCols); cudaFree(d->d_subStart); cudaFree(d->d_Jsub); cudaFree(d->d_ws); cudaFree(d->d_flags);
     cudaGetLastError();
     delete d;
 }
@@ -1211,6 +1313,49 @@ int launch_jacobian_dmma(DmmaPlanData *d, const JacView &v, cudaStream_t st, int
         if (ev0) QC_CUDA(cudaEventRecord(ev0, st));
         // persistent CTAs, one per SM: CTA b executes items b, b + grid, ... (equal-cost items)
         const unsigned grid = (unsigned)std::min<size_t>(d->work.size(), (size_t)d->numSMs);
+        // Tile-granular balancing (SPLIT kernel).  With W items on G SMs the busiest CTA executes ceil(W / G) items; when W
+        // is not a multiple of G that is up to one item too many (N = 576: 10 for 9.24).  The SPLIT instantiation gives every
+        // CTA a contiguous range of (item, column tile) units instead -- ceil(W nOt / G) tiles -- and an item cut by a range
+        // boundary is completed by the CTA holding its first tiles, which adds the other CTA's per-tile contributions in
+        // tile order: the same association as an unsplit item, so results stay bit-identical to the unsplit kernel and
+        // independent of G.  Used when it removes at least 4 % of the busiest CTA's work (measured: 4.1 % of the kernel time at
+        // N = 576 for an expected 6.7 %; nothing at N = 1000 for an expected 2.7 %) and the operand panels are small
+        // enough to stay in L2 whatever the order (contiguous ranges give up the tile-sharing order of the strided list).
+        bool split = false;
+        {
+            const long long W = (long long)d->work.size(), G = grid, nOt = d->nOt;
+            const char *env = getenv("QCDMET_B200_SPLIT");
+            const size_t footprint = ((size_t)d->nOt * d->nKc * d->wStage() + (size_t)d->nTiles * d->nKc * PV_STAGE +
+                                      (size_t)d->nComp * d->nKc * CV_STAGE + (size_t)d->nTiles * d->nOt * d->posDoubles() +
+                                      (size_t)d->nComp * d->nOt * d->cosDoubles()) * 8;
+            if (G == d->numSMs && nOt >= 2 && nOt <= 8 && W % G != 0 && !(env && env[0] == '0')) {
+                const long long before = ((W + G - 1) / G) * nOt, after = (W * nOt + G - 1) / G;
+                split = (W * nOt) / G >= 2 * nOt && after * 100 <= before * 96 && footprint <= ((size_t)48 << 20);
+            }
+            if (env && env[0] == '1' && G == d->numSMs && nOt >= 2 && (W * nOt) / G >= 2 * nOt) split = true;   // forced (tests)
+        }
+        if (split) {
+            const size_t nsDoubles = (size_t)2 * 128 * (RT * d->rf + 2);
+            const size_t need = (size_t)grid * (d->nOt - 1) * nsDoubles;
+            if (need > d->wsCapacity) {
+                cudaFree(d->d_ws);
+                d->d_ws = nullptr;
+                d->wsCapacity = 0;
+                if (cudaMalloc((void **)&d->d_ws, need * sizeof(double)) != cudaSuccess) {
+                    cudaGetLastError();
+                    split = false;                               // no room: the unsplit kernel needs no workspace
+                } else d->wsCapacity = need;
+            }
+            if (split && !d->d_flags && cudaMalloc((void **)&d->d_flags, (size_t)d->numSMs * sizeof(unsigned int)) != cudaSuccess) {
+                cudaGetLastError();
+                d->d_flags = nullptr;
+                split = false;
+            }
+            if (split) QC_CUDA(cudaMemsetAsync(d->d_flags, 0, (size_t)d->numSMs * sizeof(unsigned int), st));
+        }
+        d->launchSplit = split;
+        a.ws = d->d_ws;
+        a.flags = d->d_flags;
         int rc = QCDMET_E_STATE;
 #define QC_LAUNCH_VARIANT(RFV, NJV)                                                                           \
         if (d->rf == RFV && d->nj == NJV) {                                                                   \
@@ -1224,6 +1369,10 @@ int launch_jacobian_dmma(DmmaPlanData *d, const JacView &v, cudaStream_t st, int
                 QC_CUDA(cudaFuncSetAttribute(jac_dmma_kernel<Cfg<4, (NJV >= 6 ? NJV : 6)>, false, true>,      \
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM_BYTES));    \
                 jac_dmma_kernel<Cfg<4, (NJV >= 6 ? NJV : 6)>, false, true><<<grid, NTHREADS, K::SMEM_BYTES, st>>>(a); \
+            } else if (split) {                                                                               \
+                QC_CUDA(cudaFuncSetAttribute(jac_dmma_kernel<K, false, false, true>,                          \
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM_BYTES));    \
+                jac_dmma_kernel<K, false, false, true><<<grid, NTHREADS, K::SMEM_BYTES, st>>>(a);             \
             } else                                                                                            \
                 jac_dmma_kernel<K><<<grid, NTHREADS, K::SMEM_BYTES, st>>>(a);                                 \
             rc = QCDMET_OK;                                                                                   \
@@ -1271,6 +1420,7 @@ int launch_jacobian_dmma(DmmaPlanData *d, const JacView &v, cudaStream_t st, int
 }
 
 bool dmma_last_launch_symmetric(const DmmaPlanData *d) { return d && d->launchSym; }
+bool dmma_last_launch_split(const DmmaPlanData *d) { return d && d->launchSplit; }
 bool dmma_plan_expanded(const DmmaPlanData *d) { return d && d->expanded; }
 
 // Host-only description of the schedule the DMMA kernel would use (no device needed): tests and tooling.
@@ -1471,6 +1621,7 @@ int launch_jacobian_factorised(FactPlanData *f, const JacView &v, long long nnzI
         a.tileTab = d->d_tileTab; a.compTab = d->d_compTab;
         a.Mout = f->d_M; a.mRows = v.S; a.ldm = v.ldo;
         a.prof = nullptr;
+        a.ws = nullptr; a.flags = nullptr;
         a.nDest = 0;
         const unsigned grid = (unsigned)std::min<size_t>(d->work.size(), (size_t)d->numSMs);
         int rc = QCDMET_E_STATE;

@@ -523,6 +523,40 @@ def test_resident_contraction_matches_chunked(shape, monkeypatch):
     assert np.abs(got[:, sample - lo] - orc).max() <= TOL
 
 
+@pytest.mark.parametrize("shape", ["sweep400", "sweep576", "hubbard24_bath", "sweep1000"])
+def test_tile_split_balancing_is_bit_identical(shape, monkeypatch):
+    """When the block-pair list is not a multiple of the SM count the fused kernel balances the SMs at column-tile
+    granularity (SPLIT instantiation: an item cut by a range boundary is finished by the CTA holding its first tiles,
+    which adds the other CTA's per-tile contributions in tile order).  Same association as the unsplit item: bit-identical
+    Jacobians, whatever the split."""
+    w = {"sweep400": lambda: wl.sweep(400), "sweep576": lambda: wl.sweep(576),
+         "hubbard24_bath": lambda: wl.hubbard24(fit_imp_bath=True, l=24),       # 8-row fragments: one running-sum buffer
+         "sweep1000": lambda: wl.sweep(1000)}[shape]()
+    e, c = ro.eigh_sorted(w.h0)
+    out = {}
+    for flag in ("0", "1"):
+        monkeypatch.setenv("QCDMET_B200_SPLIT", flag)
+        plan = _lib.Plan(w.norb, w.num_pairs, w.h1start, w.h1row, w.h1col, w.row_start, w.rows, w.row_idx)
+        plan.set_orbitals(c, e)
+        plan.compute()
+        out[flag] = (plan.jacobian(), plan.split_used, plan.kernel_used)
+        again = None
+        if flag == "1":
+            plan.compute()
+            again = plan.jacobian()
+            assert np.array_equal(again, out[flag][0])          # bit-reproducible run to run
+        plan.close()
+    assert out["0"][2] == _lib.KERNEL_DMMA and not out["0"][1]
+    assert out["1"][1], "the split instantiation did not run"
+    assert np.array_equal(out["0"][0], out["1"][0])
+    sample = np.unique(np.linspace(0, w.nterms - 1, 6).astype(int))
+    lens = w.h1start[sample + 1] - w.h1start[sample]
+    hs = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    take = np.concatenate([np.arange(w.h1start[p], w.h1start[p + 1]) for p in sample])
+    orc = ro.jacobian_from_orbitals(c, e, w.num_pairs, hs, w.h1row[take], w.h1col[take], w.row_start, w.rows, w.row_idx)
+    assert np.abs(out["1"][0][:, sample] - orc).max() <= TOL
+
+
 def test_invariants_large():
     """Size-independent properties at a size the CPU oracle does not reach in seconds."""
     w = wl.sweep(1000, nterms=600)
