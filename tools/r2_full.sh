@@ -2,7 +2,7 @@
 # round-2 full check on one GPU: smoke, whole GPU suite, bench lines of every shape, ncu launch list + captures
 set -u
 mkdir -p gpurun_out
-TAG=${TAG:-r2t}
+TAG=${TAG:-r2x}
 timeout 180 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${TAG}_smoke.log 2>&1
 echo "smoke rc=$?"; tail -3 gpurun_out/${TAG}_smoke.log
 timeout 1500 python -m pytest tests -m gpu -q --tb=short --durations=12 > gpurun_out/${TAG}_pytest.log 2>&1
@@ -34,13 +34,15 @@ echo "reference arm rc=$?"; cut -c1-400 gpurun_out/${TAG}_bench_reference_N4000.
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k 'regex:jac_dmma|build_|split_transpose|gather_rows|dblocks|checksum|contract_|sum_subcolumns|zero_columns|bath_|embed_|rdm_diag' --csv --log-file gpurun_out/${TAG}_launches_N4000.csv \
   python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e --no-parity > gpurun_out/${TAG}_ncu_list.log 2>&1
 echo "ncu list rc=$?"
+if [ "${NCU_ALL:-0}" = "1" ]; then
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:jac_dmma -s 1 -c 1 -f -o gpurun_out/${TAG}_prof_dmma_N4000 \
   python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e --no-parity > gpurun_out/${TAG}_ncu_N4000.log 2>&1
 echo "ncu N4000 rc=$?"
+fi
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:jac_dmma -s 3 -c 1 -f -o gpurun_out/${TAG}_prof_dmma_hubbard24 \
   python bench.py --workload hubbard24 --steps 2 --warmup 3 --no-cpu-baseline --no-e2e --no-parity > gpurun_out/${TAG}_ncu_h24.log 2>&1
 echo "ncu hubbard24 rc=$?"
-for wl in sn2 polyyne; do
+[ "${NCU_ALL:-0}" = "1" ] && for wl in sn2 polyyne; do
   timeout 300 ncu --set full --clock-control none --import-source on -k regex:contract_resident -s 3 -c 1 -f -o gpurun_out/${TAG}_prof_contract_$wl \
     python bench.py --workload $wl --steps 2 --warmup 3 --no-cpu-baseline --no-e2e --no-parity > gpurun_out/${TAG}_ncu_contract_$wl.log 2>&1
   echo "ncu contract $wl rc=$?"
