@@ -557,6 +557,23 @@ def test_tile_split_balancing_is_bit_identical(shape, monkeypatch):
     assert np.abs(out["1"][0][:, sample] - orc).max() <= TOL
 
 
+def test_pageable_and_page_locked_host_copies_agree():
+    """A fresh (pageable) numpy destination of more than 128 MB takes the pipelined staged copy (two page-locked 32 MB
+    buffers + host threads), a page-locked destination the direct copy: same bytes."""
+    w = wl.sweep(1600)
+    plan = _lib.Plan(w.norb, w.num_pairs, w.h1start, w.h1row, w.h1col, w.row_start, w.rows, w.row_idx)
+    plan.set_h0(w.h0)
+    plan.compute()
+    assert w.nresid * w.nterms * 8 > 4 * (32 << 20)
+    fresh = plan.jacobian()                                   # new pageable array
+    pinned = plan.jacobian(pinned=True)                       # the plan's page-locked buffer
+    assert fresh.shape == pinned.shape == (w.nresid, w.nterms)
+    assert np.array_equal(fresh, pinned)
+    part = plan.jacobian_columns(1234, 3999)                  # odd offsets, still above the threshold
+    assert np.array_equal(part, pinned[:, 1234:3999])
+    plan.close()
+
+
 def test_invariants_large():
     """Size-independent properties at a size the CPU oracle does not reach in seconds."""
     w = wl.sweep(1000, nterms=600)
