@@ -497,11 +497,17 @@ int staged_d2h(qcdmet_plan *p, double *dst, const double *src, size_t bytes)
         const char *from = (const char *)p->h_stage[k & 1];
         char *to = (char *)dst + off;
         std::vector<std::thread> th;
+        size_t done = len / nthreads;                   // [0, done) is this thread's share
         for (int t = 1; t < nthreads; ++t) {
             const size_t b = len * t / nthreads, e = len * (t + 1) / nthreads;
-            th.emplace_back([=]() { memcpy(to + b, from + b, e - b); });
+            try {
+                th.emplace_back([=]() { memcpy(to + b, from + b, e - b); });
+            } catch (...) {                             // no more threads: this thread copies the rest
+                memcpy(to + b, from + b, len - b);
+                break;
+            }
         }
-        memcpy(to, from, len / nthreads);
+        memcpy(to, from, done);
         for (std::thread &x : th) x.join();
     };
     for (size_t k = 0; k < nchunks; ++k) {
@@ -1598,13 +1604,21 @@ int qcdmet_plan_get_jacobian_columns(qcdmet_plan *p, int c0, int c1, double *J)
             }
             if (hi <= lo) continue;
             double *dst = J + (size_t)p->Q * (lo - p->colBegin - c0);
-            th.emplace_back([q, lo, hi, dst, &rcs, m]() {
+            auto ship = [q, lo, hi, dst, &rcs, m]() {
                 if (cudaSetDevice(q->device) != cudaSuccess ||
                     cudaStreamSynchronize(q->stream) != cudaSuccess ||
                     cudaMemcpy(dst, q->d_J + (size_t)q->Q * lo, sizeof(double) * (size_t)q->Q * (hi - lo),
                                cudaMemcpyDeviceToHost) != cudaSuccess)
                     rcs[m] = QCDMET_E_CUDA;
-            });
+            };
+            try {
+                th.emplace_back(ship);
+            } catch (...) {                             // no thread to be had: copy this share from the caller thread
+                int prev = 0;
+                cudaGetDevice(&prev);
+                ship();
+                cudaSetDevice(prev);
+            }
         }
         for (std::thread &t : th) t.join();
         for (int m = 0; m < n; ++m)
