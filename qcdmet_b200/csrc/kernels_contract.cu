@@ -170,7 +170,7 @@ void contract_schedule_build(int F, const int *rowStart, ContractSchedule *out, 
 namespace {
 // One strip over the k-steps of a staged chunk: block b1 against N2 consecutive blocks b2.
 // D[b1,b2] += Y[b1] PO[b2]^T + PO[b1] Y[b2]^T; the two products of a pair are issued N2 DMMAs apart.
-template <int N2, int LD = CLD, bool SPLIT = false>
+template <int N2, int LD = CLD, bool SPLIT = false, int UNROLL = 2>
 __device__ __forceinline__ void strip_steps(double (&acc)[CMAXN2][2], const double *__restrict__ ya,
                                             const double *__restrict__ pa, const double *__restrict__ yb,
                                             const double *__restrict__ pb, int nk)
@@ -182,7 +182,7 @@ __device__ __forceinline__ void strip_steps(double (&acc)[CMAXN2][2], const doub
 #pragma unroll
         for (int j = 0; j < N2; ++j) c2[j][0] = c2[j][1] = 0.0;
     }
-#pragma unroll 2
+#pragma unroll UNROLL
     for (int kk = 0; kk < nk; ++kk) {
         const double aY = ya[4 * kk], aP = pa[4 * kk];
         double bP[N2], bY[N2];
@@ -508,10 +508,10 @@ contract_resident_kernel(const JacView v, const double *__restrict__ M, const in
             if (sw[s] < 0) continue;                 // warp-uniform
             const double *ya = Ys + offA[s], *pa = Ps + offA[s], *yb = Ys + offB[s], *pb = Ps + offB[s];
             switch (sw[s] >> 16) {                   // warp-uniform
-            case 4: strip_steps<4, RLD, true>(acc[s], ya, pa, yb, pb, nk); break;
-            case 3: strip_steps<3, RLD, true>(acc[s], ya, pa, yb, pb, nk); break;
-            case 2: strip_steps<2, RLD, true>(acc[s], ya, pa, yb, pb, nk); break;
-            default: strip_steps<1, RLD, true>(acc[s], ya, pa, yb, pb, nk); break;
+            case 4: strip_steps<4, RLD, true, 8>(acc[s], ya, pa, yb, pb, nk); break;
+            case 3: strip_steps<3, RLD, true, 8>(acc[s], ya, pa, yb, pb, nk); break;
+            case 2: strip_steps<2, RLD, true, 8>(acc[s], ya, pa, yb, pb, nk); break;
+            default: strip_steps<1, RLD, true, 8>(acc[s], ya, pa, yb, pb, nk); break;
             }
         }
         // (E) J[a,b] and J[b,a] from the same register, then restart the sums
