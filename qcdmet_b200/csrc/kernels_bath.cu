@@ -254,7 +254,6 @@ namespace {
 
 constexpr int EMB_THREADS = 256;
 constexpr int EMB_XCH = 128;            // lattice orbitals per staged chunk
-constexpr int EMB_MAXB = 8;             // bath orbitals per fragment for which the two-electron block is built
 
 __global__ void rdm_diag_kernel(const double *__restrict__ CoT, int ldo, int no, int N, double *__restrict__ ddiag)
 {

@@ -23,7 +23,6 @@ namespace qcdmet {
 namespace {
 constexpr int CB8 = 8;                 // rows per block
 constexpr int CMAXB = 16;              // blocks per tile
-constexpr int CSLICE = 8;              // blocks per slice of a large fragment
 constexpr int CSLOTS = CB8 * CMAXB;    // row slots per tile
 constexpr int CNT = 256;               // threads per CTA
 constexpr int CWARPS = CNT / 32;

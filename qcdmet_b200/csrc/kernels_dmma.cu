@@ -180,10 +180,6 @@ __device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void *src, uint
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
-__device__ __forceinline__ void consumer_sync()
-{
-    asm volatile("bar.sync 1, %0;" ::"n"(NCONS) : "memory");
-}
 __device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double b)
 {
     asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
