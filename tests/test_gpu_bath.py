@@ -283,3 +283,58 @@ def test_dmet_loop_with_device_embedding(case):
     assert dev.iterations == ref.iterations
     assert abs(e_dev - e_ref) <= 1e-8
     assert np.abs(dev.umat - ref.umat).max() <= 1e-7
+
+
+def oracle_embedding_problem():
+    """Disordered chain: no degenerate occupations, so every bath orbital is unique up to its sign."""
+    n, num_pairs, u = 20, 10, 3.0
+    rng = np.random.default_rng(5)
+    noise = 0.3 * rng.standard_normal((n, n))
+    hop = lh.hubbard_chain(n) + 0.5 * (noise + noise.T)
+    h0 = hop + np.diag(0.5 * rng.standard_normal(n))
+    imp_start = np.array([0, 2, 7], dtype=np.int32)
+    imp_idx = np.array([3, 4, 10, 11, 12, 15, 17], dtype=np.int32)
+    return n, num_pairs, u, hop, h0, imp_start, imp_idx
+
+
+def check_embedding_against_bath_oracle(emb, one, n, u, hop, imp_start, imp_idx):
+    """emb: what Plan.embed_hubbard returns.  Everything is recomputed by oracle/bath_oracle.py from the 1-RDM alone
+    (the reference's route: eigh of the environment block, src/qcdmethelper.py:124-168; src/dmet.py:204-226;
+    src/localintegrals_hubbard.py:84-116) and compared after fixing the sign of each bath orbital."""
+    from oracle import bath_oracle as bo
+    for f in range(len(imp_start) - 1):
+        idx = imp_idx[imp_start[f]:imp_start[f + 1]]
+        m = idx.size
+        flags = np.zeros(n, dtype=int)
+        flags[idx] = 1
+        nb, loc2dmet, core = bo.construct_bath(one, flags, m)
+        assert nb == emb["num_bath"][f]
+        act = m + nb
+        got = emb["bath"][imp_start[f]:imp_start[f] + nb].T
+        ref = loc2dmet[:, m:act]
+        dots = np.sum(got * ref, axis=0)
+        assert np.abs(np.abs(dots) - 1.0).max() <= 1e-10
+        sv = np.concatenate([np.ones(m), np.sign(dots)])
+        assert np.abs(got * sv[m:] - ref).max() <= 1e-9
+        occ_ref = np.diag(ref.T @ one @ ref)
+        assert np.abs(emb["occ"][imp_start[f]:imp_start[f] + nb] - occ_ref).max() <= 1e-10
+        core_dm, _ = bo.core_density(loc2dmet, core)
+        s2 = np.outer(sv, sv)
+        assert np.abs(emb["oei"][f] * s2 - bo.embedded_oei(hop, loc2dmet, act)).max() <= 1e-10
+        assert np.abs(emb["fock"][f] * s2 - bo.embedded_fock(hop, u, loc2dmet, act, core_dm)).max() <= 1e-10
+        s4 = np.einsum("a,b,c,d->abcd", sv, sv, sv, sv)
+        assert np.abs(emb["tei"][f] * s4 - bo.embedded_tei(u, loc2dmet, act)).max() <= 1e-10
+        assert abs(emb["core_electrons"][f] - np.trace(core_dm)) <= 1e-9
+
+
+def test_device_embedding_matches_bath_oracle_end_to_end():
+    """Baths, occupations and embedded oei / fock / tei of the device path against the independent CPU checker that
+    follows the reference's own route from the 1-RDM (no quantity of the device path enters the checker's side)."""
+    n, num_pairs, u, hop, h0, imp_start, imp_idx = oracle_embedding_problem()
+    plan = plan_for(h0, num_pairs, imp_start, imp_idx)
+    emb = plan.embed_hubbard(hop, u, imp_start, imp_idx)
+    one = plan.one_rdm()
+    e, c = np.linalg.eigh(h0)
+    assert np.abs(one - 2.0 * c[:, :num_pairs] @ c[:, :num_pairs].T).max() <= 1e-12
+    check_embedding_against_bath_oracle(emb, one, n, u, hop, imp_start, imp_idx)
+    plan.close()
